@@ -1,0 +1,438 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the MV3D per-frame hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (mv3d_tf_b200) never does.
+
+Every function restates a piece of the reference (leeyevi/MV3D_TF @ 4e1bb30) and cites the
+file:line it follows (paths relative to the reference root).  Scalar loops live in
+oracle/oracle_c.c (gcc); everything here is numpy with the reference's dtypes.
+
+PARITY PIN: tests/test_oracle_vs_reference.py runs the reference's own sources (through
+oracle/ref_shim.py, mechanical py2->py3 patches only) against these functions on seeded inputs
+in the dev container, and tests/golden/*.npz (made by tests/golden/make_golden.py from the
+*reference*, not from this file) pin them wherever the reference tree is absent.
+The TensorFlow part of the path (conv / fc / softmax) cannot run here (TF 1.0, unpinned,
+not installable): oracle/net_oracle.py restates it in torch-CPU fp32 -- parity UNPINNED there.
+
+Generalisation beyond the reference: `BevGeometry` parameterises the BEV extent.  With the
+default (0..60 m, -30..30 m, 0.1 m) every function is the reference's arithmetic verbatim;
+other extents use the de-swapped Xn/Yn form (SURVEY.md section 8a note) which is identical on
+the square reference grid.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle_c.so")
+        if not os.path.exists(path):
+            from . import build as _b  # type: ignore
+
+            path = _b.build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_nms.restype = ctypes.c_int
+        _LIB.orc_nms_new.restype = ctypes.c_int
+    return _LIB
+
+
+def _p(a, t=ctypes.c_void_p):
+    return a.ctypes.data_as(t)
+
+
+# ----------------------------------------------------------------------------------------
+# geometry constants  (lib/utils/transform.py:3-11)
+# ----------------------------------------------------------------------------------------
+LIDAR_HEIGHT = 1.73
+CAR_HEIGHT = 1.56
+
+
+@dataclass(frozen=True)
+class BevGeometry:
+    """BEV extent.  Defaults = lib/utils/transform.py:3-7 (the only extent the reference has)."""
+
+    x_min: float = 0
+    x_max: float = 60
+    y_min: float = -30
+    y_max: float = 30
+    res: float = 0.1
+
+    @property
+    def xn(self) -> int:  # transform.py:10  (note 60 // 0.1 == 599.0 -> 600)
+        return int((self.x_max - self.x_min) // self.res) + 1
+
+    @property
+    def yn(self) -> int:  # transform.py:11
+        return int((self.y_max - self.y_min) // self.res) + 1
+
+
+REF_GEOMETRY = BevGeometry()
+CFG_GEOMETRY = BevGeometry(0, 70, -40, 40, 0.1)  # BASELINE.json 700x800 grid
+
+
+# ----------------------------------------------------------------------------------------
+# a1. BEV raster  (tools/read_lidar.py:10-115)
+# ----------------------------------------------------------------------------------------
+def raster_params(res, zres, side_range, fwd_range, height_range):
+    """Host-side scalars of point_cloud_2_top (read_lidar.py:49-53,80,102-103), computed with the
+    same Python/numpy expressions as the reference so every rounding matches."""
+    x_max = int((side_range[1] - side_range[0]) / res)
+    y_max = int((fwd_range[1] - fwd_range[0]) / res)
+    z_max = int((height_range[1] - height_range[0]) / zres)
+    heights = np.arange(height_range[0], height_range[1], zres)  # float64 slice lower bounds
+    lo = np.asarray(heights, dtype=np.float64)
+    hi = np.asarray([h + zres for h in heights], dtype=np.float64)
+    xoff = int(np.floor(side_range[0] / res))
+    yoff = int(np.floor(fwd_range[1] / res))
+    return dict(H=y_max + 1, W=x_max + 1, C=z_max + 1, nslices=len(heights), lo=lo, hi=hi, xoff=xoff, yoff=yoff)
+
+
+def point_cloud_2_top(points, res=0.1, zres=0.3, side_range=(-10.0, 10.0), fwd_range=(-10.0, 10.0),
+                      height_range=(-2.0, 2.0)):
+    """tools/read_lidar.py:10-115 -- same signature, same (H,W,C) float32 result."""
+    prm = raster_params(res, zres, side_range, fwd_range, height_range)
+    pts = np.ascontiguousarray(points[:, :4], dtype=np.float32)
+    top = np.empty((prm["H"], prm["W"], prm["C"]), dtype=np.float32)
+    f = ctypes.c_float
+    _lib().orc_raster(_p(pts), ctypes.c_int(pts.shape[0]), ctypes.c_int(prm["H"]), ctypes.c_int(prm["W"]),
+                      ctypes.c_int(prm["C"]), ctypes.c_int(prm["nslices"]), _p(prm["lo"]), _p(prm["hi"]),
+                      f(res), f(fwd_range[0]), f(fwd_range[1]), f(side_range[0]), f(side_range[1]),
+                      f(height_range[0]), ctypes.c_int(prm["xoff"]), ctypes.c_int(prm["yoff"]), _p(top))
+    return top
+
+
+# ----------------------------------------------------------------------------------------
+# a4. anchors  (lib/rpn_msr/generate_anchors.py:37-51, proposal_layer_tf.py:79-95)
+# ----------------------------------------------------------------------------------------
+def generate_anchors_bv(base_size=((3.9, 1.6), (1.0, 0.6)), res=0.1):
+    """generate_anchors.py:37-51: integer (x1,y1,x2,y2) windows, each base plus its transpose."""
+    rows = []
+    for length, width in base_size:
+        bl, bw = int(length / res), int(width / res)
+        rows.append([-(bl // 2), -(bw // 2), bl - bl // 2, bw - bw // 2])
+    base = np.asarray(rows, dtype=np.int64)
+    return np.vstack((base, base[:, [1, 0, 3, 2]]))
+
+
+def enumerate_anchors(height, width, feat_stride=8, base=None):
+    """proposal_layer_tf.py:79-95 / anchor_target_layer_tf.py:76-89: (H*W*A, 4) int64, order (h, w, a)."""
+    base = generate_anchors_bv() if base is None else base
+    sx = np.arange(width, dtype=np.int64) * feat_stride
+    sy = np.arange(height, dtype=np.int64) * feat_stride
+    shifts = np.stack(np.broadcast_arrays(sx[None, :], sy[:, None], sx[None, :], sy[:, None]), axis=-1)
+    return (shifts.reshape(-1, 1, 4) + base[None, :, :]).reshape(-1, 4)
+
+
+# ----------------------------------------------------------------------------------------
+# a5-a8. box geometry
+# ----------------------------------------------------------------------------------------
+def bv_anchor_to_lidar(anchors, geom: BevGeometry = REF_GEOMETRY):
+    """transform.py:89-111 with _bv_to_lidar_coords :81-87.  float64 result (z, h columns hold
+    float32-valued constants).  The reference multiplies bv x by Xn and bv y by Yn (swapped);
+    on its square grid both are 600.  Other grids use the consistent pairing."""
+    a = anchors
+    length = ((a[:, 3] - a[:, 1]).reshape(-1, 1)) * geom.res
+    width = ((a[:, 2] - a[:, 0]).reshape(-1, 1)) * geom.res
+    cx = ((a[:, 0] + a[:, 2]) / 2.0).reshape(-1, 1)
+    cy = ((a[:, 1] + a[:, 3]) / 2.0).reshape(-1, 1)
+    n_for_bvx, n_for_bvy = (geom.xn, geom.yn) if geom == REF_GEOMETRY else (geom.yn, geom.xn)
+    y = n_for_bvx * geom.res - (cx + 0.5) * geom.res + geom.y_min
+    x = n_for_bvy * geom.res - (cy + 0.5) * geom.res + geom.x_min
+    n = a.shape[0]
+    h = np.ones((n, 1), dtype=np.float32) * CAR_HEIGHT
+    z = np.ones((n, 1), dtype=np.float32) * -(LIDAR_HEIGHT - CAR_HEIGHT / 2.0)
+    return np.hstack((x, y, z, length, width, h))
+
+
+def bbox_transform_inv_3d(boxes, deltas):
+    """bbox_transform.py:108-155 (single class): float32, separate mul and add roundings."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, deltas.shape[1]), dtype=deltas.dtype)
+    b = boxes.astype(deltas.dtype, copy=False)
+    out = np.zeros(deltas.shape, dtype=deltas.dtype)
+    for k in range(3):  # x uses l, y uses w, z uses h  (:131-133)
+        out[:, k] = deltas[:, k] * b[:, 3 + k] + b[:, k]
+        out[:, 3 + k] = np.exp(deltas[:, 3 + k]) * b[:, 3 + k]
+    return out
+
+
+def bbox_transform_3d(ex, gt):
+    """bbox_transform.py:32-58: note x is normalised by WIDTH and y by LENGTH (asymmetric to the inverse)."""
+    dx = (gt[:, 0] - ex[:, 0]) / ex[:, 4]
+    dy = (gt[:, 1] - ex[:, 1]) / ex[:, 3]
+    dz = (gt[:, 2] - ex[:, 2]) / ex[:, 5]
+    dl = np.log(gt[:, 3] / ex[:, 3])
+    dw = np.log(gt[:, 4] / ex[:, 4])
+    dh = np.log(gt[:, 5] / ex[:, 5])
+    return np.vstack((dx, dy, dz, dl, dw, dh)).transpose()
+
+
+def lidar_to_bv_coord(x, y, geom: BevGeometry = REF_GEOMETRY):
+    """transform.py:13-20.  `//` here is numpy's float64 floor-division (npy_divmod)."""
+    xx = geom.yn - (y - geom.y_min) // geom.res
+    yy = geom.xn - (x - geom.x_min) // geom.res
+    return xx, yy
+
+
+def lidar_3d_to_bv(rois_3d, geom: BevGeometry = REF_GEOMETRY):
+    """transform.py:113-142 (2-D branch): f32 corner sums stored to f64, `//`, cast f32."""
+    r = np.zeros((rois_3d.shape[0], 4))
+    r[:, 0] = rois_3d[:, 0] + rois_3d[:, 3] * 0.5
+    r[:, 1] = rois_3d[:, 1] + rois_3d[:, 4] * 0.5
+    r[:, 2] = rois_3d[:, 0] - rois_3d[:, 3] * 0.5
+    r[:, 3] = rois_3d[:, 1] - rois_3d[:, 4] * 0.5
+    x1, y1 = lidar_to_bv_coord(r[:, 0], r[:, 1], geom)
+    x2, y2 = lidar_to_bv_coord(r[:, 2], r[:, 3], geom)
+    return np.stack((x1, y1, x2, y2), axis=1).astype(np.float32)
+
+
+_SX = np.array([1, 1, -1, -1, 1, 1, -1, -1])
+_SY = np.array([1, -1, -1, 1, 1, -1, -1, 1])
+_SZ = np.array([-1, -1, -1, -1, 1, 1, 1, 1])
+
+
+def lidar_3d_to_corners(p):
+    """transform.py:290-315: (N,24) [x0..7, y0..7, z0..7], dtype of the input (f32 on the hot path).
+    +-(v/2.) then + centre, two roundings, as the reference."""
+    dt = p.dtype
+    hl, hw, hh = (p[:, 3:4] / 2.0), (p[:, 4:5] / 2.0), (p[:, 5:6] / 2.0)
+    xs = np.where(_SX > 0, hl, -hl).astype(dt) + p[:, 0:1]
+    ys = np.where(_SY > 0, hw, -hw).astype(dt) + p[:, 1:2]
+    zs = np.where(_SZ > 0, hh, -hh).astype(dt) + p[:, 2:3]
+    return np.hstack((xs, ys, zs)).astype(dt, copy=False)
+
+
+def projection_matrix(Tr, R0, P2):
+    """transform.py:371-384: mat2 = (P2 . R0[4x3]) . Tr, evaluated in the dtype the arrays arrive in
+    (float32 at the py_func boundary, MV3D_test.py:18)."""
+    Tr = np.asarray(Tr).reshape(3, 4)
+    R0 = np.asarray(R0).reshape(4, 3)
+    P2 = np.asarray(P2).reshape(3, 4)
+    return np.dot(np.dot(P2, R0), Tr)
+
+
+def lidar_cnr_to_img(corners, Tr, R0, P2):
+    """transform.py:483-500 (the live, second definition) -> (N,4) int32 [xmin,ymin,xmax,ymax]."""
+    M = np.ascontiguousarray(projection_matrix(Tr, R0, P2), dtype=np.float32)
+    c = np.ascontiguousarray(corners, dtype=np.float32)
+    out = np.empty((c.shape[0], 4), dtype=np.int32)
+    _lib().orc_cnr_to_img(_p(c), ctypes.c_int(c.shape[0]), _p(M), _p(out))
+    return out
+
+
+def lidar_cnr_to_img_loop(corners, Tr, R0, P2):
+    """Same function in the reference's own shape -- one box at a time, three np.dot each
+    (transform.py:369-386,483-500).  Used by the timing legs so that the CPU baseline pays what
+    the reference pays; tests check it equals the C loop above."""
+    Tr = np.asarray(Tr).reshape(3, 4)
+    R0 = np.asarray(R0).reshape(4, 3)
+    P2 = np.asarray(P2).reshape(3, 4)
+    out = np.zeros((corners.shape[0], 4))
+    zeros8 = np.zeros(8)
+    with np.errstate(all="ignore"):
+        for i in range(corners.shape[0]):
+            c = np.vstack((corners[i].reshape(3, 8), zeros8))
+            uvw = np.dot(np.dot(np.dot(P2, R0), Tr), c)
+            uvw = uvw / uvw[2]
+            out[i] = (np.min(uvw[0]), np.min(uvw[1]), np.max(uvw[0]), np.max(uvw[1]))
+        return out.astype(np.int32)
+
+
+def clip_boxes(boxes, im_shape):
+    """bbox_transform.py:178-191 (in place, like the reference)."""
+    boxes[:, 0::4] = np.maximum(np.minimum(boxes[:, 0::4], im_shape[1] - 1), 0)
+    boxes[:, 1::4] = np.maximum(np.minimum(boxes[:, 1::4], im_shape[0] - 1), 0)
+    boxes[:, 2::4] = np.maximum(np.minimum(boxes[:, 2::4], im_shape[1] - 1), 0)
+    boxes[:, 3::4] = np.maximum(np.minimum(boxes[:, 3::4], im_shape[0] - 1), 0)
+    return boxes
+
+
+# ----------------------------------------------------------------------------------------
+# a10-a11. sort + NMS
+# ----------------------------------------------------------------------------------------
+def argsort_desc(scores):
+    """proposal_layer_tf.py:161 / cpu_nms.pyx:25 `argsort()[::-1]` with the tie rule fixed:
+    stable ascending sort then reversed => ties come out higher-index-first."""
+    return np.argsort(scores.ravel(), kind="stable")[::-1]
+
+
+def nms(dets, thresh, rule="ge"):
+    """cpu_nms.pyx:17-68 (rule 'ge') or nms_kernel.cu:24-78 + host reduce :124-139 (rule 'gt').
+    Returns kept indices into `dets`, score-descending."""
+    if dets.shape[0] == 0:  # nms_wrapper.py:16-17
+        return []
+    d = np.ascontiguousarray(dets, dtype=np.float32)
+    order = np.ascontiguousarray(argsort_desc(d[:, 4]), dtype=np.int64)
+    keep = np.empty(d.shape[0], dtype=np.int32)
+    scratch = np.empty(d.shape[0], dtype=np.uint8)
+    n = _lib().orc_nms(_p(d), ctypes.c_int(d.shape[0]), ctypes.c_int(d.shape[1]), _p(order),
+                       ctypes.c_double(float(thresh)), ctypes.c_int(1 if rule == "ge" else 0), _p(keep), _p(scratch))
+    return keep[:n].tolist()
+
+
+def nms_new(dets, thresh):
+    """lib/utils/nms.pyx:70-123."""
+    if dets.shape[0] == 0:
+        return []
+    d = np.ascontiguousarray(dets, dtype=np.float32)
+    order = np.ascontiguousarray(argsort_desc(d[:, 4]), dtype=np.int64)
+    keep = np.empty(d.shape[0], dtype=np.int32)
+    scratch = np.empty(d.shape[0], dtype=np.uint8)
+    n = _lib().orc_nms_new(_p(d), ctypes.c_int(d.shape[0]), ctypes.c_int(d.shape[1]), _p(order),
+                           ctypes.c_double(float(thresh)), _p(keep), _p(scratch))
+    return keep[:n].tolist()
+
+
+def bbox_overlaps(boxes, query_boxes):
+    """lib/utils/bbox.pyx:15-55: (N,K) float64 IoU with the +1 pixel convention."""
+    b = np.ascontiguousarray(boxes, dtype=np.float64)
+    q = np.ascontiguousarray(query_boxes, dtype=np.float64)
+    out = np.empty((b.shape[0], q.shape[0]), dtype=np.float64)
+    _lib().orc_bbox_overlaps(_p(b), ctypes.c_int(b.shape[0]), _p(q), ctypes.c_int(q.shape[0]), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# a12. proposal_layer_3d  (lib/rpn_msr/proposal_layer_tf.py:25-202)
+# ----------------------------------------------------------------------------------------
+# cfg values the layer reads (config.py:138-147,187-196 defaults; yml overlay in parentheses)
+RPN_CFG = {
+    "TRAIN": dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5),
+    "TEST": dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5),
+    "TEST_DEFAULT": dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5),
+}
+
+
+def proposal_stages(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, calib, feat_stride=8,
+                    geom: BevGeometry = REF_GEOMETRY, img_size=(375, 1242), project="c"):
+    """Steps 1-3 of proposal_layer_3d (:63-151) for ALL anchors, no compaction: returns a dict with
+    per-anchor scores, proposals_3d (f32), proposals_bv (clipped, f32), proposals_img (int32) and the
+    two keep masks.  Split out so the CUDA decode kernel can be compared stage by stage."""
+    A = generate_anchors_bv().shape[0]
+    height, width = rpn_cls_prob_reshape.shape[1:3]
+    scores = rpn_cls_prob_reshape.reshape(1, height, width, A, 2)[..., 1].reshape(-1)
+    deltas = rpn_bbox_pred.reshape(-1, 6)
+    anchors = enumerate_anchors(height, width, feat_stride)
+    anchors_3d = bv_anchor_to_lidar(anchors, geom)
+    with np.errstate(all="ignore"):
+        p3d = bbox_transform_inv_3d(anchors_3d, deltas)
+        pbv = lidar_3d_to_bv(p3d, geom)
+        cnr = lidar_3d_to_corners(p3d)
+        fn = lidar_cnr_to_img if project == "c" else lidar_cnr_to_img_loop
+        pimg = fn(cnr, calib[3], calib[2], calib[0])
+        info = np.asarray(im_info).reshape(-1, 3)[0]
+        pbv = clip_boxes(pbv, info[:2])
+        min_size = 5 * info[2]
+        ws = pbv[:, 2] - pbv[:, 0] + 1
+        hs = pbv[:, 3] - pbv[:, 1] + 1
+        keep_size = (ws >= min_size) & (hs >= min_size)  # _filter_boxes :336-341
+        pad = 50  # _filter_img_boxes :343-352, image size hard-coded at the call site :147
+        keep_img = ((-pad <= pimg[:, 0]) & (pimg[:, 2] <= img_size[1] + pad) & (-pad <= pimg[:, 1]) &
+                    (pimg[:, 3] <= img_size[0] + pad))
+    return dict(scores=scores, anchors=anchors, anchors_3d=anchors_3d.astype(np.float32), p3d=p3d, pbv=pbv,
+                pimg=pimg, keep_size=keep_size, keep_img=keep_img)
+
+
+def proposal_layer_3d(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, calib, cfg_key, _feat_stride=(8,),
+                      anchor_scales=(1.0, 1.0), cfg=None, geom: BevGeometry = REF_GEOMETRY, img_size=(375, 1242),
+                      nms_rule="ge", project="c", return_stages=False):
+    """proposal_layer_tf.py:25-202 -> (blob_bv (R,5), blob_img (R,5), blob_3d (R,7)) float32."""
+    assert rpn_cls_prob_reshape.shape[0] == 1, "Only single item batches are supported"
+    c = (cfg or RPN_CFG)[cfg_key]
+    st = proposal_stages(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, calib, int(_feat_stride[0]), geom, img_size,
+                         project)
+    keep = np.where(st["keep_size"] & st["keep_img"])[0]  # two successive filters == one AND, order kept
+    pbv, p3d, pimg, scores = st["pbv"][keep], st["p3d"][keep], st["pimg"][keep], st["scores"][keep]
+    order = argsort_desc(scores)
+    if c["RPN_PRE_NMS_TOP_N"] > 0:
+        order = order[: c["RPN_PRE_NMS_TOP_N"]]
+    pbv, p3d, pimg, scores = pbv[order], p3d[order], pimg[order], scores[order]
+    k = nms(np.hstack((pbv, scores.reshape(-1, 1))), c["RPN_NMS_THRESH"], nms_rule)
+    if c["RPN_POST_NMS_TOP_N"] > 0:
+        k = k[: c["RPN_POST_NMS_TOP_N"]]
+    k = np.asarray(k, dtype=np.int64)
+    pbv, p3d, pimg, scores = pbv[k], p3d[k], pimg[k], scores[k]
+    z = np.zeros((pbv.shape[0], 1), dtype=np.float32)
+    blobs = (np.hstack((z, pbv.astype(np.float32))), np.hstack((z, pimg.astype(np.float32))),
+             np.hstack((z, p3d.astype(np.float32))))
+    if return_stages:
+        st.update(keep=keep, order=order, nms_keep=k, final_scores=scores, anchor_index=keep[order][k])
+        return blobs, st
+    return blobs
+
+
+# ----------------------------------------------------------------------------------------
+# a15-a16. ROI pooling  (lib/roi_pooling_layer/roi_pooling_op.cc:123-182, :369-444)
+# ----------------------------------------------------------------------------------------
+def roi_pool_fwd(data, rois, pooled_h=7, pooled_w=7, spatial_scale=0.125):
+    d = np.ascontiguousarray(data, dtype=np.float32)
+    r = np.ascontiguousarray(rois, dtype=np.float32)
+    B, H, W, C = d.shape
+    top = np.empty((r.shape[0], pooled_h, pooled_w, C), dtype=np.float32)
+    arg = np.empty(top.shape, dtype=np.int32)
+    i = ctypes.c_int
+    _lib().orc_roi_pool_fwd(_p(d), i(B), i(H), i(W), i(C), _p(r), i(r.shape[0]), i(pooled_h), i(pooled_w),
+                            ctypes.c_float(spatial_scale), _p(top), _p(arg))
+    return top, arg
+
+
+def roi_pool_bwd(data_shape, rois, argmax, dtop, pooled_h=7, pooled_w=7, spatial_scale=0.125):
+    r = np.ascontiguousarray(rois, dtype=np.float32)
+    a = np.ascontiguousarray(argmax, dtype=np.int32)
+    g = np.ascontiguousarray(dtop, dtype=np.float32)
+    B, H, W, C = data_shape
+    out = np.empty(data_shape, dtype=np.float32)
+    i = ctypes.c_int
+    _lib().orc_roi_pool_bwd(_p(r), i(r.shape[0]), _p(a), _p(g), i(B), i(H), i(W), i(C), i(pooled_h), i(pooled_w),
+                            ctypes.c_float(spatial_scale), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs -- shared by tests, golden generator and bench
+# ----------------------------------------------------------------------------------------
+# KITTI 000008-like calibration, rows P2, P3, R0_rect (9 values, zero padded), Tr_velo_to_cam
+# (layout lib/datasets/kitti_mv3d.py:63-75).  Plain KITTI numbers, not reference code.
+KITTI_CALIB = np.array([
+    [7.215377e+02, 0.0, 6.095593e+02, 4.485728e+01, 0.0, 7.215377e+02, 1.728540e+02, 2.163791e-01,
+     0.0, 0.0, 1.0, 2.745884e-03],
+    [7.215377e+02, 0.0, 6.095593e+02, -3.395242e+02, 0.0, 7.215377e+02, 1.728540e+02, 2.199936e+00,
+     0.0, 0.0, 1.0, 2.729905e-03],
+    [9.999239e-01, 9.837760e-03, -7.445048e-03, -9.869795e-03, 9.999421e-01, -4.278459e-03,
+     7.402527e-03, 4.351614e-03, 9.999631e-01, 0.0, 0.0, 0.0],
+    [7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03, 1.480249e-02, 7.280733e-04,
+     -9.998902e-01, -7.631618e-02, 9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01],
+], dtype=np.float32)
+
+
+def synth_points(n, seed=1234):
+    """LiDAR frame: x~U(-5,75), y~U(-45,45), z~U(-3,2), r~U(0,1), float32 (N,4)."""
+    rng = np.random.default_rng(seed)
+    pts = np.empty((n, 4), dtype=np.float32)
+    pts[:, 0] = rng.uniform(-5, 75, n)
+    pts[:, 1] = rng.uniform(-45, 45, n)
+    pts[:, 2] = rng.uniform(-3, 2, n)
+    pts[:, 3] = rng.uniform(0, 1, n)
+    return pts
+
+
+def synth_rpn_outputs(hf, wf, seed=1234, A=4):
+    """Tie-free fg/bg probabilities (1,Hf,Wf,2A) and deltas (1,Hf,Wf,6A) ~ N(0,0.1), float32."""
+    rng = np.random.default_rng(seed)
+    n = hf * wf * A
+    # fg probabilities are n DISTINCT float32 values (a permutation of (k+0.5)/n, squared to skew
+    # towards background like a real RPN) so that no sort ever has to break a tie
+    fg = (((rng.permutation(n) + 0.5) / n) ** 2).astype(np.float32)
+    assert np.unique(fg).size == n
+    prob = np.stack((np.float32(1) - fg, fg), axis=1).reshape(1, hf, wf, 2 * A)
+    deltas = rng.normal(0, 0.1, (1, hf, wf, 6 * A)).astype(np.float32)
+    return prob, deltas

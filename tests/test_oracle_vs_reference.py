@@ -1,0 +1,53 @@
+"""Pin the oracle on the reference itself (dev container only: needs /root/reference).
+Runs the reference's sources through oracle/ref_shim.py and compares on fresh seeds and at the
+full reference shapes.  Skipped where the reference tree is absent (GPU box)."""
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ref_shim.load()
+    r.config.cfg_from_file(r.yml)
+    return r
+
+
+@pytest.mark.parametrize("kw", [
+    dict(res=0.1, zres=0.3, side_range=(-30., 30.), fwd_range=(0., 60), height_range=(-2, 0.4)),
+    dict(res=0.1, zres=0.1, side_range=(-40., 40.), fwd_range=(0., 70.), height_range=(-2.0, 1.5)),
+])
+def test_raster_full_shapes(oracle, ref, kw):
+    pts = oracle.synth_points(60000, seed=3)
+    a = ref.read_lidar.point_cloud_2_top(pts, **kw)
+    b = oracle.point_cloud_2_top(pts, **kw)
+    assert a.shape == b.shape and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("key", ["TEST", "TRAIN"])
+def test_proposal_layer_full_shape(oracle, ref, key):
+    prob, deltas = oracle.synth_rpn_outputs(75, 75, seed=5)
+    im_info = np.array([[601, 601, 1]], dtype=np.float32)
+    want = ref.proposal_layer_tf.proposal_layer_3d(prob, deltas, im_info, oracle.KITTI_CALIB, key, [8, ], [1.0, 1.0])
+    c = ref.cfg[key]
+    cfg = {key: dict(RPN_PRE_NMS_TOP_N=c.RPN_PRE_NMS_TOP_N, RPN_POST_NMS_TOP_N=c.RPN_POST_NMS_TOP_N,
+                     RPN_NMS_THRESH=c.RPN_NMS_THRESH, RPN_MIN_SIZE=c.RPN_MIN_SIZE)}
+    got = oracle.proposal_layer_3d(prob, deltas, im_info, oracle.KITTI_CALIB, key, cfg=cfg)
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+
+
+def test_nms_and_iou_random(oracle, ref):
+    rng = np.random.default_rng(9)
+    n = 3000
+    x1, y1 = rng.integers(0, 500, n), rng.integers(0, 500, n)
+    d = np.stack((x1, y1, x1 + rng.integers(5, 80, n), y1 + rng.integers(5, 80, n), rng.permutation(n) / n), 1)
+    d = d.astype(np.float32)
+    assert list(ref.cpu_nms.cpu_nms(d, 0.7)) == oracle.nms(d, 0.7)
+    assert list(ref.cython_nms.nms(d, 0.3)) == oracle.nms(d, 0.3)
+    b = d[:500, :4].astype(np.float64)
+    q = d[500:530, :4].astype(np.float64)
+    assert np.array_equal(ref.cython_bbox.bbox_overlaps(b, q), oracle.bbox_overlaps(b, q))
