@@ -1,0 +1,195 @@
+/* mv3d_b200 -- C ABI of the B200-native MV3D per-frame hot path (libmv3d_b200.so).
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; pointers named d_* are DEVICE pointers on the current CUDA
+ *     device, h_* are HOST pointers; `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - returns MV3D_OK (0) or a negative mv3d_status; mv3d_status_string() explains it
+ *   - device-pointer entry points never allocate, never synchronise and never touch host memory
+ *     except their scalar arguments: scratch comes from the caller (mv3d_*_workspace_bytes)
+ *   - the *_host entry points mirror reference ABIs that take HOST buffers (they allocate, copy and
+ *     synchronise, exactly like the reference functions they replace)
+ *
+ * Each declaration cites the reference interface (leeyevi/MV3D_TF, paths relative to its root) it
+ * replaces.  INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef MV3D_B200_H_
+#define MV3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MV3D_OK = 0,
+    MV3D_ERR_ARG = -1,       /* invalid argument (null pointer, bad shape, unsupported size) */
+    MV3D_ERR_WORKSPACE = -2, /* workspace too small */
+    MV3D_ERR_LAUNCH = -3,    /* CUDA launch / runtime failure, see mv3d_last_cuda_error() */
+    MV3D_ERR_DRIVER = -4     /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+} mv3d_status;
+
+int mv3d_version(void);
+const char* mv3d_status_string(int status);
+/* cudaError_t of the most recent MV3D_ERR_LAUNCH on this thread (0 if none) and its text. */
+int mv3d_last_cuda_error(void);
+const char* mv3d_last_cuda_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (i) LiDAR -> bird's-eye-view raster.   Replaces point_cloud_2_top, tools/read_lidar.py:10-115
+ *     (= lib/utils/read_lidar.py:10-115).  Same result bit for bit: top (H,W,C) float32, HWC.
+ *
+ *   d_points   (n_points, point_stride) float32 rows [x, y, z, reflectance, ...]
+ *   H, W, C    = y_max+1, x_max+1, z_max+1 of read_lidar.py:49-53;  nslices = len(np.arange(h0,h1,zres))
+ *   h_slice_lo / h_slice_hi  HOST arrays of nslices doubles: slice i keeps lo[i] <= z < hi[i]
+ *                            (read_lidar.py:80-83; float64 compare)
+ *   res, fwd0, fwd1, side0, side1, height0 : the scalars of the reference call, as float32
+ *   xoff = int(floor(side0/res)), yoff = int(floor(fwd1/res))   (read_lidar.py:102-103)
+ *   Optional second output for the conv trunk (may be NULL): d_pad_hi/d_pad_lo, the same raster as
+ *   a zero-haloed bf16 hi/lo pair of shape (H+1, W+1, c_pad) -- see mv3d_pad_nhwc.
+ * ------------------------------------------------------------------------------------------- */
+size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices);
+int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W, int C,
+                    int nslices, const double* h_slice_lo, const double* h_slice_hi, float res, float fwd0,
+                    float fwd1, float side0, float side1, float height0, int xoff, int yoff, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (iii) NMS.
+ *   _nms: literal drop-in for the reference's C ABI, lib/nms/gpu_nms.hpp:1-2 / nms_kernel.cu:91-144
+ *         (HOST pointers, boxes (boxes_num, boxes_dim>=4) float32 sorted by score descending, keeps
+ *         `ovr > thresh` in float like nms_kernel.cu:71, synchronous).
+ *   mv3d_nms: device-pointer form.  rule_ge=1 reproduces lib/nms/cpu_nms.pyx:65 (`(double)ovr >= thresh`),
+ *         rule_ge=0 reproduces nms_kernel.cu:71.  d_boxes must already be in score-descending order
+ *         (gpu_nms.pyx:23-25 sorts on the host before calling _nms).  Stops after max_keep survivors
+ *         (<=0: no limit), which equals the reference's `keep[:post_nms_topN]` (proposal_layer_tf.py:173).
+ *         d_n_boxes (optional) overrides n_boxes with a count that lives on the device.
+ * ------------------------------------------------------------------------------------------- */
+void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+          float nms_overlap_thresh, int device_id);
+size_t mv3d_nms_workspace_bytes(int n_boxes);
+int mv3d_nms(const float* d_boxes, int n_boxes, int box_stride, const int* d_n_boxes, double thresh, int rule_ge,
+             int max_keep, int* d_keep_out, int* d_num_out, void* d_workspace, size_t workspace_bytes,
+             void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (iii) proposal_layer_3d.   Replaces lib/rpn_msr/proposal_layer_tf.py:25-202 with the helpers it
+ *     calls: generate_anchors_bv (generate_anchors.py:37-51), bv_anchor_to_lidar / lidar_3d_to_bv /
+ *     lidar_3d_to_corners / lidar_cnr_to_img (lib/utils/transform.py:89-142,290-315,483-500),
+ *     bbox_transform_inv_3d / clip_boxes (lib/fast_rcnn/bbox_transform.py:108-155,178-191),
+ *     _filter_boxes / _filter_img_boxes (:336-352), score sort (:161-167) and nms (:172).
+ *
+ *   d_prob (Hf,Wf,2A) float32 = rpn_cls_prob_reshape[0], d_deltas (Hf,Wf,6A) = rpn_bbox_pred[0]
+ *   d_anchors3d (Hf*Wf*A, 6) float32 : bv_anchor_to_lidar(all anchors) cast to float32 (host-made once)
+ *   h_proj 12 floats: row-major 3x4 (P2 . R0) . Tr  in float32 (transform.py:383-384)
+ *   geometry: xn, yn, x_min, y_min, res of transform.py:3-20 (doubles);  im_h, im_w, im_scale = im_info
+ *   img_h, img_w: the image size of _filter_img_boxes (the reference hard-codes 375, 1242)
+ *   Outputs (capacity post_nms_top_n rows): d_blob_bv (R,5), d_blob_img (R,5), d_blob_3d (R,7) float32
+ *   with leading batch index `batch_index`; d_scores (R) ; d_anchor_index (R) int32 ; d_num_out (1) int32.
+ *   Rows >= *d_num_out are zero-filled.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int Hf, Wf, A;
+    double xn, yn, x_min, y_min, res;
+    float im_h, im_w, im_scale;
+    float img_h, img_w;
+    float min_size; /* cfg RPN_MIN_SIZE */
+    int pre_nms_top_n, post_nms_top_n;
+    double nms_thresh;
+    int nms_rule_ge;
+    float batch_index;
+} mv3d_proposal_params;
+
+size_t mv3d_proposal_workspace_bytes(const mv3d_proposal_params* p);
+int mv3d_proposal_layer_3d(const float* d_prob, const float* d_deltas, const float* d_anchors3d,
+                           const float* h_proj, const mv3d_proposal_params* p, float* d_blob_bv,
+                           float* d_blob_img, float* d_blob_3d, float* d_scores, int* d_anchor_index,
+                           int* d_num_out, void* d_workspace, size_t workspace_bytes, void* stream);
+/* Stage outputs of the decode kernel alone, for stage-wise parity tests: per anchor score, p3d (6),
+ * clipped bv box (4), image box (4, int32), keep flag (uint8). */
+int mv3d_proposal_decode(const float* d_prob, const float* d_deltas, const float* d_anchors3d, const float* h_proj,
+                         const mv3d_proposal_params* p, float* d_score, float* d_p3d, float* d_pbv, int* d_pimg,
+                         unsigned char* d_keep, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (iv) ROI pooling.  Replaces the RoiPool / RoiPoolGrad TF ops, lib/roi_pooling_layer/
+ *     roi_pooling_op.cc:30-49 and their launchers ROIPoolForwardLaucher / ROIPoolBackwardLaucher
+ *     (roi_pooling_op_gpu.h:18-27, roi_pooling_op_gpu.cu.cc:87-110,193-215): device pointers,
+ *     NHWC float32 data, rois (R,5) [batch,x1,y1,x2,y2], top/argmax (R,PH,PW,C).
+ *     The multi-view form pools up to 3 feature maps in ONE launch (north-star (iv)).
+ * ------------------------------------------------------------------------------------------- */
+int mv3d_roi_pool_forward(const float* d_bottom_data, float spatial_scale, int num_rois, int height, int width,
+                          int channels, int pooled_height, int pooled_width, const float* d_bottom_rois,
+                          float* d_top_data, int* d_argmax_data, void* stream);
+int mv3d_roi_pool_backward(const float* d_top_diff, float spatial_scale, int batch_size, int num_rois, int height,
+                           int width, int channels, int pooled_height, int pooled_width,
+                           const float* d_bottom_rois, float* d_bottom_diff, const int* d_argmax_data,
+                           void* stream);
+
+typedef struct {
+    const float* d_data;  /* (B,H,W,C) float32 NHWC */
+    const float* d_rois;  /* (R,5) */
+    int height, width;
+    float spatial_scale;
+    float* d_top;         /* (R,PH,PW,C) float32, may be NULL */
+    int* d_argmax;        /* (R,PH,PW,C) int32, may be NULL */
+    void* d_top_hi;       /* optional bf16 (R, PH*PW*C) hi/lo pair feeding fc6, may be NULL */
+    void* d_top_lo;
+} mv3d_roi_view;
+int mv3d_roi_pool_multiview(const mv3d_roi_view* views, int n_views, int num_rois, const int* d_num_valid,
+                            int channels, int pooled_height, int pooled_width, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (ii) conv / fc as one tcgen05 implicit GEMM.  Replaces Network.conv (+bias+ReLU) and Network.fc,
+ *     lib/networks/network.py:108-132,369-397 (tf.nn.conv2d SAME stride 1 / xw_plus_b).
+ *
+ *   Activations live in a zero-haloed, channel-padded bf16 layout "PAD": (B, Hp=H+1, Wp=W+1, Cpad),
+ *   pixel (h,w) at [h][w+1], column 0 and row H are zero (one halo column / row is shared by
+ *   neighbours), so a 3x3 SAME conv is 9 row-shifted GEMMs over the flattened pixel index.
+ *   Precision: a value x is the pair (hi=bf16(x), lo=bf16(x-hi)).  passes=3 accumulates
+ *   hi*hi + lo*hi + hi*lo in fp32 (|err| ~ 2^-16, the parity mode); passes=1 uses hi only.
+ *   D[m, n] = sum_{t<taps, c<Cin} A[m + shift_t, c] * W[n, t*Cin + c]  (+ bias[n], ReLU)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int M;    /* rows of A and D: B*Hp*Wp pixels of the PAD layout, or plain rows for fc (taps=1) */
+    int N;    /* output channels */
+    int Cin;  /* channels per tap in A (padded to a multiple of 16) */
+    int taps; /* 9 (3x3) or 1 (1x1 / fc) */
+    int Hp, Wp; /* PAD geometry; 0,0 => A is a plain (M,Cin) matrix, no halo handling */
+    int passes; /* 1 or 3 */
+    const void* d_a_hi; const void* d_a_lo; /* bf16 (M, Cin) */
+    const void* d_w_hi; const void* d_w_lo; /* bf16 (N, taps*Cin), see mv3d_pack_conv_weights */
+    const float* d_bias;                    /* (N) or NULL */
+    int relu;
+    void* d_out_hi; void* d_out_lo; int ld_out;  /* bf16 (M, ld_out) PAD layout (halo pixels written as 0); NULL to skip */
+    float* d_out_f32; int ld_f32; int f32_dense; /* fp32 output; f32_dense=1 drops halo pixels: (B,H,W,ld_f32) */
+    int split_k; /* >1: K range split over blockIdx.z, partial sums atomically added into d_out_f32
+                    (which the caller zeroed); bias/relu/bf16 outputs are then ignored */
+} mv3d_gemm_desc;
+int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
+
+/* HWIO float32 weights (kh,kw,Cin,Cout) (network.py:119) -> bf16 hi/lo (Cout, kh*kw*cin_pad), K-major.
+ * k_perm (optional, device, length kh*kw*Cin ints): source k index for each destination k (used to fold
+ * the reference's NHWC->NCHW flatten before fc6, network.py:381, into the weight). */
+int mv3d_pack_weights(const float* d_w_hwio, int taps, int cin, int cout, int cin_pad, void* d_w_hi, void* d_w_lo,
+                      void* stream);
+/* (B,H,W,C) float32 NHWC -> PAD bf16 hi/lo (B,H+1,W+1,c_pad), halos and channel padding zeroed. */
+int mv3d_pad_nhwc(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi, void* d_lo, void* stream);
+/* PAD -> dense float32 (B,H,W,C) (hi+lo). */
+int mv3d_unpad_nhwc(const void* d_hi, const void* d_lo, int B, int H, int W, int C, int c_pad, float* d_out,
+                    void* stream);
+/* 2x2 stride-2 VALID max-pool on the PAD layout (Network.max_pool, network.py:181-188). */
+int mv3d_maxpool2x2_pad(const void* d_in_hi, const void* d_in_lo, int B, int H, int W, int c_pad, void* d_out_hi,
+                        void* d_out_lo, void* stream);
+/* softmax over channel pairs (2a, 2a+1) of a (rows, 2A) float32 matrix == reshape_layer + softmax +
+ * reshape_layer of MV3D_test.py:76-80 (network.py:333-341,399-405); also plain row softmax (A=1). */
+int mv3d_softmax_pairs(const float* d_in, int rows, int ld_in, int n_pairs, float* d_out, int ld_out, void* stream);
+/* split-K epilogue: out = act(acc + bias) as bf16 hi/lo and/or fp32. */
+int mv3d_bias_act(const float* d_acc, int M, int N, int ld_acc, const float* d_bias, int relu, void* d_out_hi,
+                  void* d_out_lo, int ld_out, float* d_out_f32, int ld_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MV3D_B200_H_ */

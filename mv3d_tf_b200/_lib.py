@@ -1,0 +1,121 @@
+"""ctypes binding of libmv3d_b200.so (the C ABI in include/mv3d_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  PyTorch tensors
+are used only as device-memory containers (`tensor.data_ptr()`) and for the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmv3d_b200.so")
+
+c_void_p, c_int, c_float, c_double, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
+
+
+class ProposalParams(C.Structure):
+    _fields_ = [("Hf", c_int), ("Wf", c_int), ("A", c_int),
+                ("xn", c_double), ("yn", c_double), ("x_min", c_double), ("y_min", c_double), ("res", c_double),
+                ("im_h", c_float), ("im_w", c_float), ("im_scale", c_float),
+                ("img_h", c_float), ("img_w", c_float), ("min_size", c_float),
+                ("pre_nms_top_n", c_int), ("post_nms_top_n", c_int),
+                ("nms_thresh", c_double), ("nms_rule_ge", c_int), ("batch_index", c_float)]
+
+
+class RoiView(C.Structure):
+    _fields_ = [("d_data", c_void_p), ("d_rois", c_void_p), ("height", c_int), ("width", c_int),
+                ("spatial_scale", c_float), ("d_top", c_void_p), ("d_argmax", c_void_p),
+                ("d_top_hi", c_void_p), ("d_top_lo", c_void_p)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("M", c_int), ("N", c_int), ("Cin", c_int), ("taps", c_int), ("Hp", c_int), ("Wp", c_int),
+                ("passes", c_int),
+                ("d_a_hi", c_void_p), ("d_a_lo", c_void_p), ("d_w_hi", c_void_p), ("d_w_lo", c_void_p),
+                ("d_bias", c_void_p), ("relu", c_int),
+                ("d_out_hi", c_void_p), ("d_out_lo", c_void_p), ("ld_out", c_int),
+                ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/mv3d_b200.h declares
+SIGNATURES = {
+    "mv3d_version": (c_int, []),
+    "mv3d_status_string": (C.c_char_p, [c_int]),
+    "mv3d_last_cuda_error": (c_int, []),
+    "mv3d_last_cuda_error_string": (C.c_char_p, []),
+    "mv3d_bev_raster_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mv3d_bev_raster": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_void_p,
+                                c_size_t, c_void_p]),
+    "_nms": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int]),
+    "mv3d_nms_workspace_bytes": (c_size_t, [c_int]),
+    "mv3d_nms": (c_int, [c_void_p, c_int, c_int, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                         c_size_t, c_void_p]),
+    "mv3d_proposal_workspace_bytes": (c_size_t, [C.POINTER(ProposalParams)]),
+    "mv3d_proposal_layer_3d": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(ProposalParams), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
+    "mv3d_proposal_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(ProposalParams), c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv3d_roi_pool_forward": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "mv3d_roi_pool_backward": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "mv3d_roi_pool_multiview": (c_int, [C.POINTER(RoiView), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv3d_conv_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "mv3d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_pad_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_unpad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mv3d_maxpool2x2_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_softmax_pairs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mv3d_bias_act": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                              c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class Mv3dError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Mv3dError("%s not built -- run `python -m mv3d_tf_b200.build` (there is no CPU fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            if not hasattr(handle, name) and os.environ.get("MV3D_DEV_PARTIAL_LIB") == "1":
+                continue  # development only: library built from a subset of the sources
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        L = lib()
+        msg = L.mv3d_status_string(status).decode()
+        if status == -3:
+            msg += " [%s]" % L.mv3d_last_cuda_error_string().decode()
+        raise Mv3dError("%s failed: %s" % (what or "mv3d call", msg))
+
+
+def ptr(t) -> int:
+    """Device/host address of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

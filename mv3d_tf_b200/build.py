@@ -1,0 +1,50 @@
+"""Build libmv3d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m mv3d_tf_b200.build [--force]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "csrc", "_obj")
+LIB = os.path.join(HERE, "libmv3d_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+# --fmad=false: the integer-exact kernels restate numpy arithmetic (separate mul and add roundings);
+# the tensor-core GEMM does its math in tcgen05.mma and is unaffected.
+
+
+def _deps():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "mv3d_b200.h")]
+
+
+def _compile(src: str, force: bool) -> str:
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    newest = max(os.path.getmtime(p) for p in [src] + _deps())
+    if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+        subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], check=True)
+    return obj
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force), srcs))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-cudart", "static"],
+                       check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

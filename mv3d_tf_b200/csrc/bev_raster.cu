@@ -1,0 +1,218 @@
+// LiDAR point cloud -> bird's-eye-view raster.  Replaces point_cloud_2_top (tools/read_lidar.py:10-115).
+//
+// The reference makes one pass over all points per height slice and scatters with numpy fancy indexing
+// (last write wins).  Here the cloud is binned once by 16x16-cell tile (count -> scan -> scatter of point
+// indices), then ONE CTA per tile resolves "last writer" for every (cell, slice) with atomicMax on the point
+// index in a shared-memory table and streams its tile of the (H,W,C) output exactly once, coalesced.
+// HBM traffic ~= 16 B/point (+ a 4 B index write/read) + 4*H*W*C output bytes: the algorithmic minimum.
+//
+// Exact semantics kept: float32 division for the cell index then truncation toward zero,
+// float64 slice bounds lo[i] <= z < hi[i] tested for EVERY slice, height = z - h0 in float32,
+// intensity = reflectance of the last writer of the highest occupied slice.
+#include "common.cuh"
+
+namespace mv3d {
+
+constexpr int kTile = 16;          // cells per tile side
+constexpr int kMaxSlices = 64;
+constexpr int kRasterThreads = 256;
+
+struct RasterGeom {
+    int H, W, C, nslices;
+    int tiles_x, tiles_y;
+    float res, fwd0, fwd1, side0, side1, h0;
+    int xoff, yoff;
+    double lo[kMaxSlices];
+    double hi[kMaxSlices];
+};
+
+// row/col of a point or false when the reference would not write it.
+__device__ __forceinline__ bool point_cell(const RasterGeom& g, float x, float y, int& row, int& col) {
+    if (!(x > g.fwd0 && x < g.fwd1 && y > -g.side1 && y < -g.side0)) return false;  // read_lidar.py:58-62
+    col = (int)__fdiv_rn(-y, g.res) - g.xoff;                                       // :96,102
+    row = (int)__fdiv_rn(-x, g.res) + g.yoff;                                       // :97,103
+    if (row < 0) row += g.H;  // numpy negative-index wrap
+    if (col < 0) col += g.W;
+    return row >= 0 && row < g.H && col >= 0 && col < g.W;  // (beyond the array the reference raises)
+}
+
+__global__ void raster_count_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                    int* __restrict__ tile_count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1];
+        int row, col;
+        if (point_cell(g, x, y, row, col)) atomicAdd(&tile_count[(row / kTile) * g.tiles_x + col / kTile], 1);
+    }
+}
+
+// exclusive scan of tile counts (single CTA), also clears the per-tile cursors.
+__global__ void raster_scan_kernel(const int* __restrict__ count, int n_tiles, int* __restrict__ offset,
+                                   int* __restrict__ cursor) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_tiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? count[i] : 0;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            warp_sums[lane] = s;  // inclusive over warps
+        }
+        __syncthreads();
+        const int warp_off = warp ? warp_sums[warp - 1] : 0;
+        if (i < n_tiles) {
+            offset[i] = carry + warp_off + incl - v;
+            cursor[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += warp_off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offset[n_tiles] = carry;
+}
+
+__global__ void raster_scatter_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                      const int* __restrict__ offset, int* __restrict__ cursor,
+                                      int* __restrict__ sorted_idx) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1];
+        int row, col;
+        if (point_cell(g, x, y, row, col)) {
+            const int t = (row / kTile) * g.tiles_x + col / kTile;
+            sorted_idx[offset[t] + atomicAdd(&cursor[t], 1)] = i;
+        }
+    }
+}
+
+// One CTA per tile.  smem: winner table [256 cells][nslices] (point index + 1, 0 = empty) + top winner [256].
+__global__ void __launch_bounds__(kRasterThreads)
+raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, const int* __restrict__ offset,
+                   const int* __restrict__ sorted_idx, float* __restrict__ top) {
+    extern __shared__ int tab[];
+    const int ns = g.nslices;
+    int* top_winner = tab + kTile * kTile * ns;
+    const int tile = blockIdx.x;
+    const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+    const int row0 = ty * kTile, col0 = tx * kTile;
+    for (int i = threadIdx.x; i < kTile * kTile * ns; i += blockDim.x) tab[i] = 0;
+    __syncthreads();
+
+    const int beg = offset[tile], end = offset[tile + 1];
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const int idx = sorted_idx[i];
+        const float* p = pts + (size_t)idx * stride;
+        const float x = p[0], y = p[1];
+        const double z = (double)p[2];
+        int row, col;
+        point_cell(g, x, y, row, col);  // true by construction
+        int* cell = tab + ((row - row0) * kTile + (col - col0)) * ns;
+        for (int s = 0; s < ns; ++s)
+            if (z >= g.lo[s] && z < g.hi[s]) atomicMax(&cell[s], idx + 1);  // read_lidar.py:82-83, last index wins
+    }
+    __syncthreads();
+    // intensity winner = last writer of the highest occupied slice (slices are visited in ascending order)
+    for (int c = threadIdx.x; c < kTile * kTile; c += blockDim.x) {
+        int w = 0;
+        for (int s = ns - 1; s >= 0; --s) {
+            w = tab[c * ns + s];
+            if (w) break;
+        }
+        top_winner[c] = w;
+    }
+    __syncthreads();
+
+    const int C = g.C;
+    const int cols = min(kTile, g.W - col0);
+    const int run = cols * C;  // contiguous floats of one output row inside this tile
+    for (int r = 0; r < kTile && row0 + r < g.H; ++r) {
+        float* out = top + ((size_t)(row0 + r) * g.W + col0) * C;
+        for (int j = threadIdx.x; j < run; j += blockDim.x) {
+            const int cl = j / C, ch = j - cl * C;
+            const int cell = r * kTile + cl;
+            float v = 0.f;
+            if (ch == C - 1) {
+                const int w = top_winner[cell];
+                if (w) v = pts[(size_t)(w - 1) * stride + 3];                              // :113
+            } else if (ch < ns) {
+                const int w = tab[cell * ns + ch];
+                if (w) v = __fsub_rn(pts[(size_t)(w - 1) * stride + 2], g.h0);             // :106,110
+            }
+            out[j] = v;
+        }
+    }
+}
+
+static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, size_t* off_offset, size_t* off_cursor,
+                               size_t* off_sorted) {
+    size_t o = 0;
+    *off_count = o;  o += align_up(sizeof(int) * (size_t)(n_tiles + 1), 256);
+    *off_offset = o; o += align_up(sizeof(int) * (size_t)(n_tiles + 1), 256);
+    *off_cursor = o; o += align_up(sizeof(int) * (size_t)(n_tiles + 1), 256);
+    *off_sorted = o; o += align_up(sizeof(int) * (size_t)(n_points > 0 ? n_points : 1), 256);
+    return o;
+}
+
+}  // namespace mv3d
+
+using namespace mv3d;
+
+extern "C" size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices) {
+    (void)nslices;
+    size_t a, b, c, d;
+    const int n_tiles = ceil_div(H, kTile) * ceil_div(W, kTile);
+    return raster_ws_layout(n_points, n_tiles, &a, &b, &c, &d);
+}
+
+extern "C" int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W,
+                               int C, int nslices, const double* h_lo, const double* h_hi, float res, float fwd0,
+                               float fwd1, float side0, float side1, float height0, int xoff, int yoff,
+                               void* d_workspace, size_t workspace_bytes, void* stream) {
+    MV3D_REQUIRE(d_top && H > 0 && W > 0 && C > 0 && n_points >= 0 && point_stride >= 4);
+    MV3D_REQUIRE(n_points == 0 || d_points);
+    MV3D_REQUIRE(nslices >= 0 && nslices <= kMaxSlices && nslices <= C && (nslices == 0 || (h_lo && h_hi)));
+    MV3D_REQUIRE(n_points < (1 << 30));
+    RasterGeom g;
+    g.H = H; g.W = W; g.C = C; g.nslices = nslices;
+    g.tiles_x = ceil_div(W, kTile); g.tiles_y = ceil_div(H, kTile);
+    g.res = res; g.fwd0 = fwd0; g.fwd1 = fwd1; g.side0 = side0; g.side1 = side1; g.h0 = height0;
+    g.xoff = xoff; g.yoff = yoff;
+    for (int i = 0; i < kMaxSlices; ++i) { g.lo[i] = i < nslices ? h_lo[i] : 0.0; g.hi[i] = i < nslices ? h_hi[i] : 0.0; }
+    const int n_tiles = g.tiles_x * g.tiles_y;
+    size_t oc, oo, ou, os;
+    const size_t need = raster_ws_layout(n_points, n_tiles, &oc, &oo, &ou, &os);
+    if (workspace_bytes < need || !d_workspace) return MV3D_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(d_workspace);
+    int* count = reinterpret_cast<int*>(ws + oc);
+    int* offset = reinterpret_cast<int*>(ws + oo);
+    int* cursor = reinterpret_cast<int*>(ws + ou);
+    int* sorted = reinterpret_cast<int*>(ws + os);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(n_tiles + 1), s);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+    const int pgrid = n_points > 0 ? min(ceil_div(n_points, 256), 148 * 8) : 1;
+    if (n_points > 0) raster_count_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, count);
+    raster_scan_kernel<<<1, 1024, 0, s>>>(count, n_tiles, offset, cursor);
+    if (n_points > 0)
+        raster_scatter_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, offset, cursor, sorted);
+    const size_t smem = sizeof(int) * (size_t)(kTile * kTile) * (size_t)(nslices + 1);
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(raster_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+    }
+    raster_tile_kernel<<<n_tiles, kRasterThreads, smem, s>>>(d_points, point_stride, g, offset, sorted, d_top);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}

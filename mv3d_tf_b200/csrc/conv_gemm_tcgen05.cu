@@ -1,0 +1,364 @@
+// conv3x3 / 1x1 / fc as ONE implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulator in
+// TMEM, operands staged by TMA, mbarrier pipeline).  Replaces Network.conv / Network.fc of the
+// reference (lib/networks/network.py:108-132,369-397 -> tf.nn.conv2d / xw_plus_b).
+//
+// Formulation.  Activations are stored zero-haloed and flattened ("PAD" layout, include/mv3d_b200.h):
+// pixel index p = (b*Hp + h)*Wp + (w+1).  A 3x3 SAME stride-1 conv is then
+//     D[p, n] = sum_{t=0..8} sum_c A[p + (t/3-1)*Wp + (t%3-1), c] * W[n, t*Cin + c]
+// i.e. nine row-shifted GEMMs accumulated into the same TMEM tile.  Each k-step is one TMA box
+// (128 pixel rows x KC channels, hardware 128B/32B swizzle) at a shifted row coordinate; rows before
+// the first / after the last pixel are zero-filled by TMA, halo rows/columns hold zeros.  Output rows
+// that are halo pixels are computed (<= 2/W + 1/H waste) and written as zeros by the epilogue.
+//
+// Tile: 128 (pixels) x BN (channels) per CTA, K step KC (64 -> SWIZZLE_128B, 16 -> SWIZZLE_32B).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
+//             warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// PASSES=3: x = hi + lo (bf16 pair); D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp32 accumulate).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mv3d {
+
+using namespace ptx;
+
+constexpr int kBM = 128;
+constexpr int kGemmThreads = 192;
+
+struct GemmParams {
+    int M, N, Cin, taps, Hp, Wp, H, W;
+    int k_chunks;       // Cin / KC
+    int k_steps_total;  // taps * k_chunks
+    int k_steps_per_split;
+    const float* bias;
+    int relu;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    int ld_out;
+    float* out_f32;
+    int ld_f32;
+    int f32_dense;
+    int split_k;
+};
+
+template <int BN, int KC, int PASSES>
+struct GemmCfg {
+    static constexpr int kRowBytes = KC * 2;
+    static constexpr int kABytes = kBM * kRowBytes;
+    static constexpr int kBBytes = BN * kRowBytes;
+    static constexpr int kOperands = (PASSES == 3) ? 2 : 1;
+    static constexpr int kStageBytes = kOperands * (kABytes + kBBytes);
+    static constexpr int kSmemBudget = 200 * 1024;
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+template <int BN, int KC, int PASSES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const GemmParams prm) {
+    using Cfg = GemmCfg<BN, KC, PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* accum_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * kBM;
+    const int k_begin = blockIdx.z * prm.k_steps_per_split;
+    int k_end = k_begin + prm.k_steps_per_split;
+    if (k_end > prm.k_steps_total) k_end = prm.k_steps_total;
+    const int n_k = k_end - k_begin;  // host guarantees >= 1
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_w_hi);
+        if (PASSES == 3) {
+            prefetch_tensormap(&map_a_lo);
+            prefetch_tensormap(&map_w_lo);
+        }
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int i = 0; i < n_k; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int ks = k_begin + i;
+                const int tap = ks / prm.k_chunks;
+                const int c0 = (ks - tap * prm.k_chunks) * KC;
+                int shift = 0;
+                if (prm.taps == 9) shift = (tap / 3 - 1) * prm.Wp + (tap % 3 - 1);
+                uint8_t* st = stage_base + s * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                tma_load_2d(st, &map_a_hi, &full_bar[s], c0, m0 + shift);
+                tma_load_2d(st + Cfg::kABytes, &map_w_hi, &full_bar[s], tap * prm.Cin + c0, n0);
+                if (PASSES == 3) {
+                    tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &map_a_lo, &full_bar[s], c0, m0 + shift);
+                    tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &map_w_lo, &full_bar[s], tap * prm.Cin + c0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+        for (int i = 0; i < n_k; ++i) {
+            const int s = i % Cfg::kStages;
+            const uint32_t ph = (i / Cfg::kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_hi = smem_u32(stage_base + s * Cfg::kStageBytes);
+                const uint32_t w_hi = a_hi + Cfg::kABytes;
+                const uint32_t a_lo = w_hi + Cfg::kBBytes;
+                const uint32_t w_lo = a_lo + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                    const uint32_t koff = k * 32;  // 16 bf16 along K inside the swizzled row
+                    const uint64_t da = make_kmajor_desc(a_hi + koff, Cfg::kRowBytes);
+                    const uint64_t db = make_kmajor_desc(w_hi + koff, Cfg::kRowBytes);
+                    mma_bf16_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (PASSES == 3) {
+                        const uint64_t dal = make_kmajor_desc(a_lo + koff, Cfg::kRowBytes);
+                        const uint64_t dbl = make_kmajor_desc(w_lo + koff, Cfg::kRowBytes);
+                        mma_bf16_ss(tmem_base, dal, db, idesc, 1u);
+                        mma_bf16_ss(tmem_base, da, dbl, idesc, 1u);
+                    }
+                }
+                mma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+                if (i == n_k - 1) mma_commit(accum_bar);   // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const long long p = (long long)m0 + row;
+        bool in_range = p < prm.M;
+        bool halo = false;
+        long long dense_row = p;
+        if (prm.Hp > 0) {
+            const int wp = (int)(p % prm.Wp);
+            const long long t = p / prm.Wp;
+            const int hp = (int)(t % prm.Hp);
+            const long long b = t / prm.Hp;
+            halo = (wp == 0) || (hp == prm.Hp - 1);
+            dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
+        }
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr_row = tmem_base + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
+            tmem_ld_32x32(taddr_row + c, v);
+            tmem_ld_wait();
+            if (!in_range) continue;
+            const int col0 = n0 + c;
+            if (col0 >= prm.N) continue;
+            if (prm.split_k > 1) {
+                if (halo && prm.f32_dense) continue;
+                float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < prm.N) atomicAdd(o + j, halo ? 0.f : __uint_as_float(v[j]));
+                continue;
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
+                if (prm.relu) x = fmaxf(x, 0.f);
+                f[j] = halo ? 0.f : x;
+            }
+            const bool full = (col0 + 32 <= prm.N);
+            if (prm.out_hi != nullptr) {
+                __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
+                __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
+                if (full && (prm.ld_out % 8 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t ph4[4], pl4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(f[j + 2 * e], h0, l0);
+                            split_bf16(f[j + 2 * e + 1], h1, l1);
+                            ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+                            pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                        }
+                        *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                        if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+                    }
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
+                        __nv_bfloat16 h, l;
+                        split_bf16(f[j], h, l);
+                        oh[j] = h;
+                        if (ol) ol[j] = l;
+                    }
+                }
+            }
+            if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
+                float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+                if (full && (prm.ld_f32 % 4 == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) matrix, box (box_rows, box_cols), swizzle matching box_cols*2 bytes.
+static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return MV3D_ERR_DRIVER;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? MV3D_OK : MV3D_ERR_DRIVER;
+}
+
+template <int BN, int KC, int PASSES>
+static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, KC, PASSES>;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    const uint64_t kcols = (uint64_t)d->taps * d->Cin;
+    int rc;
+    if ((rc = make_map_2d(&ma_hi, d->d_a_hi, d->M, d->Cin, kBM, KC)) != MV3D_OK) return rc;
+    if ((rc = make_map_2d(&mw_hi, d->d_w_hi, d->N, kcols, BN, KC)) != MV3D_OK) return rc;
+    if (PASSES == 3) {
+        if ((rc = make_map_2d(&ma_lo, d->d_a_lo, d->M, d->Cin, kBM, KC)) != MV3D_OK) return rc;
+        if ((rc = make_map_2d(&mw_lo, d->d_w_lo, d->N, kcols, BN, KC)) != MV3D_OK) return rc;
+    } else {
+        ma_lo = ma_hi;
+        mw_lo = mw_hi;
+    }
+    GemmParams p;
+    p.M = d->M; p.N = d->N; p.Cin = d->Cin; p.taps = d->taps; p.Hp = d->Hp; p.Wp = d->Wp;
+    p.H = d->Hp - 1; p.W = d->Wp - 1;
+    p.k_chunks = d->Cin / KC;
+    p.k_steps_total = d->taps * p.k_chunks;
+    int split = d->split_k > 1 ? d->split_k : 1;
+    if (split > p.k_steps_total) split = p.k_steps_total;
+    p.k_steps_per_split = ceil_div(p.k_steps_total, split);
+    split = ceil_div(p.k_steps_total, p.k_steps_per_split);  // no empty z-slices
+    p.split_k = split;
+    p.bias = d->d_bias; p.relu = d->relu;
+    p.out_hi = static_cast<__nv_bfloat16*>(d->d_out_hi);
+    p.out_lo = static_cast<__nv_bfloat16*>(d->d_out_lo);
+    p.ld_out = d->ld_out;
+    p.out_f32 = d->d_out_f32; p.ld_f32 = d->ld_f32; p.f32_dense = d->f32_dense;
+
+    auto kern = conv_gemm_kernel<BN, KC, PASSES>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(d->N, BN), ceil_div(d->M, kBM), split);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+template <int KC, int PASSES>
+static int dispatch_bn(const mv3d_gemm_desc* d, cudaStream_t s) {
+    const int n = d->N;
+    // widest tile that the operand staging affords: 256 columns single pass, 128 in the 3-pass mode
+    if (PASSES == 1 && n > 128) return launch_gemm<256, KC, PASSES>(d, s);
+    if (n > 64) return launch_gemm<128, KC, PASSES>(d, s);
+    if (n > 32) return launch_gemm<64, KC, PASSES>(d, s);
+    return launch_gemm<32, KC, PASSES>(d, s);
+}
+
+}  // namespace mv3d
+
+extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_gemm_desc* d, void* stream) {
+    using namespace mv3d;
+    MV3D_REQUIRE(d != nullptr && d->M > 0 && d->N > 0 && d->Cin > 0);
+    MV3D_REQUIRE(d->taps == 1 || d->taps == 9);
+    MV3D_REQUIRE(d->Cin % 16 == 0);
+    MV3D_REQUIRE(d->passes == 1 || d->passes == 3);
+    MV3D_REQUIRE(d->d_a_hi && d->d_w_hi);
+    MV3D_REQUIRE(d->passes == 1 || (d->d_a_lo && d->d_w_lo));
+    MV3D_REQUIRE(d->taps == 1 || (d->Hp > 1 && d->Wp > 1));
+    MV3D_REQUIRE((d->Hp > 0) == (d->Wp > 0));
+    MV3D_REQUIRE(d->Hp == 0 || d->M % (d->Hp * d->Wp) == 0);
+    MV3D_REQUIRE(d->d_out_hi || d->d_out_f32);
+    MV3D_REQUIRE(d->split_k <= 1 || d->d_out_f32);
+    MV3D_REQUIRE(!d->f32_dense || d->Hp > 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool kc64 = (d->Cin % 64 == 0);
+    if (d->passes == 3) return kc64 ? dispatch_bn<64, 3>(d, s) : dispatch_bn<16, 3>(d, s);
+    return kc64 ? dispatch_bn<64, 1>(d, s) : dispatch_bn<16, 1>(d, s);
+}

@@ -1,0 +1,221 @@
+// Layout / elementwise kernels around the tcgen05 GEMM: weight packing, PAD-layout conversion,
+// 2x2 max-pool on the PAD layout, pair-softmax, split-K epilogue.  All HBM-bound, one pass each.
+#include "common.cuh"
+
+namespace mv3d {
+
+// HWIO fp32 (taps, cin, cout) -> bf16 hi/lo (cout, taps*cin_pad), zero channel padding.
+__global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_pad,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long total = (long long)cout * taps * cin_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin_pad);
+        const long long r = i / cin_pad;
+        const int t = (int)(r % taps);
+        const int n = (int)(r / taps);
+        float x = 0.f;
+        if (c < cin) x = w[((long long)t * cin + c) * cout + n];
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+// (B,H,W,C) fp32 -> PAD (B,H+1,W+1,c_pad) bf16 hi/lo.
+__global__ void pad_nhwc_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int Hp = H + 1, Wp = W + 1;
+    const long long total = (long long)B * Hp * Wp * c_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c_pad);
+        long long r = i / c_pad;
+        const int wp = (int)(r % Wp);
+        r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        float x = 0.f;
+        if (c < C && wp > 0 && hp < H) x = in[(((long long)b * H + hp) * W + (wp - 1)) * C + c];
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+__global__ void unpad_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int B,
+                                  int H, int W, int C, int c_pad, float* __restrict__ out) {
+    const int Hp = H + 1, Wp = W + 1;
+    const long long total = (long long)B * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int w = (int)(r % W);
+        r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        const long long j = (((long long)b * Hp + h) * Wp + (w + 1)) * c_pad + c;
+        float x = __bfloat162float(hi[j]);
+        if (lo) x += __bfloat162float(lo[j]);
+        out[i] = x;
+    }
+}
+
+// 2x2/2 VALID max-pool, PAD in (B,H+1,W+1,c) -> PAD out (B,H/2+1,W/2+1,c).  One thread handles 8 channels
+// (16-byte vectors).  The max is taken on hi+lo and the winner's (hi,lo) pair is copied, so it is exact.
+__global__ void maxpool2x2_pad_kernel(const __nv_bfloat16* __restrict__ ih, const __nv_bfloat16* __restrict__ il,
+                                      int B, int H, int W, int c_pad, __nv_bfloat16* __restrict__ oh,
+                                      __nv_bfloat16* __restrict__ ol) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int Hp = H + 1, Wp = W + 1, Hop = Ho + 1, Wop = Wo + 1;
+    const int cv = c_pad / 8;
+    const long long total = (long long)B * Hop * Wop * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
+        const int wop = (int)(r % Wop);
+        r /= Wop;
+        const int hop = (int)(r % Hop);
+        const int b = (int)(r / Hop);
+        const long long o = ((((long long)b * Hop + hop) * Wop + wop) * c_pad) + c8 * 8;
+        uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
+        if (wop > 0 && hop < Ho) {
+            const int h0 = hop * 2, w0 = (wop - 1) * 2;
+            float best[8];
+            __nv_bfloat16 bh[8], bl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { best[e] = -3.4e38f; bh[e] = __float2bfloat16_rn(0.f); bl[e] = bh[e]; }
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const long long j = ((((long long)b * Hp + h0 + dy) * Wp + (w0 + dx + 1)) * c_pad) + c8 * 8;
+                    uint4 vh = *reinterpret_cast<const uint4*>(ih + j);
+                    uint4 vl = il ? *reinterpret_cast<const uint4*>(il + j) : make_uint4(0, 0, 0, 0);
+                    const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&vh);
+                    const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(&vl);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = __bfloat162float(ph[e]) + __bfloat162float(pl[e]);
+                        if (x > best[e]) { best[e] = x; bh[e] = ph[e]; bl[e] = pl[e]; }
+                    }
+                }
+            rh = *reinterpret_cast<uint4*>(bh);
+            rl = *reinterpret_cast<uint4*>(bl);
+        }
+        *reinterpret_cast<uint4*>(oh + o) = rh;
+        if (ol) *reinterpret_cast<uint4*>(ol + o) = rl;
+    }
+}
+
+// softmax over adjacent channel pairs: out[r, 2a+k] = exp(x_k - m) / (exp(x_0 - m) + exp(x_1 - m)).
+__global__ void softmax_pairs_kernel(const float* __restrict__ in, int rows, int ld_in, int n_pairs,
+                                     float* __restrict__ out, int ld_out) {
+    const long long total = (long long)rows * n_pairs;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i % n_pairs);
+        const long long r = i / n_pairs;
+        const float x0 = in[r * ld_in + 2 * a], x1 = in[r * ld_in + 2 * a + 1];
+        const float m = fmaxf(x0, x1);
+        const float e0 = expf(x0 - m), e1 = expf(x1 - m);
+        const float s = e0 + e1;
+        out[r * ld_out + 2 * a] = e0 / s;
+        out[r * ld_out + 2 * a + 1] = e1 / s;
+    }
+}
+
+__global__ void bias_act_kernel(const float* __restrict__ acc, int M, int N, int ld_acc,
+                                const float* __restrict__ bias, int relu, __nv_bfloat16* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ lo, int ld_out, float* __restrict__ of32, int ld_f32) {
+    const long long total = (long long)M * N;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N);
+        const long long m = i / N;
+        float x = acc[m * ld_acc + n];
+        if (bias) x += bias[n];
+        if (relu) x = fmaxf(x, 0.f);
+        if (hi) {
+            __nv_bfloat16 h, l;
+            split_bf16(x, h, l);
+            hi[m * ld_out + n] = h;
+            if (lo) lo[m * ld_out + n] = l;
+        }
+        if (of32) of32[m * ld_f32 + n] = x;
+    }
+}
+
+static inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mv3d
+
+using namespace mv3d;
+
+extern "C" __attribute__((visibility("default"))) int mv3d_pack_weights(const float* d_w, int taps, int cin, int cout, int cin_pad, void* d_hi, void* d_lo,
+                                 void* stream) {
+    MV3D_REQUIRE(d_w && d_hi && taps > 0 && cin > 0 && cout > 0 && cin_pad >= cin);
+    const long long total = (long long)cout * taps * cin_pad;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_pad_nhwc(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi, void* d_lo,
+                             void* stream) {
+    MV3D_REQUIRE(d_in && d_hi && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C);
+    const long long total = (long long)B * (H + 1) * (W + 1) * c_pad;
+    pad_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, c_pad,
+                                                                             (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_unpad_nhwc(const void* d_hi, const void* d_lo, int B, int H, int W, int C, int c_pad,
+                               float* d_out, void* stream) {
+    MV3D_REQUIRE(d_hi && d_out && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C);
+    const long long total = (long long)B * H * W * C;
+    unpad_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)d_hi, (const __nv_bfloat16*)d_lo, B, H, W, C, c_pad, d_out);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_maxpool2x2_pad(const void* d_in_hi, const void* d_in_lo, int B, int H, int W, int c_pad,
+                                   void* d_out_hi, void* d_out_lo, void* stream) {
+    MV3D_REQUIRE(d_in_hi && d_out_hi && B > 0 && H > 1 && W > 1 && c_pad % 8 == 0);
+    const long long total = (long long)B * (H / 2 + 1) * (W / 2 + 1) * (c_pad / 8);
+    maxpool2x2_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)d_in_hi, (const __nv_bfloat16*)d_in_lo, B, H, W, c_pad, (__nv_bfloat16*)d_out_hi,
+        (__nv_bfloat16*)d_out_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_softmax_pairs(const float* d_in, int rows, int ld_in, int n_pairs, float* d_out, int ld_out,
+                                  void* stream) {
+    MV3D_REQUIRE(d_in && d_out && rows > 0 && n_pairs > 0 && ld_in >= 2 * n_pairs && ld_out >= 2 * n_pairs);
+    softmax_pairs_kernel<<<grid_for((long long)rows * n_pairs, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_in, rows, ld_in, n_pairs, d_out, ld_out);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_bias_act(const float* d_acc, int M, int N, int ld_acc, const float* d_bias, int relu,
+                             void* d_out_hi, void* d_out_lo, int ld_out, float* d_out_f32, int ld_f32, void* stream) {
+    MV3D_REQUIRE(d_acc && M > 0 && N > 0 && (d_out_hi || d_out_f32));
+    bias_act_kernel<<<grid_for((long long)M * N, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_acc, M, N, ld_acc, d_bias, relu, (__nv_bfloat16*)d_out_hi, (__nv_bfloat16*)d_out_lo, ld_out, d_out_f32,
+        ld_f32);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}

@@ -1,0 +1,177 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mv3d_b200.h).
+
+Tensors are containers for device memory only; every computation below happens in
+libmv3d_b200.so.  Nothing here falls back to torch math or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, current_stream, lib, ptr
+
+BF16 = torch.bfloat16
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def pad_channels(c: int) -> int:
+    """Channel padding of the PAD layout: multiples of 16 below 64, multiples of 64 above."""
+    return round_up(c, 16) if c < 64 else round_up(c, 64)
+
+
+@dataclass
+class PadAct:
+    """Activation in the PAD layout: bf16 hi (+ optional lo) of shape (B, H+1, W+1, c_pad)."""
+
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    B: int
+    H: int
+    W: int
+    C: int
+
+    @property
+    def c_pad(self) -> int:
+        return self.hi.shape[-1]
+
+    @property
+    def rows(self) -> int:
+        return self.B * (self.H + 1) * (self.W + 1)
+
+
+def _new_pad(B, H, W, c_pad, precise, device):
+    hi = torch.empty((B, H + 1, W + 1, c_pad), dtype=BF16, device=device)
+    lo = torch.empty_like(hi) if precise else None
+    return hi, lo
+
+
+def pad_nhwc(x: torch.Tensor, precise: bool = True) -> PadAct:
+    """(B,H,W,C) float32 -> PAD."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    cp = pad_channels(Cc)
+    hi, lo = _new_pad(B, H, W, cp, precise, x.device)
+    check(lib().mv3d_pad_nhwc(ptr(x), B, H, W, Cc, cp, ptr(hi), ptr(lo), current_stream()), "mv3d_pad_nhwc")
+    return PadAct(hi, lo, B, H, W, Cc)
+
+
+def unpad_nhwc(a: PadAct) -> torch.Tensor:
+    out = torch.empty((a.B, a.H, a.W, a.C), dtype=torch.float32, device=a.hi.device)
+    check(lib().mv3d_unpad_nhwc(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.C, a.c_pad, ptr(out), current_stream()),
+          "mv3d_unpad_nhwc")
+    return out
+
+
+def maxpool2x2(a: PadAct) -> PadAct:
+    """Network.max_pool(2,2,2,2,'VALID') on the PAD layout."""
+    Ho, Wo = a.H // 2, a.W // 2
+    hi, lo = _new_pad(a.B, Ho, Wo, a.c_pad, a.lo is not None, a.hi.device)
+    check(lib().mv3d_maxpool2x2_pad(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.c_pad, ptr(hi), ptr(lo), current_stream()),
+          "mv3d_maxpool2x2_pad")
+    return PadAct(hi, lo, a.B, Ho, Wo, a.C)
+
+
+@dataclass
+class PackedWeight:
+    """bf16 hi/lo (N, taps*cin_pad) K-major weight + fp32 bias."""
+
+    hi: torch.Tensor
+    lo: torch.Tensor
+    bias: Optional[torch.Tensor]
+    taps: int
+    cin: int
+    cin_pad: int
+    cout: int
+
+
+def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None) -> PackedWeight:
+    """HWIO (kh,kw,Cin,Cout) or (Cin,Cout) float32 -> PackedWeight (network.py:119 / :388 layouts)."""
+    assert w_hwio.is_cuda and w_hwio.dtype == torch.float32
+    w = w_hwio.contiguous()
+    if w.dim() == 2:
+        w = w.view(1, 1, *w.shape)
+    kh, kw, cin, cout = w.shape
+    taps = kh * kw
+    cp = cin_pad or pad_channels(cin)
+    hi = torch.empty((cout, taps * cp), dtype=BF16, device=w.device)
+    lo = torch.empty_like(hi)
+    check(lib().mv3d_pack_weights(ptr(w), taps, cin, cout, cp, ptr(hi), ptr(lo), current_stream()), "mv3d_pack_weights")
+    b = None if bias is None else bias.to(torch.float32).contiguous()
+    return PackedWeight(hi, lo, b, taps, cin, cp, cout)
+
+
+def _run_gemm(**kw):
+    d = GemmDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    check(lib().mv3d_conv_gemm(C.byref(d), current_stream()), "mv3d_conv_gemm")
+
+
+def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
+         out_f32_dense: bool = False):
+    """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None)."""
+    assert w.cin_pad == a.c_pad, (w.cin_pad, a.c_pad)
+    assert (not precise) or a.lo is not None
+    dev = a.hi.device
+    n_pad = pad_channels(w.cout)
+    out = None
+    if out_pad:
+        hi, lo = _new_pad(a.B, a.H, a.W, n_pad, precise, dev)
+        if n_pad != w.cout:
+            hi.zero_()
+            if lo is not None:
+                lo.zero_()
+        out = PadAct(hi, lo, a.B, a.H, a.W, w.cout)
+    dense = torch.empty((a.B, a.H, a.W, w.cout), dtype=torch.float32, device=dev) if out_f32_dense else None
+    _run_gemm(M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=3 if precise else 1,
+              d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias),
+              relu=int(relu), d_out_hi=ptr(out.hi) if out else None, d_out_lo=ptr(out.lo) if out else None,
+              ld_out=n_pad, d_out_f32=ptr(dense), ld_f32=w.cout, f32_dense=1 if out_f32_dense else 0, split_k=1)
+    return out, dense
+
+
+def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, relu: bool, precise: bool = True,
+           out_bf16: bool = True, out_f32: bool = False, split_k: int = 1):
+    """Network.fc: (M,K) bf16 hi/lo rows x PackedWeight -> (hi, lo, f32).  K must equal w.cin_pad."""
+    M, K = a_hi.shape
+    assert K == w.cin_pad and w.taps == 1
+    dev = a_hi.device
+    n_pad = round_up(w.cout, 16)
+    hi = lo = f32 = None
+    if out_bf16:
+        hi = torch.zeros((M, n_pad), dtype=BF16, device=dev)
+        lo = torch.zeros_like(hi) if precise else None
+    if split_k > 1:
+        acc = torch.zeros((M, w.cout), dtype=torch.float32, device=dev)
+        _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
+                  d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=None, relu=0, d_out_hi=None,
+                  d_out_lo=None, ld_out=0, d_out_f32=ptr(acc), ld_f32=w.cout, f32_dense=0, split_k=split_k)
+        if out_f32:
+            f32 = torch.empty((M, w.cout), dtype=torch.float32, device=dev)
+        check(lib().mv3d_bias_act(ptr(acc), M, w.cout, w.cout, ptr(w.bias), int(relu), ptr(hi), ptr(lo), n_pad,
+                                  ptr(f32), w.cout, current_stream()), "mv3d_bias_act")
+        return hi, lo, f32
+    if out_f32:
+        f32 = torch.empty((M, w.cout), dtype=torch.float32, device=dev)
+    _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
+              d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias), relu=int(relu),
+              d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad, d_out_f32=ptr(f32), ld_f32=w.cout, f32_dense=0,
+              split_k=1)
+    return hi, lo, f32
+
+
+def softmax_pairs(x: torch.Tensor, n_pairs: int) -> torch.Tensor:
+    """(rows, 2*n_pairs) float32 -> pairwise softmax, same shape."""
+    x2 = x.reshape(-1, x.shape[-1])
+    out = torch.empty_like(x2)
+    check(lib().mv3d_softmax_pairs(ptr(x2), x2.shape[0], x2.shape[1], n_pairs, ptr(out), out.shape[1],
+                                   current_stream()), "mv3d_softmax_pairs")
+    return out.view(x.shape)

@@ -1,0 +1,95 @@
+"""tcgen05 implicit-GEMM conv / fc against a torch fp64 reference of the same op (GPU only).
+Tolerances: 3-pass (hi/lo split) mode <= 2e-5 of max|ref|; single-pass bf16 <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def _relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K,passes,split_k", [
+    (128, 32, 64, 1, 1), (128, 64, 64, 3, 1), (300, 128, 256, 3, 1), (1000, 512, 1152, 3, 1), (1000, 512, 1152, 1, 1),
+    (257, 50, 4096, 3, 1), (300, 2048, 3136, 3, 4), (77, 24, 48, 3, 1), (640, 256, 16, 1, 1), (130, 8, 512, 3, 1),
+])
+def test_fc_gemm(M, N, K, passes, split_k):
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(K, N, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    pw = k.pack_weights(w, b, cin_pad=K)
+    a_hi, a_lo = _split(a)
+    hi, lo, f32 = k.linear(a_hi, a_lo, pw, relu=True, precise=(passes == 3), out_bf16=True, out_f32=True, split_k=split_k)
+    torch.cuda.synchronize()
+    if passes == 3:
+        ref = torch.relu(a.double() @ w.double() + b.double())
+        tol = 3e-5
+    else:
+        ref = torch.relu(a_hi.double() @ pw.hi.double().t() + b.double())  # same rounded operands
+        tol = 1e-5
+    assert f32.shape == (M, N)
+    assert _relerr(f32, ref) < tol
+    got = hi[:, :N].float() + (lo[:, :N].float() if lo is not None else 0)
+    assert _relerr(got, ref) < (tol if lo is not None else 1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [
+    (1, 9, 11, 3, 64, 3), (2, 16, 20, 64, 64, 3), (1, 37, 41, 36, 64, 3), (1, 23, 50, 128, 256, 3),
+    (1, 23, 50, 128, 256, 1), (1, 12, 13, 512, 512, 3), (1, 75, 75, 64, 128, 3), (1, 40, 33, 9, 64, 1),
+])
+def test_conv3x3(B, H, W, Cin, Cout, passes):
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H * 31 + W)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(3, 3, Cin, Cout, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    precise = passes == 3
+    a = k.pad_nhwc(x, precise=precise)
+    assert torch.equal(k.unpad_nhwc(a), x if precise else x.bfloat16().float()) or precise
+    pw = k.pack_weights(w, b)
+    out, dense = k.conv(a, pw, relu=True, precise=precise, out_pad=True, out_f32_dense=True)
+    torch.cuda.synchronize()
+    if precise:
+        xr, wr, tol = x.double(), w.double(), 3e-5
+    else:
+        xr, wr, tol = x.bfloat16().double(), w.bfloat16().double(), 1e-5
+    ref = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), b.double(), padding=1)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    assert _relerr(dense, ref) < tol
+    got = k.unpad_nhwc(out)
+    assert _relerr(got, ref) < (tol if precise else 1e-2)
+    # halo pixels of the PAD output must be exactly zero (they are the next layer's padding)
+    assert float(out.hi[:, :, 0, :].abs().max()) == 0 and float(out.hi[:, H, :, :].abs().max()) == 0
+    # chained: pool then a second conv consumes the PAD output directly
+    if H >= 4 and W >= 4 and Cout <= 128:
+        pooled = k.maxpool2x2(out)
+        pr = torch.nn.functional.max_pool2d(ref.permute(0, 3, 1, 2), 2, 2)
+        assert _relerr(k.unpad_nhwc(pooled), pr.permute(0, 2, 3, 1)) < (tol if precise else 1e-2)
+        w2 = torch.randn(3, 3, Cout, 32, device="cuda", generator=g) * 0.05
+        pw2 = k.pack_weights(w2, None)
+        _, d2 = k.conv(pooled, pw2, relu=False, precise=precise, out_pad=False, out_f32_dense=True)
+        r2 = torch.nn.functional.conv2d(pr if precise else k.unpad_nhwc(pooled).double().permute(0, 3, 1, 2),
+                                        (w2.double() if precise else w2.bfloat16().double()).permute(3, 2, 0, 1),
+                                        None, padding=1).permute(0, 2, 3, 1)
+        assert _relerr(d2, r2) < (5e-5 if precise else 1e-5)
+
+
+def test_softmax_pairs():
+    from mv3d_tf_b200 import kernels as k
+
+    x = torch.randn(1, 13, 17, 8, device="cuda") * 3
+    y = k.softmax_pairs(x, 4)
+    ref = torch.softmax(x.view(-1, 4, 2).double(), dim=-1).view(x.shape)
+    assert _relerr(y, ref) < 1e-6
