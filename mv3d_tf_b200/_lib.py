@@ -97,7 +97,26 @@ def lib() -> C.CDLL:
     return _lib
 
 
+# kernels launched by one successful call of each entry point (memsets not counted) -- bench.py's gpu_launches
+KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
+                    "mv3d_roi_pool_forward": 1, "mv3d_roi_pool_backward": 1, "mv3d_roi_pool_multiview": 1,
+                    "mv3d_conv_gemm": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_unpad_nhwc": 1,
+                    "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1}
+_launches = 0
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
 def check(status: int, what: str = "") -> None:
+    global _launches
+    _launches += KERNELS_PER_CALL.get(what, 0)
     if status != 0:
         L = lib()
         msg = L.mv3d_status_string(status).decode()

@@ -169,14 +169,14 @@ static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, siz
 
 using namespace mv3d;
 
-extern "C" size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices) {
+extern "C" __attribute__((visibility("default"))) size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices) {
     (void)nslices;
     size_t a, b, c, d;
     const int n_tiles = ceil_div(H, kTile) * ceil_div(W, kTile);
     return raster_ws_layout(n_points, n_tiles, &a, &b, &c, &d);
 }
 
-extern "C" int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W,
+extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W,
                                int C, int nslices, const double* h_lo, const double* h_hi, float res, float fwd0,
                                float fwd1, float side0, float side1, float height0, int xoff, int yoff,
                                void* d_workspace, size_t workspace_bytes, void* stream) {

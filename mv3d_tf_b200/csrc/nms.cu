@@ -10,6 +10,8 @@
 //
 // IoU arithmetic is the reference's, float32 with IEEE roundings (file compiled with --fmad=false):
 //   area = (x2-x1+1)*(y2-y1+1); w = max(0, min(x2)-max(x1)+1); ovr = w*h / (area_i + area_j - w*h).
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace mv3d {

@@ -1,0 +1,367 @@
+// proposal_layer_3d on the device.  Replaces lib/rpn_msr/proposal_layer_tf.py:25-202 and the numpy helpers
+// it calls (see include/mv3d_b200.h).  Seven small launches, no host round trip:
+//   1 decode   : per anchor -- fg score, bbox_transform_inv_3d, lidar_3d_to_bv (numpy float `//` emulated
+//                in fp64), clip, 8 corners -> image box (int32, x86 cast semantics), both filters,
+//                and a 4096-bin score histogram of the survivors
+//   2 scan     : descending exclusive scan of the histogram, M = min(#survivors, pre_nms_topN)
+//   3 scatter  : survivors grouped by score bin (64-bit key = orderable(score) << 32 | anchor index)
+//   4 rank     : exact rank inside the bin by counting -> descending order, ties higher-index-first
+//                (what argsort(kind='stable')[::-1] yields); gathers the sorted BEV boxes
+//   5,6 NMS    : nms.cu (mask + single-CTA keep chain, stops at post_nms_topN)
+//   7 gather   : blob_bv / blob_img / blob_3d rows
+// All float arithmetic mirrors numpy's dtype pipeline; compiled with --fmad=false.
+#include "common.cuh"
+
+extern "C" size_t mv3d_nms_workspace_bytes(int n_boxes);
+extern "C" int mv3d_nms(const float*, int, int, const int*, double, int, int, int*, int*, void*, size_t, void*);
+
+namespace mv3d {
+
+constexpr int kBins = 4096;
+
+struct DecodeConst {
+    float M[12];  // (P2.R0).Tr, float32 row-major 3x4
+    double xn, yn, x_min, y_min, res;
+    float clip_x, clip_y;  // im_w - 1, im_h - 1 (float32)
+    float min_size;        // RPN_MIN_SIZE * im_scale (float32)
+    int img_x_max, img_y_max;  // img_w + 50, img_h + 50
+    int Hf, Wf, A, N;
+};
+
+// numpy float64 floor_divide == npy_divmod (numpy/core/src/npymath/npy_math_internal.h): fmod based.
+__device__ __forceinline__ double npy_floor_divide(double a, double b) {
+    if (b == 0.0) return a / b;
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0) {
+        if ((b < 0) != (mod < 0)) div -= 1.0;
+    }
+    double floordiv;
+    if (div != 0.0) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, a / b);
+    }
+    return floordiv;
+}
+
+// np.maximum(np.minimum(v, hi), 0) with numpy's NaN propagation.
+__device__ __forceinline__ float clip_np(float v, float hi) {
+    if (v != v) return v;
+    v = v < hi ? v : hi;
+    return v > 0.f ? v : 0.f;
+}
+
+// C cast double -> int32 as x86 cvttsd2si does it (numpy astype(int32)): out of range / NaN -> INT_MIN.
+__device__ __forceinline__ int cast_i32_x86(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return (int)v;
+}
+
+__device__ __forceinline__ unsigned int orderable(float s) {
+    const unsigned int u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ int score_bin(float s) {
+    if (s != s) return kBins - 1;
+    const float t = s * (float)kBins;
+    if (!(t > 0.f)) return 0;
+    return t >= (float)(kBins - 1) ? kBins - 1 : (int)t;
+}
+
+struct Decoded {
+    float score;
+    float p3d[6];
+    float bv[4];
+    int img[4];
+    bool keep;
+};
+
+__device__ __forceinline__ Decoded decode_one(const float* __restrict__ prob, const float* __restrict__ deltas,
+                                              const float* __restrict__ anchors3d, const DecodeConst& k, int i) {
+    Decoded o;
+    const int a = i % k.A;
+    const int cell = i / k.A;
+    o.score = prob[(size_t)cell * 2 * k.A + 2 * a + 1];                      // proposal_layer_tf.py:63
+    const float* d = deltas + (size_t)i * 6;                                   // :105
+    const float* an = anchors3d + (size_t)i * 6;
+    // bbox_transform_inv_3d (bbox_transform.py:131-136): float32, mul then add
+    const float px = __fadd_rn(__fmul_rn(d[0], an[3]), an[0]);
+    const float py = __fadd_rn(__fmul_rn(d[1], an[4]), an[1]);
+    const float pz = __fadd_rn(__fmul_rn(d[2], an[5]), an[2]);
+    const float pl = __fmul_rn((float)exp((double)d[3]), an[3]);
+    const float pw = __fmul_rn((float)exp((double)d[4]), an[4]);
+    const float ph = __fmul_rn((float)exp((double)d[5]), an[5]);
+    o.p3d[0] = px; o.p3d[1] = py; o.p3d[2] = pz; o.p3d[3] = pl; o.p3d[4] = pw; o.p3d[5] = ph;
+    // lidar_3d_to_bv (transform.py:132-140): f32 sums widened to f64, numpy `//`
+    const float hl = __fmul_rn(pl, 0.5f), hw = __fmul_rn(pw, 0.5f), hh = __fmul_rn(ph, 0.5f);
+    const float xp = __fadd_rn(px, hl), xm = __fsub_rn(px, hl);
+    const float yp = __fadd_rn(py, hw), ym = __fsub_rn(py, hw);
+    const float zp = __fadd_rn(pz, hh), zm = __fsub_rn(pz, hh);
+    float x1 = (float)(k.yn - npy_floor_divide((double)yp - k.y_min, k.res));
+    float y1 = (float)(k.xn - npy_floor_divide((double)xp - k.x_min, k.res));
+    float x2 = (float)(k.yn - npy_floor_divide((double)ym - k.y_min, k.res));
+    float y2 = (float)(k.xn - npy_floor_divide((double)xm - k.x_min, k.res));
+    // clip_boxes (bbox_transform.py:178-191)
+    x1 = clip_np(x1, k.clip_x); y1 = clip_np(y1, k.clip_y);
+    x2 = clip_np(x2, k.clip_x); y2 = clip_np(y2, k.clip_y);
+    o.bv[0] = x1; o.bv[1] = y1; o.bv[2] = x2; o.bv[3] = y2;
+    const float ws = __fadd_rn(__fsub_rn(x2, x1), 1.f), hs = __fadd_rn(__fsub_rn(y2, y1), 1.f);
+    const bool keep_size = (ws >= k.min_size) && (hs >= k.min_size);           // _filter_boxes :336-341
+    // lidar_3d_to_corners (transform.py:305-313) + lidar_cnr_to_img (:483-500, :369-386)
+    double umin = 0, umax = 0, vmin = 0, vmax = 0;
+    bool nan_u = false, nan_v = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const bool sx = (c == 0 || c == 1 || c == 4 || c == 5);
+        const bool sy = (c == 0 || c == 3 || c == 4 || c == 7);
+        const bool sz = (c >= 4);
+        const double X = sx ? xp : xm, Y = sy ? yp : ym, Z = sz ? zp : zm;
+        double r[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double acc = __dmul_rn((double)k.M[4 * q], X);
+            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 1], Y));
+            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 2], Z));
+            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 3], 0.0));
+            r[q] = acc;
+        }
+        const double u = r[0] / r[2], v = r[1] / r[2];
+        nan_u |= (u != u);
+        nan_v |= (v != v);
+        if (c == 0) { umin = umax = u; vmin = vmax = v; }
+        else {
+            umin = u < umin ? u : umin; umax = u > umax ? u : umax;
+            vmin = v < vmin ? v : vmin; vmax = v > vmax ? v : vmax;
+        }
+    }
+    if (nan_u) umin = umax = nan("");
+    if (nan_v) vmin = vmax = nan("");
+    o.img[0] = cast_i32_x86(umin); o.img[1] = cast_i32_x86(vmin);
+    o.img[2] = cast_i32_x86(umax); o.img[3] = cast_i32_x86(vmax);
+    const bool keep_img = (-50 <= o.img[0]) && (o.img[2] <= k.img_x_max) && (-50 <= o.img[1]) &&
+                          (o.img[3] <= k.img_y_max);                            // _filter_img_boxes :343-352
+    o.keep = keep_size && keep_img;
+    return o;
+}
+
+__global__ void proposal_decode_kernel(const float* __restrict__ prob, const float* __restrict__ deltas,
+                                       const float* __restrict__ anchors3d, DecodeConst k, float* __restrict__ score,
+                                       float* __restrict__ p3d, float4* __restrict__ pbv, int4* __restrict__ pimg,
+                                       unsigned char* __restrict__ keep, int* __restrict__ bin_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k.N) return;
+    const Decoded o = decode_one(prob, deltas, anchors3d, k, i);
+    score[i] = o.score;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p3d[(size_t)i * 6 + q] = o.p3d[q];
+    pbv[i] = make_float4(o.bv[0], o.bv[1], o.bv[2], o.bv[3]);
+    pimg[i] = make_int4(o.img[0], o.img[1], o.img[2], o.img[3]);
+    keep[i] = o.keep ? 1 : 0;
+    if (o.keep && bin_count) atomicAdd(&bin_count[score_bin(o.score)], 1);
+}
+
+// offsets in DESCENDING bin order; meta[0] = #survivors, meta[1] = M = min(#survivors, pre_top_n)
+__global__ void proposal_scan_kernel(const int* __restrict__ bin_count, int* __restrict__ bin_offset,
+                                     int* __restrict__ bin_cursor, int pre_top_n, int* __restrict__ meta) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;  // 1024 threads, 4 bins each; thread 0 owns the HIGHEST bins
+    int c[4], s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = bin_count[kBins - 1 - (t * 4 + q)]; s += c[q]; }
+    part[t] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const int v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = kBins - 1 - (t * 4 + q);
+        bin_offset[b] = run;
+        bin_cursor[b] = 0;
+        run += c[q];
+    }
+    if (t == 1023) {
+        const int total = part[1023];
+        meta[0] = total;
+        meta[1] = (pre_top_n > 0 && total > pre_top_n) ? pre_top_n : total;
+    }
+}
+
+__global__ void proposal_scatter_kernel(const float* __restrict__ score, const unsigned char* __restrict__ keep, int N,
+                                        const int* __restrict__ bin_offset, int* __restrict__ bin_cursor,
+                                        unsigned long long* __restrict__ grouped) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !keep[i]) return;
+    const float s = score[i];
+    const int b = score_bin(s);
+    const int pos = bin_offset[b] + atomicAdd(&bin_cursor[b], 1);
+    grouped[pos] = ((unsigned long long)orderable(s) << 32) | (unsigned int)i;
+}
+
+__global__ void proposal_rank_kernel(const unsigned long long* __restrict__ grouped, const float* __restrict__ score,
+                                     const int* __restrict__ bin_count, const int* __restrict__ bin_offset,
+                                     const int* __restrict__ meta, const float4* __restrict__ pbv,
+                                     int* __restrict__ sorted_idx, float4* __restrict__ sorted_box) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= meta[0]) return;
+    const unsigned long long key = grouped[pos];
+    const int idx = (int)(key & 0xffffffffu);
+    const int b = score_bin(score[idx]);
+    const int beg = bin_offset[b];
+    const int M = meta[1];
+    if (beg >= M) return;  // the whole bin ranks past pre_nms_topN
+    const int end = beg + bin_count[b];
+    int rank = beg;
+    for (int q = beg; q < end; ++q) rank += (grouped[q] > key) ? 1 : 0;
+    if (rank < M) {
+        sorted_idx[rank] = idx;
+        sorted_box[rank] = pbv[idx];
+    }
+}
+
+__global__ void proposal_gather_kernel(const int* __restrict__ keep_list, const int* __restrict__ num_keep,
+                                       const int* __restrict__ sorted_idx, const float* __restrict__ score,
+                                       const float* __restrict__ p3d, const float4* __restrict__ pbv,
+                                       const int4* __restrict__ pimg, int cap, float batch_index,
+                                       float* __restrict__ blob_bv, float* __restrict__ blob_img,
+                                       float* __restrict__ blob_3d, float* __restrict__ out_score,
+                                       int* __restrict__ out_anchor, int* __restrict__ num_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0 && num_out) *num_out = *num_keep;
+    if (r >= cap) return;
+    const bool valid = r < *num_keep;
+    int idx = -1;
+    float4 bv = make_float4(0, 0, 0, 0);
+    int4 im = make_int4(0, 0, 0, 0);
+    float sc = 0.f, p[6] = {0, 0, 0, 0, 0, 0};
+    if (valid) {
+        idx = sorted_idx[keep_list[r]];
+        bv = pbv[idx];
+        im = pimg[idx];
+        sc = score[idx];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[q] = p3d[(size_t)idx * 6 + q];
+    }
+    const float bi = valid ? batch_index : 0.f;
+    float* o = blob_bv + (size_t)r * 5;
+    o[0] = bi; o[1] = bv.x; o[2] = bv.y; o[3] = bv.z; o[4] = bv.w;
+    o = blob_img + (size_t)r * 5;
+    o[0] = bi; o[1] = (float)im.x; o[2] = (float)im.y; o[3] = (float)im.z; o[4] = (float)im.w;
+    o = blob_3d + (size_t)r * 7;
+    o[0] = bi;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) o[1 + q] = p[q];
+    if (out_score) out_score[r] = sc;
+    if (out_anchor) out_anchor[r] = idx;
+}
+
+struct ProposalWs {
+    size_t score, p3d, pbv, pimg, keep, bin_count, bin_offset, bin_cursor, meta, grouped, sorted_idx, sorted_box,
+        keep_list, num_keep, nms, total;
+};
+
+static ProposalWs proposal_layout(const mv3d_proposal_params* p) {
+    ProposalWs w;
+    const size_t N = (size_t)p->Hf * p->Wf * p->A;
+    const size_t cap = (p->pre_nms_top_n > 0 && (size_t)p->pre_nms_top_n < N) ? (size_t)p->pre_nms_top_n : N;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+    w.score = take(4 * N); w.p3d = take(24 * N); w.pbv = take(16 * N); w.pimg = take(16 * N); w.keep = take(N);
+    w.bin_count = take(4 * kBins); w.bin_offset = take(4 * kBins); w.bin_cursor = take(4 * kBins); w.meta = take(16);
+    w.grouped = take(8 * N); w.sorted_idx = take(4 * cap); w.sorted_box = take(16 * cap);
+    w.keep_list = take(4 * cap); w.num_keep = take(16);
+    w.nms = take(mv3d_nms_workspace_bytes((int)cap));
+    w.total = o;
+    return w;
+}
+
+static int make_decode_const(const mv3d_proposal_params* p, const float* h_proj, DecodeConst* k) {
+    if (!p || !h_proj || p->Hf <= 0 || p->Wf <= 0 || p->A <= 0) return MV3D_ERR_ARG;
+    for (int i = 0; i < 12; ++i) k->M[i] = h_proj[i];
+    k->xn = p->xn; k->yn = p->yn; k->x_min = p->x_min; k->y_min = p->y_min; k->res = p->res;
+    k->clip_x = p->im_w - 1.0f;  // im_shape[1] - 1 on a float32 array element
+    k->clip_y = p->im_h - 1.0f;
+    k->min_size = p->min_size * p->im_scale;
+    k->img_x_max = (int)p->img_w + 50;
+    k->img_y_max = (int)p->img_h + 50;
+    k->Hf = p->Hf; k->Wf = p->Wf; k->A = p->A; k->N = p->Hf * p->Wf * p->A;
+    return MV3D_OK;
+}
+
+}  // namespace mv3d
+
+using namespace mv3d;
+
+extern "C" __attribute__((visibility("default"))) size_t mv3d_proposal_workspace_bytes(const mv3d_proposal_params* p) {
+    if (!p) return 0;
+    return proposal_layout(p).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_proposal_decode(
+    const float* d_prob, const float* d_deltas, const float* d_anchors3d, const float* h_proj,
+    const mv3d_proposal_params* p, float* d_score, float* d_p3d, float* d_pbv, int* d_pimg, unsigned char* d_keep,
+    void* stream) {
+    DecodeConst k;
+    int rc = make_decode_const(p, h_proj, &k);
+    if (rc != MV3D_OK) return rc;
+    MV3D_REQUIRE(d_prob && d_deltas && d_anchors3d && d_score && d_p3d && d_pbv && d_pimg && d_keep);
+    proposal_decode_kernel<<<ceil_div(k.N, 128), 128, 0, (cudaStream_t)stream>>>(
+        d_prob, d_deltas, d_anchors3d, k, d_score, d_p3d, (float4*)d_pbv, (int4*)d_pimg, d_keep, nullptr);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_proposal_layer_3d(
+    const float* d_prob, const float* d_deltas, const float* d_anchors3d, const float* h_proj,
+    const mv3d_proposal_params* p, float* d_blob_bv, float* d_blob_img, float* d_blob_3d, float* d_scores,
+    int* d_anchor_index, int* d_num_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    DecodeConst k;
+    int rc = make_decode_const(p, h_proj, &k);
+    if (rc != MV3D_OK) return rc;
+    MV3D_REQUIRE(d_prob && d_deltas && d_anchors3d && d_blob_bv && d_blob_img && d_blob_3d && d_num_out);
+    const ProposalWs w = proposal_layout(p);
+    if (!d_workspace || workspace_bytes < w.total) return MV3D_ERR_WORKSPACE;
+    char* ws = static_cast<char*>(d_workspace);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = k.N;
+    const int cap = (p->pre_nms_top_n > 0 && p->pre_nms_top_n < N) ? p->pre_nms_top_n : N;
+    const int out_cap = (p->post_nms_top_n > 0 && p->post_nms_top_n < cap) ? p->post_nms_top_n : cap;
+    float* score = (float*)(ws + w.score);
+    float* p3d = (float*)(ws + w.p3d);
+    float4* pbv = (float4*)(ws + w.pbv);
+    int4* pimg = (int4*)(ws + w.pimg);
+    unsigned char* keep = (unsigned char*)(ws + w.keep);
+    int* bin_count = (int*)(ws + w.bin_count);
+    int* bin_offset = (int*)(ws + w.bin_offset);
+    int* bin_cursor = (int*)(ws + w.bin_cursor);
+    int* meta = (int*)(ws + w.meta);
+    unsigned long long* grouped = (unsigned long long*)(ws + w.grouped);
+    int* sorted_idx = (int*)(ws + w.sorted_idx);
+    float4* sorted_box = (float4*)(ws + w.sorted_box);
+    int* keep_list = (int*)(ws + w.keep_list);
+    int* num_keep = (int*)(ws + w.num_keep);
+
+    cudaError_t e = cudaMemsetAsync(bin_count, 0, sizeof(int) * kBins, s);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+    proposal_decode_kernel<<<ceil_div(N, 128), 128, 0, s>>>(d_prob, d_deltas, d_anchors3d, k, score, p3d, pbv, pimg,
+                                                             keep, bin_count);
+    proposal_scan_kernel<<<1, 1024, 0, s>>>(bin_count, bin_offset, bin_cursor, p->pre_nms_top_n, meta);
+    proposal_scatter_kernel<<<ceil_div(N, 256), 256, 0, s>>>(score, keep, N, bin_offset, bin_cursor, grouped);
+    proposal_rank_kernel<<<ceil_div(N, 128), 128, 0, s>>>(grouped, score, bin_count, bin_offset, meta, pbv, sorted_idx,
+                                                           sorted_box);
+    MV3D_CHECK_LAUNCH();
+    rc = mv3d_nms((const float*)sorted_box, cap, 4, meta + 1, p->nms_thresh, p->nms_rule_ge, out_cap, keep_list,
+                  num_keep, ws + w.nms, w.total - w.nms, s);
+    if (rc != MV3D_OK) return rc;
+    proposal_gather_kernel<<<ceil_div(out_cap, 128), 128, 0, s>>>(keep_list, num_keep, sorted_idx, score, p3d, pbv, pimg,
+                                                                  out_cap, p->batch_index, d_blob_bv, d_blob_img,
+                                                                  d_blob_3d, d_scores, d_anchor_index, d_num_out);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}

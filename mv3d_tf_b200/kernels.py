@@ -108,11 +108,20 @@ def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Op
     return PackedWeight(hi, lo, b, taps, cin, cp, cout)
 
 
+GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch with CUDA events on its stream
+
+
 def _run_gemm(**kw):
     d = GemmDesc()
     for k, v in kw.items():
         setattr(d, k, v)
+    if GEMM_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
     check(lib().mv3d_conv_gemm(C.byref(d), current_stream()), "mv3d_conv_gemm")
+    if GEMM_EVENTS is not None:
+        e1.record(torch.cuda.current_stream())
+        GEMM_EVENTS.append((e0, e1))
 
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,

@@ -1,0 +1,79 @@
+"""MV3D inference network: same layer names, wiring and placeholders as lib/networks/MV3D_test.py:8-123.
+`bv_channels` generalises the BEV depth (9 in the reference, 36 for the BASELINE 700x800x36 grid)."""
+from .network import Network
+
+n_classes = 2
+_feat_stride = [8, 8]
+anchor_scales = [1, 1]
+
+
+class MV3D_test(Network):
+    def __init__(self, trainable=True, bv_channels=9, **kw):
+        self.lidar_bv_data = Network.placeholder('lidar_bv_data', bv_channels)
+        self.image_data = Network.placeholder('image_data', 3)
+        self.im_info = Network.placeholder('im_info')
+        self.gt_boxes = Network.placeholder('gt_boxes')
+        self.gt_boxes_bv = Network.placeholder('gt_boxes_bv')
+        self.gt_boxes_3d = Network.placeholder('gt_boxes_3d')
+        self.gt_boxes_corners = Network.placeholder('gt_boxes_corners')
+        self.calib = Network.placeholder('calib')
+        self.keep_prob = Network.placeholder('keep_prob')
+        inputs = {'lidar_bv_data': self.lidar_bv_data, 'image_data': self.image_data, 'calib': self.calib,
+                  'im_info': self.im_info, 'gt_boxes': self.gt_boxes, 'gt_boxes_bv': self.gt_boxes_bv,
+                  'gt_boxes_3d': self.gt_boxes_3d, 'gt_boxes_corners': self.gt_boxes_corners}
+        super().__init__(inputs, trainable=trainable, **kw)
+
+    def _vgg_trunk(self, source, suffix):
+        s = suffix
+        (self.feed(source)
+             .conv(3, 3, 64, 1, 1, name='conv1_1' + s)
+             .conv(3, 3, 64, 1, 1, name='conv1_2' + s)
+             .max_pool(2, 2, 2, 2, padding='VALID', name='pool1' + s)
+             .conv(3, 3, 128, 1, 1, name='conv2_1' + s)
+             .conv(3, 3, 128, 1, 1, name='conv2_2' + s)
+             .max_pool(2, 2, 2, 2, padding='VALID', name='pool2' + s)
+             .conv(3, 3, 256, 1, 1, name='conv3_1' + s)
+             .conv(3, 3, 256, 1, 1, name='conv3_2' + s)
+             .conv(3, 3, 256, 1, 1, name='conv3_3' + s)
+             .max_pool(2, 2, 2, 2, padding='VALID', name='pool3' + s)
+             .conv(3, 3, 512, 1, 1, name='conv4_1' + s)
+             .conv(3, 3, 512, 1, 1, name='conv4_2' + s)
+             .conv(3, 3, 512, 1, 1, name='conv4_3' + s)
+             .conv(3, 3, 512, 1, 1, name='conv5_1' + s)
+             .conv(3, 3, 512, 1, 1, name='conv5_2' + s)
+             .conv(3, 3, 512, 1, 1, name='conv5_3' + s))
+
+    def setup(self):
+        self._vgg_trunk('lidar_bv_data', '')     # MV3D_test.py:33-49
+        self._vgg_trunk('image_data', '_2')      # :51-67
+        # ========= RPN ============  (:70-86)
+        (self.feed('conv5_3')
+             .conv(3, 3, 512, 1, 1, name='rpn_conv/3x3')
+             .conv(1, 1, len(anchor_scales) * 2 * 2, 1, 1, padding='VALID', relu=False, name='rpn_cls_score'))
+        (self.feed('rpn_conv/3x3')
+             .conv(1, 1, len(anchor_scales) * 2 * 6, 1, 1, padding='VALID', relu=False, name='rpn_bbox_pred'))
+        (self.feed('rpn_cls_score')
+             .reshape_layer(2, name='rpn_cls_score_reshape')
+             .softmax(name='rpn_cls_prob'))
+        (self.feed('rpn_cls_prob')
+             .reshape_layer(len(anchor_scales) * 2 * 2, name='rpn_cls_prob_reshape'))
+        (self.feed('rpn_cls_prob_reshape', 'rpn_bbox_pred', 'im_info', 'calib')
+             .proposal_layer_3d(_feat_stride[0], 'TEST', name='rois'))
+        (self.feed('rois').proposal_transform(target='img', name='roi_data_img'))
+        (self.feed('rois').proposal_transform(target='bv', name='roi_data_bv'))
+        # ========= RoI Proposal ============  (:103-123)
+        (self.feed('conv5_3', 'roi_data_bv')
+             .roi_pool(7, 7, 1.0 / 8, name='pool_5')
+             .fc(2048, name='fc6_1')
+             .fc(2048, name='fc7_1'))
+        (self.feed('conv5_3_2', 'roi_data_img')
+             .roi_pool(7, 7, 1.0 / 8, name='pool_5_2')
+             .fc(2048, name='fc6_2')
+             .fc(2048, name='fc7_2'))
+        (self.feed('fc7_1', 'fc7_2')
+             .concat(axis=1, name='concat1')
+             .fc(n_classes, relu=False, name='cls_score')
+             .softmax(name='cls_prob'))
+        (self.feed('fc7_1', 'fc7_2')
+             .concat(axis=1, name='concat2')
+             .fc(n_classes * 24, relu=False, name='bbox_pred'))

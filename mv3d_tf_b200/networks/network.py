@@ -1,0 +1,413 @@
+"""Graph builder with the reference's layer-method signatures (lib/networks/network.py:14-409).
+
+The reference builds a TF1 graph with `self.feed(...).conv(...).max_pool(...)` chains and runs it with
+`sess.run(fetches, feed_dict)`.  This class keeps exactly that surface -- `feed`, `get_output`, the
+`@layer` methods with the same argument lists, `load` of the `.npy` weight dict -- but records a small
+program of kernel launches; `run(fetches, feed_dict)` plays it on the current CUDA stream through the
+C ABI (mv3d_tf_b200.kernels).  Nothing here computes on the host or with torch math.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import kernels as K
+from .._lib import RoiView, check, current_stream, lib, ptr
+from ..fast_rcnn.config import cfg
+from ..rpn_msr.proposal_layer_tf import ProposalLayer3D
+from ..utils.transform import REF_GEOMETRY, BevGeometry
+
+DEFAULT_PADDING = 'SAME'
+
+
+@dataclass
+class Node:
+    """A symbolic layer output (the analogue of a tf.Tensor handle)."""
+    name: str
+    kind: str
+    inputs: List["Node"] = field(default_factory=list)
+    fn: Optional[Callable] = None
+    channels: int = 0            # feature channels (maps) or vector width (fc)
+    pooled: Optional[tuple] = None  # (PH, PW) after roi_pool
+    consumers: List[str] = field(default_factory=list)
+    attrs: Dict[str, Any] = field(default_factory=dict)
+
+    def __hash__(self):
+        return id(self)
+
+
+@dataclass
+class Val:
+    """Runtime value of a node: any subset of the representations below."""
+    pad: Optional[K.PadAct] = None          # conv activations (PAD layout, bf16 hi/lo)
+    dense: Optional[torch.Tensor] = None    # float32 NHWC / generic float32 tensor
+    hi: Optional[torch.Tensor] = None       # (rows, width) bf16 pair feeding fc
+    lo: Optional[torch.Tensor] = None
+    extra: Any = None
+
+
+def layer(op):
+    def layer_decorated(self, *args, **kwargs):
+        name = kwargs.setdefault('name', self.get_unique_name(op.__name__))
+        if len(self.inputs) == 0:
+            raise RuntimeError('No input variables found for layer %s.' % name)
+        elif len(self.inputs) == 1:
+            layer_input = self.inputs[0]
+        else:
+            layer_input = list(self.inputs)
+        layer_output = op(self, layer_input, *args, **kwargs)
+        self.layers[name] = layer_output
+        self.feed(layer_output)
+        return self
+    return layer_decorated
+
+
+class Network(object):
+    def __init__(self, inputs, trainable=True, precise=True, geometry: BevGeometry = REF_GEOMETRY,
+                 img_size=(375, 1242), device='cuda'):
+        self.inputs = []
+        self.layers = dict(inputs)
+        self.trainable = trainable
+        self.precise = precise          # True: 3-pass bf16 hi/lo GEMMs (parity mode); False: single pass
+        self.geometry = geometry
+        self.img_size = img_size
+        self.device = torch.device(device)
+        self.params: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.param_specs: Dict[str, dict] = {}
+        self._packed: Dict[str, K.PackedWeight] = {}
+        self._program: List[Node] = []
+        self._proposal_layers: Dict[tuple, ProposalLayer3D] = {}
+        self._roi_nodes: List[Node] = []
+        self.last_num_rois = None
+        self.setup()
+
+    def setup(self):
+        raise NotImplementedError('Must be subclassed.')
+
+    # ------------------------------------------------------------------ graph plumbing
+    def feed(self, *args):
+        assert len(args) != 0
+        self.inputs = []
+        for lyr in args:
+            if isinstance(lyr, str):
+                try:
+                    lyr = self.layers[lyr]
+                except KeyError:
+                    raise KeyError('Unknown layer name fed: %s' % lyr)
+            self.inputs.append(lyr)
+        return self
+
+    def get_output(self, layer):
+        try:
+            return self.layers[layer]
+        except KeyError:
+            raise KeyError('Unknown layer name fed: %s' % layer)
+
+    def get_unique_name(self, prefix):
+        idx = sum(t.startswith(prefix) for t, _ in self.layers.items()) + 1
+        return '%s_%d' % (prefix, idx)
+
+    def validate_padding(self, padding):
+        assert padding in ('SAME', 'VALID')
+
+    def _node(self, name, kind, inputs, fn, **kw):
+        ins = [i[0] if isinstance(i, tuple) else i for i in inputs]
+        n = Node(name=name, kind=kind, inputs=ins, fn=fn, **kw)
+        for i in ins:
+            if isinstance(i, Node):
+                i.consumers.append(kind)
+        self._program.append(n)
+        return n
+
+    @staticmethod
+    def placeholder(name, channels=0):
+        return Node(name=name, kind='placeholder', channels=channels)
+
+    # ------------------------------------------------------------------ parameters
+    def _declare(self, name, shape, stddev):
+        self.param_specs[name] = dict(shape=tuple(int(s) for s in shape), stddev=stddev)
+
+    def init_weights(self, seed=7, mode='reference'):
+        """Random initialisation.  'reference': truncated_normal(0, 0.01) (0.001 for bbox_pred), zero biases
+        (network.py:117-118,385-390).  'he': fan-in scaled so activations survive 13 layers (synthetic benchmarks)."""
+        g = torch.Generator(device='cpu').manual_seed(seed)
+        for name, spec in self.param_specs.items():
+            shape = spec['shape']
+            w = torch.empty(shape, dtype=torch.float32)
+            torch.nn.init.trunc_normal_(w, 0.0, 1.0, -2.0, 2.0, generator=g)
+            if mode == 'he':
+                fan_in = int(np.prod(shape[:-1]))
+                w *= (2.0 / fan_in) ** 0.5
+                b = torch.empty(shape[-1]).uniform_(-0.05, 0.05, generator=g)
+            else:
+                w *= spec['stddev']
+                b = torch.zeros(shape[-1])
+            self.params[name] = dict(weights=w.to(self.device), biases=b.to(self.device))
+        self._packed.clear()
+
+    def load(self, data_path, session=None, saver=None, ignore_missing=False):
+        """`.npy` dict {layer: {'weights': HWIO / (in,out), 'biases'}} (network.py:45-64).  session/saver are
+        accepted for signature compatibility and unused."""
+        data_dict = np.load(data_path, allow_pickle=True, encoding='latin1').item()
+        for key in data_dict:
+            if key not in self.param_specs:
+                if not ignore_missing:
+                    raise ValueError('no layer named %s' % key)
+                continue
+            tgt = self.params.setdefault(key, {})
+            for subkey, arr in data_dict[key].items():
+                t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
+                want = self.param_specs[key]['shape'] if subkey == 'weights' else (self.param_specs[key]['shape'][-1],)
+                if tuple(t.shape) != tuple(want):
+                    if not ignore_missing:
+                        raise ValueError('shape mismatch for %s/%s' % (key, subkey))
+                    continue
+                tgt[subkey] = t
+        self._packed.clear()
+
+    def _weight(self, name, transform=None) -> K.PackedWeight:
+        pw = self._packed.get(name)
+        if pw is None:
+            p = self.params[name]
+            w = p['weights']
+            if transform is not None:
+                w = transform(w)
+            pw = self._packed[name] = K.pack_weights(w, p['biases'])
+        return pw
+
+    # ------------------------------------------------------------------ layers (reference signatures)
+    @layer
+    def conv(self, input, k_h, k_w, c_o, s_h, s_w, name, relu=True, padding=DEFAULT_PADDING, group=1, trainable=True):
+        self.validate_padding(padding)
+        assert group == 1 and s_h == 1 and s_w == 1, 'the MV3D nets only use stride-1 ungrouped convs'
+        assert (k_h, k_w) in ((3, 3), (1, 1))
+        assert (k_h, k_w) == (1, 1) or padding == 'SAME'
+        c_i = input.channels
+        self._declare(name, (k_h, k_w, c_i, c_o), 0.01)
+
+        def run(vals, node):
+            v = vals[node.inputs[0]]
+            if v.pad is None:
+                v.pad = K.pad_nhwc(v.dense, precise=self.precise)
+            want_pad = any(c in ('conv', 'max_pool') for c in node.consumers)
+            want_dense = (not want_pad) or any(c not in ('conv', 'max_pool') for c in node.consumers) \
+                or node.attrs.get('fetched', False)
+            out, dense = K.conv(v.pad, self._weight(name), relu=relu, precise=self.precise, out_pad=want_pad,
+                                out_f32_dense=want_dense)
+            return Val(pad=out, dense=dense)
+        return self._node(name, 'conv', [input], run, channels=c_o)
+
+    @layer
+    def max_pool(self, input, k_h, k_w, s_h, s_w, name, padding=DEFAULT_PADDING):
+        self.validate_padding(padding)
+        assert (k_h, k_w, s_h, s_w) == (2, 2, 2, 2) and padding == 'VALID'
+
+        def run(vals, node):
+            v = vals[node.inputs[0]]
+            return Val(pad=K.maxpool2x2(v.pad))
+        return self._node(name, 'max_pool', [input], run, channels=input.channels)
+
+    @layer
+    def reshape_layer(self, input, d, name):
+        def run(vals, node):
+            x = vals[node.inputs[0]].dense
+            return Val(dense=x.reshape(x.shape[0], x.shape[1], -1, int(d)))
+        return self._node(name, 'reshape', [input], run, channels=int(d))
+
+    @layer
+    def softmax(self, input, name):
+        def run(vals, node):
+            x = vals[node.inputs[0]].dense
+            assert x.shape[-1] == 2, 'MV3D only ever takes 2-way softmaxes'
+            return Val(dense=K.softmax_pairs(x.contiguous(), 1))
+        return self._node(name, 'softmax', [input], run, channels=input.channels)
+
+    @layer
+    def proposal_layer_3d(self, input, _feat_stride, cfg_key, name):
+        def run(vals, node):
+            prob = vals[node.inputs[0]].dense
+            deltas = vals[node.inputs[1]].dense
+            im_info = np.asarray(vals[node.inputs[2]].extra, dtype=np.float32).reshape(-1, 3)
+            calib = np.asarray(vals[node.inputs[3]].extra, dtype=np.float32)
+            B, H, W = prob.shape[0], prob.shape[1], prob.shape[2]
+            info = tuple(float(x) for x in im_info[0])
+            key = (H, W, cfg_key, int(_feat_stride), info, cfg[cfg_key].RPN_PRE_NMS_TOP_N,
+                   cfg[cfg_key].RPN_POST_NMS_TOP_N, bool(cfg.USE_GPU_NMS))
+            pl = self._proposal_layers.get(key)
+            if pl is None:
+                pl = self._proposal_layers[key] = ProposalLayer3D(H, W, cfg_key, int(_feat_stride), info,
+                                                                  geom=self.geometry, img_size=self.img_size,
+                                                                  device=self.device)
+            outs = []
+            for b in range(B):  # the reference asserts B == 1; frames of a batch are independent
+                cb = calib.reshape(-1, 4, 12)[b if calib.size > 48 else 0]
+                outs.append(pl(prob[b], deltas[b], cb, batch_index=float(b)))
+            if B == 1:
+                o = outs[0]
+                bv, img, p3d, num = o['bv'], o['img'], o['p3d'], o['num']
+            else:
+                bv = torch.cat([o['bv'] for o in outs]); img = torch.cat([o['img'] for o in outs])
+                p3d = torch.cat([o['p3d'] for o in outs]); num = torch.cat([o['num'] for o in outs])
+            self.last_num_rois = num
+            return Val(extra=dict(bv=bv, img=img, p3d=p3d, num=num, per_frame=pl.capacity, outs=outs))
+        n = self._node(name, 'proposal', list(input), run)
+        # the reference returns the 4-tuple (rois_bv, rois_img, rois_3d, rois_3d)  (network.py:234)
+        return (n, n, n, n)
+
+    @layer
+    def proposal_transform(self, input, name, target='bv'):
+        assert target in ('bv', 'img', 'fv')
+        if target == 'fv':
+            return None  # as the reference (network.py:313-315)
+        src = input[0] if isinstance(input, (tuple, list)) else input
+
+        def run(vals, node):
+            e = vals[node.inputs[0]].extra
+            return Val(dense=e[target], extra=e)
+        return self._node(name, 'rois', [src], run)
+
+    @layer
+    def roi_pool(self, input, pooled_height, pooled_width, spatial_scale, name):
+        data, rois = input[0], input[1]
+        if isinstance(data, tuple):
+            data = data[0]
+        if isinstance(rois, tuple):
+            rois = rois[0]
+
+        def run(vals, node):
+            cached = node.attrs.pop('result', None)
+            if cached is not None:
+                return cached
+            # fuse every roi_pool node whose inputs are ready into one multi-view launch
+            group = [m for m in self._roi_nodes if all(i in vals for i in m.inputs) and 'result' not in m.attrs]
+            views = (RoiView * len(group))()
+            results = []
+            R = None
+            for k, m in enumerate(group):
+                feat = vals[m.inputs[0]].dense
+                r = vals[m.inputs[1]].dense.contiguous()
+                R = r.shape[0]
+                ph, pw, sc = m.attrs['cfg']
+                Cc = feat.shape[-1]
+                hi = torch.empty((R, ph * pw * Cc), dtype=torch.bfloat16, device=feat.device)
+                lo = torch.empty_like(hi) if self.precise else None
+                top = None
+                if m.attrs.get('fetched', False):
+                    top = torch.empty((R, ph, pw, Cc), dtype=torch.float32, device=feat.device)
+                v = views[k]
+                v.d_data, v.d_rois, v.height, v.width = ptr(feat), ptr(r), feat.shape[1], feat.shape[2]
+                v.spatial_scale, v.d_top, v.d_argmax, v.d_top_hi, v.d_top_lo = sc, ptr(top), None, ptr(hi), ptr(lo)
+                results.append(Val(dense=top, hi=hi, lo=lo, extra=(feat, r)))
+            ph, pw, _ = node.attrs['cfg']
+            e = vals[node.inputs[1]].extra
+            num = e['num'] if (isinstance(e, dict) and e['num'].numel() == 1) else None
+            check(lib().mv3d_roi_pool_multiview(views, len(group), R, ptr(num), group[0].channels, ph, pw,
+                                                current_stream()), 'mv3d_roi_pool_multiview')
+            mine = None
+            for m, res in zip(group, results):
+                if m is node:
+                    mine = res
+                else:
+                    m.attrs['result'] = res
+            return mine
+        n = self._node(name, 'roi_pool', [data, rois], run, channels=data.channels,
+                       pooled=(pooled_height, pooled_width))
+        n.attrs['cfg'] = (pooled_height, pooled_width, float(spatial_scale))
+        self._roi_nodes.append(n)
+        return n
+
+    @layer
+    def fc(self, input, num_out, name, relu=True, trainable=True):
+        if isinstance(input, tuple):
+            input = input[0]
+        if input.pooled is not None:
+            ph, pw = input.pooled
+            dim = ph * pw * input.channels
+            cc = input.channels
+            # the reference flattens NHWC pooled maps in (C,H,W) order (network.py:381); our pooled rows are
+            # (H,W,C), so the weight rows are permuted once instead of transposing activations every frame
+            transform = lambda w: w.view(cc, ph * pw, num_out).permute(1, 0, 2).reshape(dim, num_out).contiguous()
+        else:
+            dim, transform = input.channels, None
+        self._declare(name, (dim, num_out), 0.001 if name == 'bbox_pred' else 0.01)
+
+        def run(vals, node):
+            v = vals[node.inputs[0]]
+            want_vec = any(c in ('fc', 'concat', 'dropout') for c in node.consumers)
+            want_f32 = (not want_vec) or node.attrs.get('fetched', False) or \
+                any(c not in ('fc', 'concat', 'dropout') for c in node.consumers)
+            M = v.hi.shape[0]
+            split = 1
+            if dim >= 8192:  # weight-streaming GEMM with few output tiles: split K to fill the 148 SMs
+                bn = 128 if self.precise else 256
+                ctas = ((M + 127) // 128) * ((num_out + bn - 1) // bn)
+                split = max(1, min(8, 148 // max(1, ctas)))
+            hi, lo, f32 = K.linear(v.hi, v.lo, self._weight(name, transform), relu=relu, precise=self.precise,
+                                   out_bf16=want_vec, out_f32=want_f32, split_k=split)
+            return Val(hi=hi, lo=lo, dense=f32)
+        return self._node(name, 'fc', [input], run, channels=num_out)
+
+    @layer
+    def concat(self, inputs, axis, name):
+        assert axis == 1
+
+        def run(vals, node):
+            vs = [vals[i] for i in node.inputs]
+            hi = torch.cat([v.hi for v in vs], dim=1)
+            lo = torch.cat([v.lo for v in vs], dim=1) if vs[0].lo is not None else None
+            return Val(hi=hi, lo=lo)
+        return self._node(name, 'concat', list(inputs), run, channels=sum(i.channels for i in inputs))
+
+    @layer
+    def dropout(self, input, keep_prob, name):
+        def run(vals, node):  # inference / parity runs use keep_prob = 1 (identity)
+            return vals[node.inputs[0]]
+        return self._node(name, 'dropout', [input], run, channels=input.channels, pooled=input.pooled)
+
+    # ------------------------------------------------------------------ execution (the sess.run analogue)
+    def run(self, fetches, feed_dict):
+        """Execute the recorded program.  `fetches`: list of Nodes / layer names; feed_dict: {placeholder Node or
+        name: numpy array or CUDA tensor}.  Returns a list of CUDA tensors (float32) -- no host sync."""
+        fetch_nodes = []
+        for f in fetches:
+            n = self.layers[f] if isinstance(f, str) else f
+            n = n[0] if isinstance(n, tuple) else n
+            fetch_nodes.append(n)
+        for n in self._program:
+            n.attrs['fetched'] = n in fetch_nodes
+            n.attrs.pop('result', None)
+        vals: Dict[Node, Val] = {}
+        for k, v in feed_dict.items():
+            node = self.layers[k] if isinstance(k, str) else k
+            if node.name in ('im_info', 'calib', 'keep_prob') or node.name.startswith('gt_'):
+                vals[node] = Val(extra=v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+            else:
+                t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+                vals[node] = Val(dense=t.to(self.device, dtype=torch.float32).contiguous())
+        needed = self._needed(fetch_nodes)
+        for n in self._program:
+            if n in needed:
+                vals[n] = n.fn(vals, n)
+        out = []
+        for n in fetch_nodes:
+            v = vals[n]
+            if v.dense is not None:
+                out.append(v.dense)
+            elif v.pad is not None:
+                out.append(K.unpad_nhwc(v.pad))
+            else:
+                out.append(v.hi.float() + (v.lo.float() if v.lo is not None else 0))
+        return out
+
+    def _needed(self, fetch_nodes):
+        need, stack = set(), list(fetch_nodes)
+        while stack:
+            n = stack.pop()
+            if n in need or not isinstance(n, Node):
+                continue
+            need.add(n)
+            stack.extend(n.inputs)
+        return need

@@ -156,6 +156,22 @@ def build(force: bool = False) -> str:
     return SHIM_ROOT
 
 
+def export_binaries(dst: str) -> list:
+    """Copy the COMPILED reference Cython modules (binaries only, never sources) to `dst` (oracle/_ref/,
+    git-ignored) so that they travel to the GPU box as the reference's own cpu_nms / bbox_overlaps."""
+    import glob
+
+    root = build()
+    os.makedirs(dst, exist_ok=True)
+    out = []
+    for so in glob.glob(os.path.join(root, "nms", "*.so")) + glob.glob(os.path.join(root, "utils", "*.so")):
+        tgt = os.path.join(dst, os.path.basename(so))
+        if not os.path.exists(tgt) or os.path.getmtime(tgt) < os.path.getmtime(so):
+            shutil.copy2(so, tgt)
+        out.append(tgt)
+    return out
+
+
 _PKGS = ("fast_rcnn", "rpn_msr", "utils", "nms", "easydict")
 
 

@@ -1,0 +1,225 @@
+"""CUDA kernels vs the CPU oracle and the reference-made golden vectors, through the C ABI (GPU only).
+Bit-exact for raster values, anchor indices, integer boxes, NMS survivor lists, ROI-pool values/argmax."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ulp(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return np.abs(a - b)
+
+
+# ------------------------------------------------------------------ raster
+RASTER_CASES = [
+    dict(res=0.1, zres=0.3, side_range=(-8., 8.), fwd_range=(0., 16.), height_range=(-2, 0.4)),
+    dict(res=0.1, zres=0.1, side_range=(-8., 8.), fwd_range=(0., 12.), height_range=(-2.0, 1.5)),
+]
+
+
+def test_raster_golden(golden_dir):
+    from mv3d_tf_b200.utils.read_lidar import point_cloud_2_top
+
+    g = np.load(os.path.join(golden_dir, "raster.npz"))
+    for kw, name in zip(RASTER_CASES, ("top_a", "top_b")):
+        got = point_cloud_2_top(g["points"], **kw)
+        assert got.shape == g[name].shape and got.dtype == np.float32
+        assert np.array_equal(got, g[name])
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 120000, 1000000])
+@pytest.mark.parametrize("grid", ["ref", "cfg"])
+def test_raster_vs_oracle_full_grid(oracle, n, grid):
+    from mv3d_tf_b200.utils.read_lidar import point_cloud_2_top
+
+    kw = (dict(res=0.1, zres=0.3, side_range=(-30., 30.), fwd_range=(0., 60), height_range=(-2, 0.4)) if grid == "ref"
+          else dict(res=0.1, zres=0.1, side_range=(-40., 40.), fwd_range=(0., 70.), height_range=(-2.0, 1.5)))
+    pts = oracle.synth_points(n, seed=100 + n % 97)
+    got = point_cloud_2_top(pts, **kw)
+    want = oracle.point_cloud_2_top(pts, **kw)
+    assert got.shape == want.shape == ((601, 601, 9) if grid == "ref" else (701, 801, 36))
+    assert np.array_equal(got, want)
+
+
+def test_raster_duplicates_and_idempotence(oracle):
+    """last-write-wins under heavy collisions, and a size-independent property: rasterising twice or with the
+    cloud concatenated to itself gives the same map."""
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+
+    pts = oracle.synth_points(200000, seed=5)
+    pts[:, :2] = np.round(pts[:, :2] * 2) / 2  # half-metre lattice: ~45 points per occupied cell
+    r = BevRasterizer(0.1, 0.1, (-40., 40.), (0., 70.), (-2.0, 1.5))
+    d = torch.from_numpy(pts).cuda()
+    a = r(d).cpu().numpy()
+    assert np.array_equal(a, oracle.point_cloud_2_top(pts, 0.1, 0.1, (-40., 40.), (0., 70.), (-2.0, 1.5)))
+    assert np.array_equal(a, r(d).cpu().numpy())
+    assert np.array_equal(a, r(torch.cat([d, d])).cpu().numpy())
+
+
+# ------------------------------------------------------------------ NMS
+def test_nms_golden(golden_dir):
+    from mv3d_tf_b200.nms.gpu_nms import cpu_nms
+
+    g = np.load(os.path.join(golden_dir, "nms_iou.npz"))
+    assert cpu_nms(g["dets"], 0.7) == g["keep07"].tolist()
+    assert cpu_nms(g["dets"], 0.5) == g["keep05"].tolist()
+    assert cpu_nms(g["dets"], 0.1) == g["keep01"].tolist()
+    assert cpu_nms(np.zeros((0, 5), np.float32), 0.7) == []
+
+
+@pytest.mark.parametrize("n,thresh", [(1, 0.7), (63, 0.7), (64, 0.5), (65, 0.7), (6000, 0.7), (12000, 0.7), (12000, 0.3)])
+def test_nms_vs_oracle(oracle, n, thresh):
+    from mv3d_tf_b200.nms.gpu_nms import cpu_nms, gpu_nms
+
+    rng = np.random.default_rng(n)
+    x1, y1 = rng.integers(0, 560, n), rng.integers(0, 560, n)
+    d = np.stack((x1, y1, np.minimum(x1 + rng.integers(4, 70, n), 600), np.minimum(y1 + rng.integers(4, 70, n), 600),
+                  rng.permutation(n) / n), 1).astype(np.float32)
+    assert cpu_nms(d, thresh) == oracle.nms(d, thresh, "ge")
+    assert gpu_nms(d, thresh) == oracle.nms(d, thresh, "gt")
+
+
+def test_nms_rules_and_early_stop(oracle):
+    from mv3d_tf_b200.nms.gpu_nms import cpu_nms, gpu_nms, nms_device
+
+    d = np.array([[0, 0, 9, 9, .9], [0, 0, 9, 4, .8]], np.float32)  # IoU exactly 0.5
+    assert cpu_nms(d, 0.5) == [0] and gpu_nms(d, 0.5) == [0, 1]
+    rng = np.random.default_rng(3)
+    n = 5000
+    x1, y1 = rng.integers(0, 500, n), rng.integers(0, 500, n)
+    b = np.stack((x1, y1, x1 + rng.integers(5, 60, n), y1 + rng.integers(5, 60, n)), 1).astype(np.float32)
+    sc = (np.arange(n)[::-1] / n).astype(np.float32)
+    full = oracle.nms(np.hstack((b, sc[:, None])), 0.7)
+    keep, num = nms_device(torch.from_numpy(b).cuda(), 0.7, True, max_keep=300)
+    assert int(num.item()) == 300 and keep[:300].cpu().tolist() == full[:300]
+    # idempotence: NMS of the survivors keeps all of them
+    kb = np.hstack((b, sc[:, None]))[full]
+    assert cpu_nms(kb, 0.7) == list(range(len(full)))
+
+
+# ------------------------------------------------------------------ proposals
+def _layer(hf, wf, key, **kw):
+    from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
+    from mv3d_tf_b200.rpn_msr.proposal_layer_tf import ProposalLayer3D
+
+    cfg_from_end2end_yml()
+    cfg.USE_GPU_NMS = False  # DEVICE=cpu parity target: cpu_nms `>=` rule
+    return ProposalLayer3D(hf, wf, key, 8, (601, 601, 1), **kw)
+
+
+def test_proposal_decode_golden(golden_dir, oracle):
+    g = np.load(os.path.join(golden_dir, "proposal.npz"))
+    hf, wf = g["prob"].shape[1:3]
+    layer = _layer(hf, wf, "TEST")
+    assert np.array_equal(layer.anchors3d.cpu().numpy(), g["anchors_3d"].astype(np.float32))
+    st = layer.decode(torch.from_numpy(g["prob"][0]).cuda(), torch.from_numpy(g["deltas"][0]).cuda(), g["calib"])
+    p3d = st["p3d"].cpu().numpy()
+    fin = np.isfinite(g["p3d"])
+    assert np.array_equal(fin, np.isfinite(p3d))
+    assert _ulp(p3d[fin], g["p3d"][fin]).max() <= 2          # np.exp vs device exp
+    same = _ulp(np.nan_to_num(p3d), np.nan_to_num(g["p3d"])).max(axis=1) == 0
+    assert same.mean() > 0.9
+    pbv_ref = oracle.clip_boxes(g["pbv"].copy(), g["im_info"][0, :2])
+    assert np.array_equal(st["pbv"].cpu().numpy()[same], pbv_ref[same], equal_nan=True)
+    assert np.array_equal(st["pimg"].cpu().numpy()[same], g["pimg"][same])
+    # rows whose float inputs differ by an ulp may only differ in an integer output next to a bin edge
+    diff_rows = np.where(~same)[0]
+    bad = [i for i in diff_rows if not np.array_equal(st["pbv"].cpu().numpy()[i], pbv_ref[i], equal_nan=True)]
+    assert len(bad) <= max(2, len(diff_rows) // 20), (len(bad), len(diff_rows))
+
+
+@pytest.mark.parametrize("key", ["TEST", "TRAIN"])
+def test_proposal_layer_golden(golden_dir, key):
+    g = np.load(os.path.join(golden_dir, "proposal.npz"))
+    hf, wf = g["prob"].shape[1:3]
+    layer = _layer(hf, wf, key)
+    out = layer(torch.from_numpy(g["prob"][0]).cuda(), torch.from_numpy(g["deltas"][0]).cuda(), g["calib"])
+    n = int(out["num"].item())
+    k = key.lower()
+    assert n == g[k + "_bv"].shape[0]
+    assert np.array_equal(out["bv"][:n].cpu().numpy(), g[k + "_bv"])
+    assert np.array_equal(out["img"][:n].cpu().numpy(), g[k + "_img"])
+    assert _ulp(out["p3d"][:n].cpu().numpy(), g[k + "_3d"]).max() <= 2
+    assert float(out["bv"][n:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("shape,geom", [((75, 75), "ref"), ((87, 100), "cfg")])
+@pytest.mark.parametrize("key", ["TEST", "TRAIN"])
+def test_proposal_layer_vs_oracle_full(oracle, shape, geom, key):
+    """BASELINE config 1 at the reference shape (22 500 anchors) and the 700x800 shape (34 800)."""
+    from mv3d_tf_b200.utils.transform import CFG_GEOMETRY, REF_GEOMETRY
+
+    hf, wf = shape
+    prob, deltas = oracle.synth_rpn_outputs(hf, wf, seed=77)
+    if geom == "ref":
+        im_info, pg, og = (601, 601, 1), REF_GEOMETRY, oracle.REF_GEOMETRY
+    else:
+        im_info, pg, og = (701, 801, 1), CFG_GEOMETRY, oracle.CFG_GEOMETRY
+    from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
+    from mv3d_tf_b200.rpn_msr.proposal_layer_tf import ProposalLayer3D
+
+    cfg_from_end2end_yml()
+    cfg.USE_GPU_NMS = False
+    layer = ProposalLayer3D(hf, wf, key, 8, im_info, geom=pg)
+    out = layer(torch.from_numpy(prob[0]).cuda(), torch.from_numpy(deltas[0]).cuda(), oracle.KITTI_CALIB)
+    n = int(out["num"].item())
+    c = cfg[key]
+    ocfg = {key: dict(RPN_PRE_NMS_TOP_N=c.RPN_PRE_NMS_TOP_N, RPN_POST_NMS_TOP_N=c.RPN_POST_NMS_TOP_N,
+                      RPN_NMS_THRESH=c.RPN_NMS_THRESH, RPN_MIN_SIZE=c.RPN_MIN_SIZE)}
+    (bv, img, p3d), st = oracle.proposal_layer_3d(prob, deltas, np.array([im_info], np.float32), oracle.KITTI_CALIB, key,
+                                                  cfg=ocfg, geom=og, return_stages=True)
+    assert n == bv.shape[0]
+    assert np.array_equal(out["anchor"][:n].cpu().numpy(), st["anchor_index"].astype(np.int32))  # anchor indices
+    assert np.array_equal(out["bv"][:n].cpu().numpy(), bv)
+    assert np.array_equal(out["img"][:n].cpu().numpy(), img)
+    assert _ulp(out["p3d"][:n].cpu().numpy(), p3d).max() <= 2
+
+
+def test_proposal_layer_dropin_signature(oracle):
+    from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
+    from mv3d_tf_b200.rpn_msr.proposal_layer_tf import proposal_layer_3d
+
+    cfg_from_end2end_yml()
+    cfg.USE_GPU_NMS = False
+    prob, deltas = oracle.synth_rpn_outputs(30, 28, seed=4)
+    im_info = np.array([[601, 601, 1]], np.float32)
+    got = proposal_layer_3d(prob, deltas, im_info, oracle.KITTI_CALIB, "TEST", [8, ], [1.0, 1.0])
+    want = oracle.proposal_layer_3d(prob, deltas, im_info, oracle.KITTI_CALIB, "TEST")
+    assert [a.shape for a in got] == [a.shape for a in want]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+# ------------------------------------------------------------------ ROI pooling
+def _rois(rng, n, w, h, batch=1):
+    x1, y1 = rng.integers(-60, w, n), rng.integers(-60, h, n)
+    r = np.stack((rng.integers(0, batch, n), x1, y1, x1 + rng.integers(0, 300, n), y1 + rng.integers(0, 200, n)), 1)
+    return r.astype(np.float32)
+
+
+@pytest.mark.parametrize("B,H,W,C,R", [(1, 9, 11, 4, 6), (2, 20, 31, 7, 40), (1, 75, 75, 512, 300), (1, 46, 155, 512, 64)])
+def test_roi_pool_forward_backward(oracle, B, H, W, C, R):
+    from mv3d_tf_b200.roi_pooling_layer.roi_pooling_op import roi_pool, roi_pool_grad
+
+    rng = np.random.default_rng(H * W)
+    data = rng.normal(size=(B, H, W, C)).astype(np.float32)
+    data[0, 0, :, :] = 1.25  # ties: the first maximum in (h,w) order must win
+    rois = _rois(rng, R, W * 8, H * 8, B)
+    rois[0] = [0, -500, -500, -300, -300]      # entirely outside -> zeros, argmax -1
+    rois[1] = [0, 40, 40, 8, 8]                # malformed (end < start) -> forced 1x1
+    top, arg = roi_pool(torch.from_numpy(data).cuda(), torch.from_numpy(rois).cuda(), 7, 7, 0.125)
+    wt, wa = oracle.roi_pool_fwd(data, rois)
+    assert np.array_equal(top.cpu().numpy(), wt)
+    assert np.array_equal(arg.cpu().numpy(), wa)
+    if C <= 8:
+        g = rng.normal(size=wt.shape).astype(np.float32)
+        got = roi_pool_grad(torch.from_numpy(data).cuda(), torch.from_numpy(rois).cuda(), arg,
+                            torch.from_numpy(g).cuda(), 7, 7, 0.125).cpu().numpy()
+        want = oracle.roi_pool_bwd(data.shape, rois, wa, g)
+        assert np.allclose(got, want, rtol=1e-5, atol=2e-5)  # fp32 sum order differs (atomics)

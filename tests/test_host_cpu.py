@@ -1,0 +1,125 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/mv3d_b200.h declares (no compute
+calls), the host-side constants (anchor table, projection matrix, raster scalars, config) agree with the oracle,
+and the product package never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from mv3d_tf_b200 import build
+
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "mv3d_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mv3d_[a-z0-9_]+|_nms)\s*\(", hdr))
+    declared -= {"mv3d_status"}
+    h = ctypes.CDLL(built_lib)
+    missing = [n for n in sorted(declared) if not hasattr(h, n)]
+    assert not missing, missing
+    from mv3d_tf_b200 import _lib
+
+    assert set(_lib.SIGNATURES) == declared
+    h.mv3d_version.restype = ctypes.c_int
+    assert h.mv3d_version() >= 100
+    h.mv3d_status_string.restype = ctypes.c_char_p
+    assert h.mv3d_status_string(-2) == b"workspace too small"
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
+    from mv3d_tf_b200 import _lib
+
+    L = _lib.lib()
+    assert L.mv3d_conv_gemm(None, None) == -1
+    assert L.mv3d_nms(None, -1, 4, None, 0.7, 1, 0, None, None, None, 0, None) == -1
+    assert L.mv3d_bev_raster(None, 10, 4, None, 0, 0, 0, 0, None, None, 0.1, 0, 1, 0, 1, 0, 0, 0, None, 0, None) == -1
+    assert L.mv3d_roi_pool_forward(None, 0.125, 5, 0, 0, 0, 7, 7, None, None, None, None) == -1
+    assert L.mv3d_proposal_workspace_bytes(None) == 0
+    with pytest.raises(_lib.Mv3dError):
+        _lib.check(-1, "x")
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from mv3d_tf_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmv3d_b200.so")
+    with pytest.raises(_lib.Mv3dError):
+        _lib.lib()
+
+
+def test_host_constants_match_oracle(oracle):
+    from mv3d_tf_b200.rpn_msr.generate_anchors import all_anchors, generate_anchors_bv
+    from mv3d_tf_b200.utils import transform as T
+    from mv3d_tf_b200.utils.read_lidar import raster_geometry
+
+    assert np.array_equal(generate_anchors_bv(), oracle.generate_anchors_bv())
+    for hf, wf in ((3, 5), (75, 75), (87, 100)):
+        a = all_anchors(hf, wf, 8)
+        assert np.array_equal(a, oracle.enumerate_anchors(hf, wf, 8))
+        assert np.array_equal(T.bv_anchor_to_lidar(a, T.REF_GEOMETRY), oracle.bv_anchor_to_lidar(a, oracle.REF_GEOMETRY))
+        assert np.array_equal(T.bv_anchor_to_lidar(a, T.CFG_GEOMETRY), oracle.bv_anchor_to_lidar(a, oracle.CFG_GEOMETRY))
+    assert (T.REF_GEOMETRY.xn, T.REF_GEOMETRY.yn, T.CFG_GEOMETRY.xn, T.CFG_GEOMETRY.yn) == (600, 600, 700, 800)
+    c = oracle.KITTI_CALIB
+    assert np.array_equal(T.projection_matrix(c), oracle.projection_matrix(c[3], c[2], c[0]).astype(np.float32))
+    for args in ((0.1, 0.3, (-30., 30.), (0., 60), (-2, 0.4)), (0.1, 0.1, (-40., 40.), (0., 70.), (-2.0, 1.5))):
+        g, o = raster_geometry(*args), oracle.raster_params(*args)
+        assert (g["H"], g["W"], g["C"], g["nslices"], g["xoff"], g["yoff"]) == \
+               (o["H"], o["W"], o["C"], o["nslices"], o["xoff"], o["yoff"])
+        assert np.array_equal(g["lo"], o["lo"]) and np.array_equal(g["hi"], o["hi"])
+    assert raster_geometry(0.1, 0.1, (-40., 40.), (0., 70.), (-2.0, 1.5))["H"] == 701
+
+
+def test_config_overlay_and_set():
+    from mv3d_tf_b200.fast_rcnn import config as C
+
+    C.cfg_from_end2end_yml()
+    assert (C.cfg.TEST.RPN_PRE_NMS_TOP_N, C.cfg.TEST.RPN_POST_NMS_TOP_N) == (6000, 300)
+    assert (C.cfg.TRAIN.RPN_PRE_NMS_TOP_N, C.cfg.TRAIN.RPN_POST_NMS_TOP_N, C.cfg.TRAIN.FG_THRESH) == (12000, 2000, 0.7)
+    C.cfg_from_list(["TEST.RPN_POST_NMS_TOP_N", "100"])
+    assert C.cfg.TEST.RPN_POST_NMS_TOP_N == 100
+    C.cfg_from_end2end_yml()
+    with pytest.raises(AssertionError):
+        C.cfg_from_list(["TEST.NOPE", "1"])
+
+
+def test_graph_builder_wiring_without_gpu():
+    """The reference's layer names / shapes exist; building the graph needs no device."""
+    from mv3d_tf_b200.networks.factory import get_network
+
+    net = get_network("MV3D_test", bv_channels=36, device="cpu")
+    for name in ("conv5_3", "conv5_3_2", "rpn_cls_prob_reshape", "rpn_bbox_pred", "rois", "roi_data_bv", "roi_data_img",
+                 "pool_5", "pool_5_2", "fc7_1", "fc7_2", "cls_prob", "bbox_pred"):
+        assert net.get_output(name) is not None
+    s = net.param_specs
+    assert s["conv1_1"]["shape"] == (3, 3, 36, 64) and s["conv1_1_2"]["shape"] == (3, 3, 3, 64)
+    assert s["fc6_1"]["shape"] == (25088, 2048) and s["bbox_pred"]["shape"] == (4096, 48)
+    assert s["bbox_pred"]["stddev"] == 0.001 and s["rpn_cls_score"]["shape"] == (1, 1, 512, 8)
+    assert isinstance(net.get_output("rois"), tuple) and len(net.get_output("rois")) == 4
+    with pytest.raises(KeyError):
+        net.feed("nope")
+    n_params = sum(int(np.prod(v["shape"])) + v["shape"][-1] for v in s.values())
+    assert 140e6 < n_params < 150e6  # ~143 M
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "mv3d_tf_b200")
+    bad = []
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.\.?oracle|oracle/", txt, flags=re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
