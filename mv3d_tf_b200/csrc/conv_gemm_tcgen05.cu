@@ -31,6 +31,7 @@ struct GemmParams {
     int k_chunks;       // Cin / KC
     int k_steps_total;  // taps * k_chunks
     int k_steps_per_split;
+    int tiles_m, tiles_n, n_work;  // work item = (n tile fastest, m tile, k split)
     const float* bias;
     int relu;
     __nv_bfloat16* out_hi;
@@ -53,9 +54,16 @@ struct GemmCfg {
     static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kAccCols = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator
+    static constexpr int kTmemCols = 2 * kAccCols;       // double-buffered: MMA of tile i+1 overlaps epilogue of tile i
     static_assert(kStages >= 2, "need at least a double buffer");
+    static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
 
+// Persistent: grid = min(#work items, #SMs); CTA c processes work items c, c+grid, ... where a work item is
+// (n tile fastest, m tile, k split).  Three asynchronous pipelines run concurrently inside a CTA:
+//   TMA producer  --full/empty mbarriers (smem ring, continuous across tiles)-->  MMA issuer
+//   MMA issuer    --tmem_full/tmem_empty mbarriers (2 accumulators)-->            epilogue warps
 template <int BN, int KC, int PASSES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -68,17 +76,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint8_t* stage_base = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
-    uint64_t* accum_bar = empty_bar + Cfg::kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* tmem_full = empty_bar + Cfg::kStages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * kBM;
-    const int k_begin = blockIdx.z * prm.k_steps_per_split;
-    int k_end = k_begin + prm.k_steps_per_split;
-    if (k_end > prm.k_steps_total) k_end = prm.k_steps_total;
-    const int n_k = k_end - k_begin;  // host guarantees >= 1
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -91,11 +94,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -103,139 +109,171 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    const int tiles_n = prm.tiles_n, tiles_m = prm.tiles_m;
+    const int n_work = prm.n_work;
+
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int i = 0; i < n_k; ++i) {
-                const int s = i % Cfg::kStages;
-                const uint32_t ph = (i / Cfg::kStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int ks = k_begin + i;
-                const int tap = ks / prm.k_chunks;
-                const int c0 = (ks - tap * prm.k_chunks) * KC;
-                int shift = 0;
-                if (prm.taps == 9) shift = (tap / 3 - 1) * prm.Wp + (tap % 3 - 1);
-                uint8_t* st = stage_base + s * Cfg::kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                tma_load_2d(st, &map_a_hi, &full_bar[s], c0, m0 + shift);
-                tma_load_2d(st + Cfg::kABytes, &map_w_hi, &full_bar[s], tap * prm.Cin + c0, n0);
-                if (PASSES == 3) {
-                    tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &map_a_lo, &full_bar[s], c0, m0 + shift);
-                    tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &map_w_lo, &full_bar[s], tap * prm.Cin + c0, n0);
+            int it = 0;  // smem ring position, continuous across work items
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int n0 = (w % tiles_n) * BN;
+                const int r = w / tiles_n;
+                const int m0 = (r % tiles_m) * kBM;
+                const int k_begin = (r / tiles_m) * prm.k_steps_per_split;
+                const int k_end = min(k_begin + prm.k_steps_per_split, prm.k_steps_total);
+                for (int ks = k_begin; ks < k_end; ++ks, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int tap = ks / prm.k_chunks;
+                    const int c0 = (ks - tap * prm.k_chunks) * KC;
+                    int shift = 0;
+                    if (prm.taps == 9) shift = (tap / 3 - 1) * prm.Wp + (tap % 3 - 1);
+                    uint8_t* st = stage_base + s * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    tma_load_2d(st, &map_a_hi, &full_bar[s], c0, m0 + shift);
+                    tma_load_2d(st + Cfg::kABytes, &map_w_hi, &full_bar[s], tap * prm.Cin + c0, n0);
+                    if (PASSES == 3) {
+                        tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &map_a_lo, &full_bar[s], c0, m0 + shift);
+                        tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &map_w_lo, &full_bar[s], tap * prm.Cin + c0,
+                                    n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
-        for (int i = 0; i < n_k; ++i) {
-            const int s = i % Cfg::kStages;
-            const uint32_t ph = (i / Cfg::kStages) & 1;
-            mbar_wait(&full_bar[s], ph);
+        int it = 0, tl = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
+            const int r = w / tiles_n;
+            const int k_begin = (r / tiles_m) * prm.k_steps_per_split;
+            const int k_end = min(k_begin + prm.k_steps_per_split, prm.k_steps_total);
+            const int acc = tl & 1;
+            const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+            mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t a_hi = smem_u32(stage_base + s * Cfg::kStageBytes);
-                const uint32_t w_hi = a_hi + Cfg::kABytes;
-                const uint32_t a_lo = w_hi + Cfg::kBBytes;
-                const uint32_t w_lo = a_lo + Cfg::kABytes;
+            for (int ks = k_begin; ks < k_end; ++ks, ++it) {
+                const int s = it % Cfg::kStages;
+                const uint32_t ph = (it / Cfg::kStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_hi = smem_u32(stage_base + s * Cfg::kStageBytes);
+                    const uint32_t w_hi = a_hi + Cfg::kABytes;
+                    const uint32_t a_lo = w_hi + Cfg::kBBytes;
+                    const uint32_t w_lo = a_lo + Cfg::kABytes;
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                    const uint32_t koff = k * 32;  // 16 bf16 along K inside the swizzled row
-                    const uint64_t da = make_kmajor_desc(a_hi + koff, Cfg::kRowBytes);
-                    const uint64_t db = make_kmajor_desc(w_hi + koff, Cfg::kRowBytes);
-                    mma_bf16_ss(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                    if (PASSES == 3) {
-                        const uint64_t dal = make_kmajor_desc(a_lo + koff, Cfg::kRowBytes);
-                        const uint64_t dbl = make_kmajor_desc(w_lo + koff, Cfg::kRowBytes);
-                        mma_bf16_ss(tmem_base, dal, db, idesc, 1u);
-                        mma_bf16_ss(tmem_base, da, dbl, idesc, 1u);
+                    for (int k = 0; k < KC / 16; ++k) {
+                        const uint32_t koff = k * 32;  // 16 bf16 along K inside the swizzled row
+                        const uint64_t da = make_kmajor_desc(a_hi + koff, Cfg::kRowBytes);
+                        const uint64_t db = make_kmajor_desc(w_hi + koff, Cfg::kRowBytes);
+                        mma_bf16_ss(d_tmem, da, db, idesc, (ks > k_begin || k > 0) ? 1u : 0u);
+                        if (PASSES == 3) {
+                            const uint64_t dal = make_kmajor_desc(a_lo + koff, Cfg::kRowBytes);
+                            const uint64_t dbl = make_kmajor_desc(w_lo + koff, Cfg::kRowBytes);
+                            mma_bf16_ss(d_tmem, dal, db, idesc, 1u);
+                            mma_bf16_ss(d_tmem, da, dbl, idesc, 1u);
+                        }
                     }
+                    mma_commit(&empty_bar[s]);                       // frees the smem slot when these MMAs retire
+                    if (ks == k_end - 1) mma_commit(&tmem_full[acc]);  // accumulator complete
                 }
-                mma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
-                if (i == n_k - 1) mma_commit(accum_bar);   // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
-        const long long p = (long long)m0 + row;
-        bool in_range = p < prm.M;
-        bool halo = false;
-        long long dense_row = p;
-        if (prm.Hp > 0) {
-            const int wp = (int)(p % prm.Wp);
-            const long long t = p / prm.Wp;
-            const int hp = (int)(t % prm.Hp);
-            const long long b = t / prm.Hp;
-            halo = (wp == 0) || (hp == prm.Hp - 1);
-            dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
-        }
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr_row = tmem_base + (uint32_t(q * 32) << 16);
+        int tl = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
+            const int n0 = (w % tiles_n) * BN;
+            const int m0 = ((w / tiles_n) % tiles_m) * kBM;
+            const int acc = tl & 1;
+            const long long p = (long long)m0 + row;
+            const bool in_range = p < prm.M;
+            bool halo = false;
+            long long dense_row = p;
+            if (prm.Hp > 0) {
+                const int wp = (int)(p % prm.Wp);
+                const long long t = p / prm.Wp;
+                const int hp = (int)(t % prm.Hp);
+                const long long b = t / prm.Hp;
+                halo = (wp == 0) || (hp == prm.Hp - 1);
+                dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
+            }
+            mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr_row = tmem_base + acc * Cfg::kAccCols + (uint32_t(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t v[32];
-            __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
-            tmem_ld_32x32(taddr_row + c, v);
-            tmem_ld_wait();
-            if (!in_range) continue;
-            const int col0 = n0 + c;
-            if (col0 >= prm.N) continue;
-            if (prm.split_k > 1) {
-                if (halo && prm.f32_dense) continue;
-                float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
+                tmem_ld_32x32(taddr_row + c, v);
+                tmem_ld_wait();
+                if (c + 32 >= BN) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                if (!in_range) continue;
+                const int col0 = n0 + c;
+                if (col0 >= prm.N) continue;
+                if (prm.split_k > 1) {
+                    if (halo) continue;
+                    float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < prm.N) atomicAdd(o + j, halo ? 0.f : __uint_as_float(v[j]));
-                continue;
-            }
-            float f[32];
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
+                    continue;
+                }
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(v[j]);
-                if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
-                if (prm.relu) x = fmaxf(x, 0.f);
-                f[j] = halo ? 0.f : x;
-            }
-            const bool full = (col0 + 32 <= prm.N);
-            if (prm.out_hi != nullptr) {
-                __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
-                __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
-                if (full && (prm.ld_out % 8 == 0)) {
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
+                    if (prm.relu) x = fmaxf(x, 0.f);
+                    f[j] = halo ? 0.f : x;
+                }
+                const bool full = (col0 + 32 <= prm.N);
+                if (prm.out_hi != nullptr) {
+                    __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
+                    __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
+                    if (full && (prm.ld_out % 8 == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint32_t ph4[4], pl4[4];
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t ph4[4], pl4[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(f[j + 2 * e], h0, l0);
-                            split_bf16(f[j + 2 * e + 1], h1, l1);
-                            ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-                            pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                            for (int e = 0; e < 4; ++e) {
+                                __nv_bfloat16 h0, l0, h1, l1;
+                                split_bf16(f[j + 2 * e], h0, l0);
+                                split_bf16(f[j + 2 * e + 1], h1, l1);
+                                ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+                                pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                            }
+                            *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                            if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
                         }
-                        *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
-                        if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
-                    }
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
-                        __nv_bfloat16 h, l;
-                        split_bf16(f[j], h, l);
-                        oh[j] = h;
-                        if (ol) ol[j] = l;
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
+                            __nv_bfloat16 h, l;
+                            split_bf16(f[j], h, l);
+                            oh[j] = h;
+                            if (ol) ol[j] = l;
+                        }
                     }
                 }
-            }
-            if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
-                float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
-                if (full && (prm.ld_f32 % 4 == 0)) {
+                if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
+                    float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+                    if (full && (prm.ld_f32 % 4 == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
+                    }
                 }
             }
         }
@@ -244,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -325,7 +363,18 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
         if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
         attr_set = true;
     }
-    dim3 grid(ceil_div(d->N, BN), ceil_div(d->M, kBM), split);
+    p.tiles_n = ceil_div(d->N, BN);
+    p.tiles_m = ceil_div(d->M, kBM);
+    const long long n_work = (long long)p.tiles_n * p.tiles_m * split;
+    if (n_work > 0x7fffffffLL) return MV3D_ERR_ARG;
+    p.n_work = (int)n_work;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int grid = p.n_work < n_sm ? p.n_work : n_sm;
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;

@@ -105,16 +105,23 @@ __global__ void roi_pool_fwd_kernel(RoiViews views, int R, const int* __restrict
 
 // Backward = scatter-add of top_diff through argmax (equivalent to the reference's gather over all rois,
 // roi_pooling_op_gpu.cu.cc:114-190; fp32 sum order differs -> compare at 1e-5).  bottom_diff is zeroed first.
+// The reference only visits pixels inside [roi_start, roi_end] (roi_pooling_op.cc:398-409), so a malformed ROI
+// (end < start, pooled as 1x1 in the forward pass) receives no gradient -- reproduced by the bounds test below.
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ top_diff, const int* __restrict__ argmax,
                                     const float* __restrict__ rois, long long total, int per_roi, long long img_elems,
-                                    int batch_size, float* __restrict__ bottom_diff) {
+                                    int batch_size, int W, int C, float scale, float* __restrict__ bottom_diff) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int a = argmax[i];
         if (a < 0) continue;
         const int n = (int)(i / per_roi);
-        const int b = (int)rois[(size_t)n * 5];
+        const float* roi = rois + (size_t)n * 5;
+        const int b = (int)roi[0];
         if (b < 0 || b >= batch_size) continue;
+        const int pix = a / C, w = pix % W, h = pix / W;
+        const int rsw = (int)roundf(roi[1] * scale), rsh = (int)roundf(roi[2] * scale);
+        const int rew = (int)roundf(roi[3] * scale), reh = (int)roundf(roi[4] * scale);
+        if (!(w >= rsw && w <= rew && h >= rsh && h <= reh)) continue;
         atomicAdd(bottom_diff + (size_t)b * img_elems + a, top_diff[i]);
     }
 }
@@ -173,7 +180,6 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_backward(
     const float* d_top_diff, float spatial_scale, int batch_size, int num_rois, int height, int width, int channels,
     int pooled_height, int pooled_width, const float* d_bottom_rois, float* d_bottom_diff, const int* d_argmax_data,
     void* stream) {
-    (void)spatial_scale;
     MV3D_REQUIRE(batch_size > 0 && num_rois >= 0 && height > 0 && width > 0 && channels > 0 && d_bottom_diff);
     cudaStream_t s = (cudaStream_t)stream;
     const long long img = (long long)height * width * channels;
@@ -186,7 +192,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_backward(
     long long g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     roi_pool_bwd_kernel<<<(int)g, 256, 0, s>>>(d_top_diff, d_argmax_data, d_bottom_rois, total, per_roi, img, batch_size,
-                                              d_bottom_diff);
+                                              width, channels, spatial_scale, d_bottom_diff);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -124,15 +124,17 @@ def test_proposal_decode_golden(golden_dir, oracle):
     fin = np.isfinite(g["p3d"])
     assert np.array_equal(fin, np.isfinite(p3d))
     assert _ulp(p3d[fin], g["p3d"][fin]).max() <= 2          # np.exp vs device exp
+    # numpy's SIMD float32 exp is not correctly rounded (it differs from the device's exp-in-double on ~35 % of
+    # l/w/h values by 1-2 ulp), so the INTEGER outputs are the exact targets: they may only differ on a row whose
+    # float inputs differ AND whose pre-floor value sits next to a 0.1 m bin edge (expected count here: 0).
     same = _ulp(np.nan_to_num(p3d), np.nan_to_num(g["p3d"])).max(axis=1) == 0
-    assert same.mean() > 0.9
     pbv_ref = oracle.clip_boxes(g["pbv"].copy(), g["im_info"][0, :2])
-    assert np.array_equal(st["pbv"].cpu().numpy()[same], pbv_ref[same], equal_nan=True)
-    assert np.array_equal(st["pimg"].cpu().numpy()[same], g["pimg"][same])
-    # rows whose float inputs differ by an ulp may only differ in an integer output next to a bin edge
-    diff_rows = np.where(~same)[0]
-    bad = [i for i in diff_rows if not np.array_equal(st["pbv"].cpu().numpy()[i], pbv_ref[i], equal_nan=True)]
-    assert len(bad) <= max(2, len(diff_rows) // 20), (len(bad), len(diff_rows))
+    pbv, pimg = st["pbv"].cpu().numpy(), st["pimg"].cpu().numpy()
+    assert np.array_equal(pbv[same], pbv_ref[same], equal_nan=True)
+    assert np.array_equal(pimg[same], g["pimg"][same])
+    bad_bv = int((~((pbv == pbv_ref) | (np.isnan(pbv) & np.isnan(pbv_ref))).all(axis=1)).sum())
+    bad_img = int((pimg != g["pimg"]).any(axis=1).sum())
+    assert bad_bv <= 2 and bad_img <= 2, (bad_bv, bad_img)
 
 
 @pytest.mark.parametrize("key", ["TEST", "TRAIN"])
