@@ -232,10 +232,12 @@ def main():
     dev_frames = [(torch.from_numpy(p).cuda(), torch.from_numpy(i).cuda()) for p, i in frames]
     pin_frames = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(i).pin_memory()) for p, i in frames]
 
+    precise = args.mode == "precise"
+
     def step_device(i):
         pts, img = dev_frames[i % n_frames]
-        bv = raster(pts)
-        return net.run(fetch, {net.lidar_bv_data: bv[None], net.image_data: img, net.im_info: im_info, net.calib: calib})
+        bv = raster.to_pad(pts, precise=precise)  # LiDAR -> BEV directly in the trunk's input layout
+        return net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: calib})
 
     host_out = None
 
@@ -244,9 +246,8 @@ def main():
         pts_h, img_h = pin_frames[i % n_frames]
         pts = pts_h.cuda(non_blocking=True)
         img = img_h.cuda(non_blocking=True)
-        bv = raster(pts)
-        outs = net.run(fetch, {net.lidar_bv_data: bv[None], net.image_data: img, net.im_info: im_info,
-                               net.calib: calib})
+        bv = raster.to_pad(pts, precise=precise)
+        outs = net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: calib})
         if host_out is None:
             host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
         for h, o in zip(host_out, outs):

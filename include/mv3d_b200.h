@@ -46,14 +46,19 @@ const char* mv3d_last_cuda_error_string(void);
  *                            (read_lidar.py:80-83; float64 compare)
  *   res, fwd0, fwd1, side0, side1, height0 : the scalars of the reference call, as float32
  *   xoff = int(floor(side0/res)), yoff = int(floor(fwd1/res))   (read_lidar.py:102-103)
- *   Optional second output for the conv trunk (may be NULL): d_pad_hi/d_pad_lo, the same raster as
- *   a zero-haloed bf16 hi/lo pair of shape (H+1, W+1, c_pad) -- see mv3d_pad_nhwc.
+ *   mv3d_bev_raster_pad writes the same raster directly in the conv trunk's input layout instead:
+ *   a zero-haloed bf16 hi/lo pair of shape (H+1, W+1, c_pad) (see mv3d_pad_nhwc; d_pad_lo may be NULL),
+ *   saving the float32 map's write and re-read when the BEV only feeds the network.
  * ------------------------------------------------------------------------------------------- */
 size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices);
 int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W, int C,
                     int nslices, const double* h_slice_lo, const double* h_slice_hi, float res, float fwd0,
                     float fwd1, float side0, float side1, float height0, int xoff, int yoff, void* d_workspace,
                     size_t workspace_bytes, void* stream);
+int mv3d_bev_raster_pad(const float* d_points, int n_points, int point_stride, void* d_pad_hi, void* d_pad_lo,
+                        int c_pad, int H, int W, int C, int nslices, const double* h_slice_lo,
+                        const double* h_slice_hi, float res, float fwd0, float fwd1, float side0, float side1,
+                        float height0, int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (iii) NMS.
@@ -170,8 +175,8 @@ typedef struct {
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
 
 /* HWIO float32 weights (kh,kw,Cin,Cout) (network.py:119) -> bf16 hi/lo (Cout, kh*kw*cin_pad), K-major.
- * k_perm (optional, device, length kh*kw*Cin ints): source k index for each destination k (used to fold
- * the reference's NHWC->NCHW flatten before fc6, network.py:381, into the weight). */
+ * (The reference's NHWC->NCHW flatten before fc6, network.py:381, is folded into the weight by permuting
+ * its rows on the caller's side before packing.) */
 int mv3d_pack_weights(const float* d_w_hwio, int taps, int cin, int cout, int cin_pad, void* d_w_hi, void* d_w_lo,
                       void* stream);
 /* (B,H,W,C) float32 NHWC -> PAD bf16 hi/lo (B,H+1,W+1,c_pad), halos and channel padding zeroed. */

@@ -19,7 +19,9 @@ constexpr int kRasterThreads = 256;
 
 struct RasterGeom {
     int H, W, C, nslices;
-    int tiles_x, tiles_y;
+    int pad;          // 0: float32 (H,W,C) output; 1: PAD bf16 output (H+1, W+1, c_pad), pixel (r,c) at [r][c+1]
+    int Hout, Wout, c_pad;
+    int tiles_x, tiles_y;  // 16x16 tiles over the OUTPUT grid
     float res, fwd0, fwd1, side0, side1, h0;
     int xoff, yoff;
     double lo[kMaxSlices];
@@ -33,7 +35,9 @@ __device__ __forceinline__ bool point_cell(const RasterGeom& g, float x, float y
     row = (int)__fdiv_rn(-x, g.res) + g.yoff;                                       // :97,103
     if (row < 0) row += g.H;  // numpy negative-index wrap
     if (col < 0) col += g.W;
-    return row >= 0 && row < g.H && col >= 0 && col < g.W;  // (beyond the array the reference raises)
+    if (!(row >= 0 && row < g.H && col >= 0 && col < g.W)) return false;  // (beyond the array the reference raises)
+    col += g.pad;  // position in the output grid
+    return true;
 }
 
 __global__ void raster_count_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
@@ -100,7 +104,8 @@ __global__ void raster_scatter_kernel(const float* __restrict__ pts, int n, int 
 // One CTA per tile.  smem: winner table [256 cells][nslices] (point index + 1, 0 = empty) + top winner [256].
 __global__ void __launch_bounds__(kRasterThreads)
 raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, const int* __restrict__ offset,
-                   const int* __restrict__ sorted_idx, float* __restrict__ top) {
+                   const int* __restrict__ sorted_idx, float* __restrict__ top, __nv_bfloat16* __restrict__ pad_hi,
+                   __nv_bfloat16* __restrict__ pad_lo) {
     extern __shared__ int tab[];
     const int ns = g.nslices;
     int* top_winner = tab + kTile * kTile * ns;
@@ -134,23 +139,59 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
     }
     __syncthreads();
 
-    const int C = g.C;
-    const int cols = min(kTile, g.W - col0);
-    const int run = cols * C;  // contiguous floats of one output row inside this tile
-    for (int r = 0; r < kTile && row0 + r < g.H; ++r) {
-        float* out = top + ((size_t)(row0 + r) * g.W + col0) * C;
-        for (int j = threadIdx.x; j < run; j += blockDim.x) {
-            const int cl = j / C, ch = j - cl * C;
-            const int cell = r * kTile + cl;
-            float v = 0.f;
-            if (ch == C - 1) {
-                const int w = top_winner[cell];
-                if (w) v = pts[(size_t)(w - 1) * stride + 3];                              // :113
-            } else if (ch < ns) {
-                const int w = tab[cell * ns + ch];
-                if (w) v = __fsub_rn(pts[(size_t)(w - 1) * stride + 2], g.h0);             // :106,110
+    auto value = [&](int cell, int ch) -> float {
+        if (ch == g.C - 1) {
+            const int w = top_winner[cell];
+            return w ? pts[(size_t)(w - 1) * stride + 3] : 0.f;                                   // :113
+        }
+        if (ch < ns) {
+            const int w = tab[cell * ns + ch];
+            return w ? __fsub_rn(pts[(size_t)(w - 1) * stride + 2], g.h0) : 0.f;                  // :106,110
+        }
+        return 0.f;
+    };
+    const int cols = min(kTile, g.Wout - col0);
+    if (g.pad) {
+        // PAD bf16 hi/lo: 8 channels (16 B) per thread and plane; halo cells hold no points -> zeros
+        const int vpc = g.c_pad / 8;
+        const int run = cols * vpc;
+        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
+            const size_t base = ((size_t)(row0 + r) * g.Wout + col0) * g.c_pad;
+            for (int j = threadIdx.x; j < run; j += blockDim.x) {
+                const int cl = j / vpc, v8 = j - cl * vpc;
+                const int cell = r * kTile + cl;
+                __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int ch = v8 * 8 + e;
+                    split_bf16(ch < g.C ? value(cell, ch) : 0.f, hi[e], lo[e]);
+                }
+                *reinterpret_cast<uint4*>(pad_hi + base + (size_t)cl * g.c_pad + v8 * 8) = *reinterpret_cast<uint4*>(hi);
+                if (pad_lo)
+                    *reinterpret_cast<uint4*>(pad_lo + base + (size_t)cl * g.c_pad + v8 * 8) = *reinterpret_cast<uint4*>(lo);
             }
-            out[j] = v;
+        }
+    } else if (g.C % 4 == 0) {
+        const int vpc = g.C / 4;
+        const int run = cols * vpc;
+        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
+            float* out = top + ((size_t)(row0 + r) * g.Wout + col0) * g.C;
+            for (int j = threadIdx.x; j < run; j += blockDim.x) {
+                const int cl = j / vpc, v4 = j - cl * vpc;
+                const int cell = r * kTile + cl;
+                const float4 v = make_float4(value(cell, v4 * 4), value(cell, v4 * 4 + 1), value(cell, v4 * 4 + 2),
+                                             value(cell, v4 * 4 + 3));
+                *reinterpret_cast<float4*>(out + (size_t)cl * g.C + v4 * 4) = v;
+            }
+        }
+    } else {
+        const int run = cols * g.C;  // contiguous floats of one output row inside this tile
+        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
+            float* out = top + ((size_t)(row0 + r) * g.Wout + col0) * g.C;
+            for (int j = threadIdx.x; j < run; j += blockDim.x) {
+                const int cl = j / g.C, ch = j - cl * g.C;
+                out[j] = value(r * kTile + cl, ch);
+            }
         }
     }
 }
@@ -169,24 +210,20 @@ static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, siz
 
 using namespace mv3d;
 
-extern "C" __attribute__((visibility("default"))) size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W, int nslices) {
-    (void)nslices;
-    size_t a, b, c, d;
-    const int n_tiles = ceil_div(H, kTile) * ceil_div(W, kTile);
-    return raster_ws_layout(n_points, n_tiles, &a, &b, &c, &d);
-}
-
-extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster(const float* d_points, int n_points, int point_stride, float* d_top, int H, int W,
-                               int C, int nslices, const double* h_lo, const double* h_hi, float res, float fwd0,
-                               float fwd1, float side0, float side1, float height0, int xoff, int yoff,
-                               void* d_workspace, size_t workspace_bytes, void* stream) {
-    MV3D_REQUIRE(d_top && H > 0 && W > 0 && C > 0 && n_points >= 0 && point_stride >= 4);
+static int raster_impl(const float* d_points, int n_points, int point_stride, float* d_top, void* d_pad_hi,
+                       void* d_pad_lo, int c_pad, int H, int W, int C, int nslices, const double* h_lo,
+                       const double* h_hi, float res, float fwd0, float fwd1, float side0, float side1, float height0,
+                       int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream) {
+    const int pad = d_pad_hi ? 1 : 0;
+    MV3D_REQUIRE((d_top || d_pad_hi) && H > 0 && W > 0 && C > 0 && n_points >= 0 && point_stride >= 4);
     MV3D_REQUIRE(n_points == 0 || d_points);
     MV3D_REQUIRE(nslices >= 0 && nslices <= kMaxSlices && nslices <= C && (nslices == 0 || (h_lo && h_hi)));
     MV3D_REQUIRE(n_points < (1 << 30));
+    MV3D_REQUIRE(!pad || (c_pad >= C && c_pad % 8 == 0));
     RasterGeom g;
     g.H = H; g.W = W; g.C = C; g.nslices = nslices;
-    g.tiles_x = ceil_div(W, kTile); g.tiles_y = ceil_div(H, kTile);
+    g.pad = pad; g.Hout = H + pad; g.Wout = W + pad; g.c_pad = c_pad;
+    g.tiles_x = ceil_div(g.Wout, kTile); g.tiles_y = ceil_div(g.Hout, kTile);
     g.res = res; g.fwd0 = fwd0; g.fwd1 = fwd1; g.side0 = side0; g.side1 = side1; g.h0 = height0;
     g.xoff = xoff; g.yoff = yoff;
     for (int i = 0; i < kMaxSlices; ++i) { g.lo[i] = i < nslices ? h_lo[i] : 0.0; g.hi[i] = i < nslices ? h_hi[i] : 0.0; }
@@ -212,7 +249,34 @@ extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster(const floa
         e = cudaFuncSetAttribute(raster_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
     }
-    raster_tile_kernel<<<n_tiles, kRasterThreads, smem, s>>>(d_points, point_stride, g, offset, sorted, d_top);
+    raster_tile_kernel<<<n_tiles, kRasterThreads, smem, s>>>(d_points, point_stride, g, offset, sorted, d_top,
+                                                           (__nv_bfloat16*)d_pad_hi, (__nv_bfloat16*)d_pad_lo);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t mv3d_bev_raster_workspace_bytes(int n_points, int H, int W,
+                                                                                         int nslices) {
+    (void)nslices;
+    size_t a, b, c, d;
+    const int n_tiles = ceil_div(H + 1, kTile) * ceil_div(W + 1, kTile);  // large enough for both output forms
+    return raster_ws_layout(n_points, n_tiles, &a, &b, &c, &d);
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster(
+    const float* d_points, int n_points, int point_stride, float* d_top, int H, int W, int C, int nslices,
+    const double* h_lo, const double* h_hi, float res, float fwd0, float fwd1, float side0, float side1, float height0,
+    int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream) {
+    MV3D_REQUIRE(d_top != nullptr);
+    return raster_impl(d_points, n_points, point_stride, d_top, nullptr, nullptr, 0, H, W, C, nslices, h_lo, h_hi, res,
+                       fwd0, fwd1, side0, side1, height0, xoff, yoff, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster_pad(
+    const float* d_points, int n_points, int point_stride, void* d_pad_hi, void* d_pad_lo, int c_pad, int H, int W,
+    int C, int nslices, const double* h_lo, const double* h_hi, float res, float fwd0, float fwd1, float side0,
+    float side1, float height0, int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream) {
+    MV3D_REQUIRE(d_pad_hi != nullptr);
+    return raster_impl(d_points, n_points, point_stride, nullptr, d_pad_hi, d_pad_lo, c_pad, H, W, C, nslices, h_lo,
+                       h_hi, res, fwd0, fwd1, side0, side1, height0, xoff, yoff, d_workspace, workspace_bytes, stream);
 }

@@ -15,6 +15,7 @@
 //             warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 // PASSES=3: x = hi + lo (bf16 pair); D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp32 accumulate).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -59,6 +60,99 @@ struct GemmCfg {
     static_assert(kStages >= 2, "need at least a double buffer");
     static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
+
+// Epilogue of one 128 x BN tile, executed by the 4 epilogue warps (TMEM lane quarter q = warp % 4):
+// TMEM -> registers -> bias / ReLU -> bf16 hi/lo split -> PAD layout and/or fp32.  Halo pixels are written as
+// zeros; the accumulator is handed back to the MMA warp as soon as its last chunk is in registers.
+template <int BN, int ACC_COLS>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tmem_base, int acc, int m0, int n0, int q,
+                                              int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl) {
+    const int row = q * 32 + lane;
+    const long long p = (long long)m0 + row;
+    const bool in_range = p < prm.M;
+    bool halo = false;
+    long long dense_row = p;
+    if (prm.Hp > 0) {
+        const int wp = (int)(p % prm.Wp);
+        const long long t = p / prm.Wp;
+        const int hp = (int)(t % prm.Hp);
+        const long long b = t / prm.Hp;
+        halo = (wp == 0) || (hp == prm.Hp - 1);
+        dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
+    }
+    mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + acc * ACC_COLS + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
+        tmem_ld_32x32(taddr_row + c, v);
+        tmem_ld_wait();
+        if (c + 32 >= BN) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!in_range) continue;
+        const int col0 = n0 + c;
+        if (col0 >= prm.N) continue;
+        if (prm.split_k > 1) {
+            if (halo) continue;
+            float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
+            continue;
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
+            if (prm.relu) x = fmaxf(x, 0.f);
+            f[j] = halo ? 0.f : x;
+        }
+        const bool full = (col0 + 32 <= prm.N);
+        if (prm.out_hi != nullptr) {
+            __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
+            __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
+            if (full && (prm.ld_out % 8 == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t ph4[4], pl4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(f[j + 2 * e], h0, l0);
+                        split_bf16(f[j + 2 * e + 1], h1, l1);
+                        ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+                        pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                    if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+                }
+            } else {
+                for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
+                    __nv_bfloat16 h, l;
+                    split_bf16(f[j], h, l);
+                    oh[j] = h;
+                    if (ol) ol[j] = l;
+                }
+            }
+        }
+        if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
+            float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+            if (full && (prm.ld_f32 % 4 == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+                for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
+            }
+        }
+    }
+}
 
 // Persistent: grid = min(#work items, #SMs); CTA c processes work items c, c+grid, ... where a work item is
 // (n tile fastest, m tile, k split).  Three asynchronous pipelines run concurrently inside a CTA:
@@ -186,96 +280,173 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;
         int tl = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = ((w / tiles_n) % tiles_m) * kBM;
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, lane, tmem_full, tmem_empty, tl);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 conv with TAP REUSE.  The three kw taps of one kernel row read the same activation rows displaced by one
+// pixel.  Instead of three 128-row TMA boxes the producer fetches ONE 136-row box (rows m0-1 .. m0+134 of the
+// shifted image row) and the MMA issuer addresses it three times with the descriptor start advanced by kw rows
+// (128 B each).  The tensor core applies the 128B-swizzle XOR to the absolute shared-memory address bits, exactly
+// as TMA did when it wrote the box, so a start displaced by whole rows needs no descriptor base_offset (measured
+// on B200: base_offset = kw gives wrong results, 0 is bit-identical to the three-box kernel).  Activation traffic from L2
+// drops 3x -- the early, L2-bound layers (Cout = 64/128) are bounded by exactly that traffic.
+// Two rings: A entries (one per (cin chunk, kh)) and W entries (one per (cin chunk, kh, kw)).
+// ------------------------------------------------------------------------------------------------
+constexpr int kReuseRows = 136;  // 128 + 2 shifted rows, rounded to the 8-row swizzle group
+
+template <int BN, int PASSES>
+struct ReuseCfg {
+    static constexpr int kOperands = (PASSES == 3) ? 2 : 1;
+    static constexpr int kAPlane = 18 * 1024;                 // 136 rows x 128 B = 17408, padded to 1024 multiple
+    static constexpr int kABoxBytes = kReuseRows * 128;
+    static constexpr int kAEntry = kAPlane * kOperands;
+    static constexpr int kWPlane = BN * 128;
+    static constexpr int kWEntry = kWPlane * kOperands;
+    static constexpr int kNA = (BN <= 64 ? 3 : 2) * (PASSES == 3 ? 1 : 2);
+    static constexpr int kBudget = 200 * 1024;
+    static constexpr int kNWRaw = (kBudget - kNA * kAEntry) / kWEntry;
+    static constexpr int kNW = kNWRaw > 8 ? 8 : kNWRaw;
+    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512;
+    static constexpr int kAccCols = BN < 32 ? 32 : BN;
+    static constexpr int kTmemCols = 2 * kAccCols;
+    static_assert(kNW >= 3, "W ring too shallow");
+    static_assert(kTmemCols <= 512, "TMEM has 512 columns");
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                     const GemmParams prm) {
+    using Cfg = ReuseCfg<BN, PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* w_ring = smem + Cfg::kNA * Cfg::kAEntry;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_ring + Cfg::kNW * Cfg::kWEntry);
+    uint64_t* a_empty = a_full + Cfg::kNA;
+    uint64_t* w_full = a_empty + Cfg::kNA;
+    uint64_t* w_empty = w_full + Cfg::kNW;
+    uint64_t* tmem_full = w_empty + Cfg::kNW;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_w_hi);
+        if (PASSES == 3) {
+            prefetch_tensormap(&map_a_lo);
+            prefetch_tensormap(&map_w_lo);
+        }
+        for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < Cfg::kNW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_n = prm.tiles_n, tiles_m = prm.tiles_m, n_work = prm.n_work;
+    const int n_groups = prm.k_chunks * 3;  // (cin chunk, kh) groups per tile, 3 kw taps each
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ia = 0, iw = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int n0 = (w % tiles_n) * BN;
+                const int m0 = ((w / tiles_n) % tiles_m) * kBM;
+                for (int g = 0; g < n_groups; ++g, ++ia) {
+                    const int chunk = g / 3, kh = g - chunk * 3;
+                    const int c0 = chunk * 64;
+                    const int ea = ia % Cfg::kNA;
+                    mbar_wait(&a_empty[ea], ((ia / Cfg::kNA) & 1) ^ 1);
+                    uint8_t* ab = a_ring + ea * Cfg::kAEntry;
+                    mbar_arrive_expect_tx(&a_full[ea], Cfg::kABoxBytes * Cfg::kOperands);
+                    const int arow = m0 + (kh - 1) * prm.Wp - 1;
+                    tma_load_2d(ab, &map_a_hi, &a_full[ea], c0, arow);
+                    if (PASSES == 3) tma_load_2d(ab + Cfg::kAPlane, &map_a_lo, &a_full[ea], c0, arow);
+                    for (int kw = 0; kw < 3; ++kw, ++iw) {
+                        const int ew = iw % Cfg::kNW;
+                        mbar_wait(&w_empty[ew], ((iw / Cfg::kNW) & 1) ^ 1);
+                        uint8_t* wb = w_ring + ew * Cfg::kWEntry;
+                        mbar_arrive_expect_tx(&w_full[ew], Cfg::kWEntry);
+                        const int kcol = (kh * 3 + kw) * prm.Cin + c0;
+                        tma_load_2d(wb, &map_w_hi, &w_full[ew], kcol, n0);
+                        if (PASSES == 3) tma_load_2d(wb + Cfg::kWPlane, &map_w_lo, &w_full[ew], kcol, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+        int ia = 0, iw = 0, tl = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int acc = tl & 1;
-            const long long p = (long long)m0 + row;
-            const bool in_range = p < prm.M;
-            bool halo = false;
-            long long dense_row = p;
-            if (prm.Hp > 0) {
-                const int wp = (int)(p % prm.Wp);
-                const long long t = p / prm.Wp;
-                const int hp = (int)(t % prm.Hp);
-                const long long b = t / prm.Hp;
-                halo = (wp == 0) || (hp == prm.Hp - 1);
-                dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
-            }
-            mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+            const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+            mbar_wait(&tmem_empty[acc], ((tl >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t taddr_row = tmem_base + acc * Cfg::kAccCols + (uint32_t(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t v[32];
-                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
-                tmem_ld_32x32(taddr_row + c, v);
-                tmem_ld_wait();
-                if (c + 32 >= BN) {  // last chunk is in registers: hand the accumulator back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                }
-                if (!in_range) continue;
-                const int col0 = n0 + c;
-                if (col0 >= prm.N) continue;
-                if (prm.split_k > 1) {
-                    if (halo) continue;
-                    float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+            for (int g = 0; g < n_groups; ++g, ++ia) {
+                const int ea = ia % Cfg::kNA;
+                mbar_wait(&a_full[ea], (ia / Cfg::kNA) & 1);
+                const uint32_t a_hi = smem_u32(a_ring + ea * Cfg::kAEntry);
+                const uint32_t a_lo = a_hi + Cfg::kAPlane;
+                for (int kw = 0; kw < 3; ++kw, ++iw) {
+                    const int ew = iw % Cfg::kNW;
+                    mbar_wait(&w_full[ew], (iw / Cfg::kNW) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t w_hi = smem_u32(w_ring + ew * Cfg::kWEntry);
+                        const uint32_t w_lo = w_hi + Cfg::kWPlane;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
-                    continue;
-                }
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
-                    if (prm.relu) x = fmaxf(x, 0.f);
-                    f[j] = halo ? 0.f : x;
-                }
-                const bool full = (col0 + 32 <= prm.N);
-                if (prm.out_hi != nullptr) {
-                    __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
-                    __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
-                    if (full && (prm.ld_out % 8 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint32_t ph4[4], pl4[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                __nv_bfloat16 h0, l0, h1, l1;
-                                split_bf16(f[j + 2 * e], h0, l0);
-                                split_bf16(f[j + 2 * e + 1], h1, l1);
-                                ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-                                pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t aoff = kw * 128 + k * 32;  // kw rows down, 16 bf16 along K
+                            const uint64_t da = make_kmajor_desc(a_hi + aoff, 128);
+                            const uint64_t db = make_kmajor_desc(w_hi + k * 32, 128);
+                            mma_bf16_ss(d_tmem, da, db, idesc, (g > 0 || kw > 0 || k > 0) ? 1u : 0u);
+                            if (PASSES == 3) {
+                                const uint64_t dal = make_kmajor_desc(a_lo + aoff, 128);
+                                const uint64_t dbl = make_kmajor_desc(w_lo + k * 32, 128);
+                                mma_bf16_ss(d_tmem, dal, db, idesc, 1u);
+                                mma_bf16_ss(d_tmem, da, dbl, idesc, 1u);
                             }
-                            *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
-                            if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
                         }
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
-                            __nv_bfloat16 h, l;
-                            split_bf16(f[j], h, l);
-                            oh[j] = h;
-                            if (ol) ol[j] = l;
-                        }
+                        mma_commit(&w_empty[ew]);
+                        if (kw == 2) mma_commit(&a_empty[ea]);
+                        if (kw == 2 && g == n_groups - 1) mma_commit(&tmem_full[acc]);
                     }
-                }
-                if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
-                    float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
-                    if (full && (prm.ld_f32 % 4 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
-                    }
+                    __syncwarp();
                 }
             }
+        }
+    } else {
+        const int q = warp & 3;
+        int tl = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
+            const int n0 = (w % tiles_n) * BN;
+            const int m0 = ((w / tiles_n) % tiles_m) * kBM;
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, lane, tmem_full, tmem_empty, tl);
         }
     }
     tc_fence_before();
@@ -325,9 +496,72 @@ static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS ? MV3D_OK : MV3D_ERR_DRIVER;
 }
 
+static int num_sms() {
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    return n_sm;
+}
+
+static int tap_reuse_mode() {  // MV3D_TAP_REUSE=0 selects the plain nine-box kernel (A/B comparisons); default on
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("MV3D_TAP_REUSE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+template <int BN, int PASSES>
+static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    using Cfg = ReuseCfg<BN, PASSES>;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    const uint64_t kcols = (uint64_t)9 * d->Cin;
+    int rc;
+    if ((rc = make_map_2d(&ma_hi, d->d_a_hi, d->M, d->Cin, kReuseRows, 64)) != MV3D_OK) return rc;
+    if ((rc = make_map_2d(&mw_hi, d->d_w_hi, d->N, kcols, BN, 64)) != MV3D_OK) return rc;
+    if (PASSES == 3) {
+        if ((rc = make_map_2d(&ma_lo, d->d_a_lo, d->M, d->Cin, kReuseRows, 64)) != MV3D_OK) return rc;
+        if ((rc = make_map_2d(&mw_lo, d->d_w_lo, d->N, kcols, BN, 64)) != MV3D_OK) return rc;
+    } else {
+        ma_lo = ma_hi;
+        mw_lo = mw_hi;
+    }
+    GemmParams p;
+    p.M = d->M; p.N = d->N; p.Cin = d->Cin; p.taps = 9; p.Hp = d->Hp; p.Wp = d->Wp;
+    p.H = d->Hp - 1; p.W = d->Wp - 1;
+    p.k_chunks = d->Cin / 64;
+    p.k_steps_total = 9 * p.k_chunks;
+    p.k_steps_per_split = p.k_steps_total;
+    p.split_k = 1;
+    p.bias = d->d_bias; p.relu = d->relu;
+    p.out_hi = static_cast<__nv_bfloat16*>(d->d_out_hi);
+    p.out_lo = static_cast<__nv_bfloat16*>(d->d_out_lo);
+    p.ld_out = d->ld_out;
+    p.out_f32 = d->d_out_f32; p.ld_f32 = d->ld_f32; p.f32_dense = d->f32_dense;
+    p.tiles_n = ceil_div(d->N, BN);
+    p.tiles_m = ceil_div(d->M, kBM);
+    p.n_work = p.tiles_n * p.tiles_m;
+    auto kern = conv3x3_reuse_kernel<BN, PASSES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    const int grid = p.n_work < num_sms() ? p.n_work : num_sms();
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
 template <int BN, int KC, int PASSES>
 static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, KC, PASSES>;
+    if (KC == 64 && d->taps == 9 && d->split_k <= 1 && tap_reuse_mode() != 0) return launch_reuse<BN, PASSES>(d, stream);
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const uint64_t kcols = (uint64_t)d->taps * d->Cin;
     int rc;
@@ -368,13 +602,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     const long long n_work = (long long)p.tiles_n * p.tiles_m * split;
     if (n_work > 0x7fffffffLL) return MV3D_ERR_ARG;
     p.n_work = (int)n_work;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
-    const int grid = p.n_work < n_sm ? p.n_work : n_sm;
+    const int grid = p.n_work < num_sms() ? p.n_work : num_sms();
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
@@ -384,7 +612,9 @@ template <int KC, int PASSES>
 static int dispatch_bn(const mv3d_gemm_desc* d, cudaStream_t s) {
     const int n = d->N;
     // widest tile that the operand staging affords: 256 columns single pass, 128 in the 3-pass mode
-    if (PASSES == 1 && n > 128) return launch_gemm<256, KC, PASSES>(d, s);
+    if constexpr (PASSES == 1) {
+        if (n > 128) return launch_gemm<256, KC, PASSES>(d, s);
+    }
     if (n > 64) return launch_gemm<128, KC, PASSES>(d, s);
     if (n > 32) return launch_gemm<64, KC, PASSES>(d, s);
     return launch_gemm<32, KC, PASSES>(d, s);

@@ -23,25 +23,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int c
     }
 }
 
-// (B,H,W,C) fp32 -> PAD (B,H+1,W+1,c_pad) bf16 hi/lo.
+// (B,H,W,C) fp32 -> PAD (B,H+1,W+1,c_pad) bf16 hi/lo.  One thread per 8 output channels (16-byte stores).
 __global__ void pad_nhwc_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    const int Hp = H + 1, Wp = W + 1;
-    const long long total = (long long)B * Hp * Wp * c_pad;
+    const int Hp = H + 1, Wp = W + 1, cv = c_pad / 8;
+    const long long total = (long long)B * Hp * Wp * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c_pad);
-        long long r = i / c_pad;
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
         const int wp = (int)(r % Wp);
         r /= Wp;
         const int hp = (int)(r % Hp);
         const int b = (int)(r / Hp);
-        float x = 0.f;
-        if (c < C && wp > 0 && hp < H) x = in[(((long long)b * H + hp) * W + (wp - 1)) * C + c];
-        __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
-        hi[i] = h;
-        if (lo) lo[i] = l;
+        __nv_bfloat16 vh[8], vl[8];
+        const bool inside = wp > 0 && hp < H;
+        const float* src = in + (((long long)b * H + hp) * W + (wp - 1)) * C;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            split_bf16((inside && c < C) ? src[c] : 0.f, vh[e], vl[e]);
+        }
+        *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<uint4*>(vh);
+        if (lo) *reinterpret_cast<uint4*>(lo + i * 8) = *reinterpret_cast<uint4*>(vl);
     }
 }
 
@@ -172,8 +176,8 @@ extern "C" __attribute__((visibility("default"))) int mv3d_pack_weights(const fl
 
 extern "C" __attribute__((visibility("default"))) int mv3d_pad_nhwc(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi, void* d_lo,
                              void* stream) {
-    MV3D_REQUIRE(d_in && d_hi && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C);
-    const long long total = (long long)B * (H + 1) * (W + 1) * c_pad;
+    MV3D_REQUIRE(d_in && d_hi && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C && c_pad % 8 == 0);
+    const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
     pad_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, c_pad,
                                                                              (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
     MV3D_CHECK_LAUNCH();

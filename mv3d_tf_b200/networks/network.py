@@ -222,7 +222,7 @@ class Network(object):
         def run(vals, node):
             x = vals[node.inputs[0]].dense
             assert x.shape[-1] == 2, 'MV3D only ever takes 2-way softmaxes'
-            return Val(dense=K.softmax_pairs(x.contiguous(), 1))
+            return Val(dense=K.softmax_pairs(x, 1))
         return self._node(name, 'softmax', [input], run, channels=input.channels)
 
     @layer
@@ -334,21 +334,58 @@ class Network(object):
             dim, transform = input.channels, None
         self._declare(name, (dim, num_out), 0.001 if name == 'bbox_pred' else 0.01)
 
+        def split_for(M, n_out, k):
+            # few output tiles + long K (weight streaming): split K across CTAs to fill the 148 SMs
+            if self.precise:
+                bn = 128 if n_out > 64 else (64 if n_out > 32 else 32)   # mirrors dispatch_bn in conv_gemm_tcgen05.cu
+            else:
+                bn = 256 if n_out > 128 else (128 if n_out > 64 else (64 if n_out > 32 else 32))
+            ctas = ((M + 127) // 128) * ((n_out + bn - 1) // bn)
+            if k < 2048:
+                return 1
+            return max(1, min(8, 148 // max(1, ctas), k // 512))
+
         def run(vals, node):
+            cached = node.attrs.pop('result', None)
+            if cached is not None:
+                return cached
             v = vals[node.inputs[0]]
             want_vec = any(c in ('fc', 'concat', 'dropout') for c in node.consumers)
             want_f32 = (not want_vec) or node.attrs.get('fetched', False) or \
                 any(c not in ('fc', 'concat', 'dropout') for c in node.consumers)
             M = v.hi.shape[0]
-            split = 1
-            if dim >= 8192:  # weight-streaming GEMM with few output tiles: split K to fill the 148 SMs
-                bn = 128 if self.precise else 256
-                ctas = ((M + 127) // 128) * ((num_out + bn - 1) // bn)
-                split = max(1, min(8, 148 // max(1, ctas)))
+            followers = node.attrs.get('fused_followers', [])
+            if followers:  # sibling heads on the same input (cls_score + bbox_pred): ONE GEMM over concatenated weights
+                key = name + '+' + '+'.join(f.name for f in followers)
+                pw = self._packed.get(key)
+                if pw is None:
+                    ws = [self.params[name]] + [self.params[f.name] for f in followers]
+                    wcat = torch.cat([p['weights'] for p in ws], dim=1).contiguous()
+                    bcat = torch.cat([p['biases'] for p in ws], dim=0).contiguous()
+                    pw = self._packed[key] = K.pack_weights(wcat, bcat)
+                _, _, f32 = K.linear(v.hi, v.lo, pw, relu=False, precise=self.precise, out_bf16=False, out_f32=True,
+                                     split_k=split_for(M, pw.cout, dim))
+                off = num_out
+                for f in followers:
+                    f.attrs['result'] = Val(dense=f32[:, off:off + f.channels])
+                    off += f.channels
+                return Val(dense=f32[:, :num_out])
             hi, lo, f32 = K.linear(v.hi, v.lo, self._weight(name, transform), relu=relu, precise=self.precise,
-                                   out_bf16=want_vec, out_f32=want_f32, split_k=split)
+                                   out_bf16=want_vec, out_f32=want_f32, split_k=split_for(M, num_out, dim))
             return Val(hi=hi, lo=lo, dense=f32)
-        return self._node(name, 'fc', [input], run, channels=num_out)
+        n = self._node(name, 'fc', [input], run, channels=num_out)
+        n.attrs['relu'] = relu
+        # fusion planning: an earlier fc without ReLU fed by the same tensors (directly or through identical concats)
+        if not relu:
+            def src(x):
+                return tuple(id(i) for i in x.inputs) if x.kind == 'concat' else (id(x),)
+            for m in self._program:
+                if m is not n and m.kind == 'fc' and not m.attrs.get('relu', True) and 'fused_into' not in m.attrs \
+                        and src(m.inputs[0]) == src(input):
+                    m.attrs.setdefault('fused_followers', []).append(n)
+                    n.attrs['fused_into'] = m
+                    break
+        return n
 
     @layer
     def concat(self, inputs, axis, name):
@@ -382,7 +419,9 @@ class Network(object):
         vals: Dict[Node, Val] = {}
         for k, v in feed_dict.items():
             node = self.layers[k] if isinstance(k, str) else k
-            if node.name in ('im_info', 'calib', 'keep_prob') or node.name.startswith('gt_'):
+            if isinstance(v, K.PadAct):  # already in the trunk's input layout (BevRasterizer.to_pad)
+                vals[node] = Val(pad=v)
+            elif node.name in ('im_info', 'calib', 'keep_prob') or node.name.startswith('gt_'):
                 vals[node] = Val(extra=v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
             else:
                 t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
@@ -409,5 +448,8 @@ class Network(object):
             if n in need or not isinstance(n, Node):
                 continue
             need.add(n)
-            stack.extend(n.inputs)
+            if 'fused_into' in n.attrs:
+                stack.append(n.attrs['fused_into'])
+            else:
+                stack.extend(n.inputs)
         return need

@@ -43,10 +43,7 @@ class BevRasterizer:
         n = points.shape[0]
         g = self.g
         L = lib()
-        if n > self._ws_points:
-            nbytes = L.mv3d_bev_raster_workspace_bytes(max(n, 1), g["H"], g["W"], g["nslices"])
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
-            self._ws_points = n
+        self._workspace(n, points.device)
         if out is None:
             out = torch.empty(self.shape, dtype=torch.float32, device=points.device)
         res, zres, side, fwd, hr = self.args
@@ -54,6 +51,39 @@ class BevRasterizer:
                                 ptr(g["lo"]), ptr(g["hi"]), res, fwd[0], fwd[1], side[0], side[1], hr[0], g["xoff"],
                                 g["yoff"], ptr(self._ws), self._ws.numel(), current_stream()), "mv3d_bev_raster")
         return out
+
+
+    def _workspace(self, n, device):
+        g = self.g
+        if n > self._ws_points:
+            nbytes = lib().mv3d_bev_raster_workspace_bytes(max(n, 1), g["H"], g["W"], g["nslices"])
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws_points = n
+        return self._ws
+
+    def to_pad(self, clouds, precise: bool = True):
+        """Rasterise one cloud per frame straight into the conv trunk's input layout (kernels.PadAct, bf16 hi/lo,
+        zero halo) -- the float32 map is never materialised."""
+        from ..kernels import BF16, PadAct, pad_channels
+
+        if isinstance(clouds, torch.Tensor):
+            clouds = [clouds]
+        g = self.g
+        cp = pad_channels(g["C"])
+        dev = clouds[0].device
+        hi = torch.empty((len(clouds), g["H"] + 1, g["W"] + 1, cp), dtype=BF16, device=dev)
+        lo = torch.empty_like(hi) if precise else None
+        res, zres, side, fwd, hr = self.args
+        for b, pts in enumerate(clouds):
+            assert pts.is_cuda and pts.dtype == torch.float32 and pts.dim() == 2 and pts.shape[1] >= 4
+            pts = pts.contiguous()
+            ws = self._workspace(pts.shape[0], dev)
+            check(lib().mv3d_bev_raster_pad(ptr(pts), pts.shape[0], pts.shape[1], ptr(hi[b]),
+                                            ptr(lo[b]) if lo is not None else None, cp, g["H"], g["W"], g["C"],
+                                            g["nslices"], ptr(g["lo"]), ptr(g["hi"]), res, fwd[0], fwd[1], side[0],
+                                            side[1], hr[0], g["xoff"], g["yoff"], ptr(ws), ws.numel(),
+                                            current_stream()), "mv3d_bev_raster_pad")
+        return PadAct(hi, lo, len(clouds), g["H"], g["W"], g["C"])
 
 
 def point_cloud_2_top(points, res=0.1, zres=0.3, side_range=(-10., 10.), fwd_range=(-10., 10.),

@@ -63,6 +63,22 @@ def test_raster_duplicates_and_idempotence(oracle):
     assert np.array_equal(a, r(torch.cat([d, d])).cpu().numpy())
 
 
+def test_raster_pad_output_equals_padded_float_raster(oracle):
+    """mv3d_bev_raster_pad == mv3d_pad_nhwc(mv3d_bev_raster): same bf16 hi/lo planes, zero halo, zero pad channels."""
+    from mv3d_tf_b200 import kernels as k
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+
+    for args in ((0.1, 0.3, (-30., 30.), (0., 60.), (-2., 0.4)), (0.1, 0.1, (-40., 40.), (0., 70.), (-2.0, 1.5))):
+        r = BevRasterizer(*args)
+        pts = torch.from_numpy(oracle.synth_points(90000, seed=8)).cuda()
+        top = r(pts)
+        want = k.pad_nhwc(top[None].contiguous(), precise=True)
+        got = r.to_pad(pts, precise=True)
+        assert got.hi.shape == want.hi.shape
+        assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+        assert float((k.unpad_nhwc(got)[0] - top).abs().max()) <= 4.0 * 2.0 ** -17  # hi+lo keeps 16 mantissa bits
+
+
 # ------------------------------------------------------------------ NMS
 def test_nms_golden(golden_dir):
     from mv3d_tf_b200.nms.gpu_nms import cpu_nms

@@ -1,0 +1,57 @@
+"""N>1 host logic on CPU: two gloo ranks shard frames with no data-path collective, and the gathered result
+equals the single-rank result (frame order and content)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _fake_detect(frame_id: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(1000 + frame_id)
+    n = 3 + frame_id % 4
+    return torch.cat([torch.full((n, 1), float(frame_id)), torch.rand((n, 5), generator=g)], dim=1)
+
+
+def _worker(rank, world, port, n_frames, q):
+    from mv3d_tf_b200 import sharding
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.shard_range(n_frames, rank, world)
+    rows = torch.cat([_fake_detect(f) for f in mine]) if len(mine) else torch.zeros((0, 6))
+    parts = sharding.gather_rows(rows)
+    t = sharding.max_over_ranks(1.0 + rank)
+    if rank == 0:
+        q.put((torch.cat(parts), t, [list(sharding.shard_range(n_frames, r, world)) for r in range(world)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [64, 7, 1])
+def test_two_rank_sharding_matches_single_rank(n_frames):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_frames) % 500
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, tmax, shards = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.cat([_fake_detect(f) for f in range(n_frames)])
+    assert torch.equal(got, want)
+    assert tmax == 2.0
+    assert sorted(sum(shards, [])) == list(range(n_frames))
+
+
+def test_shard_range_properties():
+    from mv3d_tf_b200.sharding import shard_range
+
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 4, 8):
+            parts = [list(shard_range(n, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1

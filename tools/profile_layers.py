@@ -43,12 +43,12 @@ def main():
     for i in range(reps):
         if i == 3:
             kernels._run_gemm = traced
-        bv = raster(pts)
-        net.run(fetch, {net.lidar_bv_data: bv[None], net.image_data: img, net.im_info: im_info, net.calib: orc.KITTI_CALIB})
+        bv = raster.to_pad(pts, precise=(mode == "precise"))
+        net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: orc.KITTI_CALIB})
     torch.cuda.synchronize()
     kernels._run_gemm = orig
     n = len(log) // (reps - 3)
-    names = [nd.name for nd in net._program if nd.kind in ("conv", "fc")]
+    names = [nd.name for nd in net._program if nd.kind in ("conv", "fc") and "fused_into" not in nd.attrs]
     rows, tot_ms, tot_fl = [], 0.0, 0.0
     for j in range(n):
         M, N, Kd, taps, split = log[j][:5]
@@ -57,7 +57,8 @@ def main():
         rows.append((names[j] if j < len(names) else "?", M, N, Kd, split, ms, fl / ms / 1e9))
         tot_ms += ms
         tot_fl += fl
-    out = os.path.join(ROOT, "profiles", "layers_%s_%s.md" % (tag, mode))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    out = os.path.join(ROOT, "gpurun_out", "layers_%s_%s.md" % (tag, mode))
     with open(out, "w") as f:
         f.write("# per-layer conv/fc GEMM timing, mode=%s (CUDA events, median of 5 frames; TFLOP/s counts padded "
                 "M,K once -- multiply by 3 for the MMA rate in precise mode)\n\n" % mode)
