@@ -171,8 +171,39 @@ typedef struct {
     float* d_out_f32; int ld_f32; int f32_dense; /* fp32 output; f32_dense=1 drops halo pixels: (B,H,W,ld_f32) */
     int split_k; /* >1: K range split over blockIdx.z, partial sums atomically added into d_out_f32
                     (which the caller zeroed); bias/relu/bf16 outputs are then ignored */
+    /* backward-data epilogue (training): out = (acc + addend) * (mask > 0 ? mask_scale : 0).
+     * d_mask_hi: bf16, same row indexing as d_out_hi with pitch ld_mask -- the forward activation whose ReLU
+     * (and dropout) mask gates this gradient; d_addend_f32: dense float32 (B,H,W,ld_addend) (f32_dense row
+     * indexing) or plain rows when Hp == 0 -- a second gradient path summed in before masking.  NULL = unused. */
+    const void* d_mask_hi; int ld_mask; float mask_scale;
+    const float* d_addend_f32; int ld_addend;
 } mv3d_gemm_desc;
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward-filter GEMM (training):  dW[t, c, n] (+)= sum_p X[p + shift_t, c] * G[p, n].
+ *   Replaces the filter-gradient TensorFlow derives for Network.conv / Network.fc when the reference calls
+ *   tf.train.AdamOptimizer(lr).minimize(loss)  (lib/fast_rcnn/train_mv.py:144-146; ops at network.py:114,395).
+ *   X = the layer's forward input, G = dLoss/d(pre-bias output) with the ReLU mask applied, both bf16 hi/lo in
+ *   the PAD layout (taps == 9, Wp = PAD row width) or plain rows (taps == 1).  d_dw is float32
+ *   (taps, cin, cout) = the reference's HWIO / (in, out) variable layout.  accumulate=1: dW += (row splits use
+ *   red.global.add; caller zeroes once per step); accumulate=0: dW = (single split, plain stores).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int P;        /* rows of X and G: B*Hp*Wp PAD pixels, or plain rows (ROIs) for fc */
+    int Cx, Cg;   /* row pitch in elements (padded channels) of X (16 or multiple of 64) and G (multiple of 64) */
+    int cin, cout;
+    int taps;     /* 9 or 1 */
+    int Wp;
+    int passes;   /* 1 or 3 (bf16 hi/lo split, see mv3d_gemm_desc) */
+    const void* d_x_hi; const void* d_x_lo;
+    const void* d_g_hi; const void* d_g_lo;
+    float* d_dw; int ld_dw; /* ld_dw = 0 -> cout */
+    int accumulate;
+    int split_rows;  /* 0 = automatic */
+    int tap_window;  /* 1: the three kw taps of a kernel row share one displaced X window box; 0: one box per tap */
+} mv3d_wgrad_desc;
+int mv3d_conv_wgrad(const mv3d_wgrad_desc* desc, void* stream);
 
 /* HWIO float32 weights (kh,kw,Cin,Cout) (network.py:119) -> bf16 hi/lo (Cout, kh*kw*cin_pad), K-major.
  * (The reference's NHWC->NCHW flatten before fc6, network.py:381, is folded into the weight by permuting
@@ -193,6 +224,66 @@ int mv3d_softmax_pairs(const float* d_in, int rows, int ld_in, int n_pairs, floa
 /* split-K epilogue: out = act(acc + bias) as bf16 hi/lo and/or fp32. */
 int mv3d_bias_act(const float* d_acc, int M, int N, int ld_acc, const float* d_bias, int relu, void* d_out_hi,
                   void* d_out_lo, int ld_out, float* d_out_f32, int ld_f32, void* stream);
+
+/* =============================================================================================
+ * Training step (BASELINE config 3).  The reference gets its backward pass
+ * from TensorFlow autodiff over the graph of lib/networks/MV3D_train.py and the loss/optimizer of
+ * lib/fast_rcnn/train_mv.py:94-146; these entry points are that backward pass, hand-written.
+ * ============================================================================================= */
+
+/* Backward of Network.max_pool(2,2,2,2,'VALID') (network.py:181-188) fused with the ReLU' of the conv that produced
+ * its input: x = pre-pool activation (PAD, HxW), g = gradient of the pooled map (PAD, H/2 x W/2), out PAD HxW. */
+int mv3d_maxpool2x2_bwd_pad(const void* d_x_hi, const void* d_x_lo, const void* d_g_hi, const void* d_g_lo, int B,
+                            int H, int W, int c_pad, void* d_out_hi, void* d_out_lo, void* stream);
+/* db[n] += sum over rows of (g_hi + g_lo)[row, n]  -- bias gradient of conv / fc (network.py:130,395). */
+int mv3d_bias_grad(const void* d_g_hi, const void* d_g_lo, long long rows, int ld, int n, float* d_db, void* stream);
+/* HWIO / (in,out) float32 weights -> backward-data operand: bf16 hi/lo (cin, taps*cout_pad), taps flipped. */
+int mv3d_pack_weights_dgrad(const float* d_w_hwio, int taps, int cin, int cout, int cout_pad, void* d_w_hi,
+                            void* d_w_lo, void* stream);
+/* dense float32 (B,H,W,C) gradient -> PAD bf16 hi/lo gated by (d_mask_hi > 0) (mask: PAD, same c_pad; may be NULL). */
+int mv3d_pad_nhwc_masked(const float* d_in, int B, int H, int W, int C, int c_pad, const void* d_mask_hi, void* d_hi,
+                         void* d_lo, void* stream);
+/* Network.dropout (network.py:407-409): in place, y = x/keep_prob with probability keep_prob else 0. */
+int mv3d_dropout(void* d_hi, void* d_lo, long long rows, int n, int ld, float keep_prob, unsigned long long seed,
+                 void* stream);
+/* RPN losses + gradients (train_mv.py:94-119, _modified_smooth_l1 :67-84 with sigma).  labels (B,Hf,Wf,A) float32
+ * in {-1,0,1}, targets (B,Hf*Wf*A,6), d_counts (B,2) int32 {#label != -1, #label == 1}.  Gradient out: PAD bf16 hi/lo
+ * (B,Hf+1,Wf+1,c_pad), channels [0,2A) d rpn_cls_score, [2A,8A) d rpn_bbox_pred.  d_loss[0] += rpn_cross_entropy,
+ * d_loss[1] += rpn_loss_box, each the mean over the B frames of the reference's per-frame value. */
+int mv3d_rpn_loss(const float* d_cls_score, const float* d_bbox_pred, const float* d_labels, const float* d_targets,
+                  const int* d_counts, int B, int Hf, int Wf, int A, int c_pad, float sigma, void* d_grad_hi,
+                  void* d_grad_lo, float* d_loss, void* stream);
+/* R-CNN losses + gradients (train_mv.py:121-133).  d_rois (R,5) gives each row's frame; d_frame_counts (B) rows per
+ * frame.  Gradient out: bf16 hi/lo (R,c_pad): [0,2) d cls_score, [2,2+n_bbox) d bbox_pred.  d_loss[0] += cross_entropy,
+ * d_loss[1] += loss_box. */
+int mv3d_rcnn_loss(const float* d_cls_score, int ld_cls, const float* d_bbox_pred, int ld_bbox, const int* d_labels,
+                   const float* d_targets, int n_bbox, const float* d_rois, const int* d_frame_counts, int B, int R,
+                   int c_pad, float sigma, void* d_grad_hi, void* d_grad_lo, float* d_loss, void* stream);
+/* tf.train.AdamOptimizer(lr) with TF-1.0 defaults (train_mv.py:144-146) over a flat parameter buffer; grad_scale
+ * folds in 1/world_size after the data-parallel gradient all-reduce. */
+int mv3d_adam(float* d_theta, const float* d_grad, float* d_m, float* d_v, long long n, float lr, float beta1,
+              float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* anchor_target_layer before its random sub-sampling (lib/rpn_msr/anchor_target_layer_tf.py:93-143,164-165).
+ *   d_anchors (N,4) int32 all shifted anchors, d_anchors3d (N,6) float64 = bv_anchor_to_lidar(anchors)
+ *   d_gt_bv (G,5) / d_gt_3d (G,7) float32.  Outputs: d_max_ov (N) float64 (-1 outside the image), d_argmax (N),
+ *   d_code (N) int8: bits 0-1 = label+1, bit 2 = inside, bit 3 = max_overlap < neg_thr; d_targets (N,6) float32
+ *   (bbox_transform_3d vs the arg-max GT, zeros outside).  d_gt_max_ws: G x 8 bytes scratch. */
+int mv3d_anchor_targets(const int* d_anchors, const double* d_anchors3d, int N, const float* d_gt_bv,
+                        const float* d_gt_3d, int G, float im_h, float im_w, double pos_thr, double neg_thr,
+                        int clobber, double* d_max_ov, int* d_argmax, unsigned long long* d_gt_max_ws,
+                        signed char* d_code, float* d_targets, void* stream);
+/* proposal_target_layer_3d, IoU stage (proposal_target_layer_tf.py:38-44,232-236): candidates = rois ++ GT. */
+int mv3d_roi_overlaps(const float* d_rois_bv, int R, const float* d_gt_bv, int G, double* d_max_ov, int* d_argmax,
+                      void* stream);
+/* proposal_target_layer_3d, output stage (:270-298, :80-92): d_keep (K) indexes the candidates, first n_fg are
+ * foreground; d_proj = 12 floats (P2.R0).Tr on the DEVICE.  Outputs rois_bv (K,5), rois_img (K,5), labels (K) int32,
+ * bbox_targets (K,24*num_classes), rois_3d (K,7); column 0 of the roi blobs = batch_index. */
+int mv3d_proposal_targets(const float* d_rois_bv, const float* d_rois_3d, int R, const float* d_gt_bv,
+                          const float* d_gt_3d, const float* d_gt_corners, int G, const int* d_keep, int K, int n_fg,
+                          const int* d_assign, const float* d_proj, int num_classes, float batch_index,
+                          float* d_out_bv, float* d_out_img, int* d_out_labels, float* d_out_targets, float* d_out_3d,
+                          void* stream);
 
 #ifdef __cplusplus
 }

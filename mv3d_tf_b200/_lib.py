@@ -35,7 +35,17 @@ class GemmDesc(C.Structure):
                 ("d_a_hi", c_void_p), ("d_a_lo", c_void_p), ("d_w_hi", c_void_p), ("d_w_lo", c_void_p),
                 ("d_bias", c_void_p), ("relu", c_int),
                 ("d_out_hi", c_void_p), ("d_out_lo", c_void_p), ("ld_out", c_int),
-                ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int)]
+                ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int),
+                ("d_mask_hi", c_void_p), ("ld_mask", c_int), ("mask_scale", c_float),
+                ("d_addend_f32", c_void_p), ("ld_addend", c_int)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("P", c_int), ("Cx", c_int), ("Cg", c_int), ("cin", c_int), ("cout", c_int), ("taps", c_int),
+                ("Wp", c_int), ("passes", c_int),
+                ("d_x_hi", c_void_p), ("d_x_lo", c_void_p), ("d_g_hi", c_void_p), ("d_g_lo", c_void_p),
+                ("d_dw", c_void_p), ("ld_dw", c_int), ("accumulate", c_int), ("split_rows", c_int),
+                ("tap_window", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/mv3d_b200.h declares
@@ -67,11 +77,31 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     "mv3d_roi_pool_multiview": (c_int, [C.POINTER(RoiView), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mv3d_conv_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "mv3d_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "mv3d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_pad_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_unpad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mv3d_maxpool2x2_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_softmax_pairs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mv3d_maxpool2x2_bwd_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
+    "mv3d_bias_grad": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "mv3d_pack_weights_dgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_pad_nhwc_masked": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "mv3d_dropout": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_int, c_float, C.c_ulonglong, c_void_p]),
+    "mv3d_rpn_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv3d_rcnn_loss": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                               c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv3d_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_longlong, c_float, c_float, c_float, c_float,
+                          c_int, c_float, c_void_p]),
+    "mv3d_anchor_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_float, c_double,
+                                    c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mv3d_roi_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_proposal_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                      c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     "mv3d_bias_act": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_void_p]),
 }
@@ -103,8 +133,11 @@ def lib() -> C.CDLL:
 # kernels launched by one successful call of each entry point (memsets not counted) -- bench.py's gpu_launches
 KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
                     "mv3d_roi_pool_forward": 1, "mv3d_roi_pool_backward": 1, "mv3d_roi_pool_multiview": 1,
-                    "mv3d_conv_gemm": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_unpad_nhwc": 1,
-                    "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1}
+                    "mv3d_conv_gemm": 1, "mv3d_conv_wgrad": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_unpad_nhwc": 1,
+                    "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1,
+                    "mv3d_maxpool2x2_bwd_pad": 1, "mv3d_bias_grad": 1, "mv3d_pack_weights_dgrad": 1,
+                    "mv3d_pad_nhwc_masked": 1, "mv3d_dropout": 1, "mv3d_rpn_loss": 1, "mv3d_rcnn_loss": 1,
+                    "mv3d_adam": 1, "mv3d_anchor_targets": 2, "mv3d_roi_overlaps": 1, "mv3d_proposal_targets": 1}
 _launches = 0
 
 

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mv3d {
 
@@ -42,6 +43,11 @@ struct GemmParams {
     int ld_f32;
     int f32_dense;
     int split_k;
+    const __nv_bfloat16* mask_hi;  // backward-data epilogue: gate by (mask > 0), see mv3d_gemm_desc
+    int ld_mask;
+    float mask_scale;
+    const float* addend;
+    int ld_addend;
 };
 
 template <int BN, int KC, int PASSES>
@@ -114,6 +120,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
             f[j] = halo ? 0.f : x;
         }
         const bool full = (col0 + 32 <= prm.N);
+        if (prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
+            const float* ad = prm.addend + dense_row * prm.ld_addend + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < prm.N) f[j] += __ldg(ad + j);
+        }
+        if (prm.mask_hi != nullptr && !halo) {  // ReLU / dropout gate of the forward activation
+            const __nv_bfloat16* mk = prm.mask_hi + p * prm.ld_mask + col0;
+            if (full && (prm.ld_mask % 8 == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mk + j));
+                    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                        const uint32_t a = mw[e] & 0xFFFFu, b = mw[e] >> 16;
+                        f[j + 2 * e] = (a != 0 && a < 0x8000u) ? f[j + 2 * e] * prm.mask_scale : 0.f;
+                        f[j + 2 * e + 1] = (b != 0 && b < 0x8000u) ? f[j + 2 * e + 1] * prm.mask_scale : 0.f;
+                    }
+                }
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < prm.N) f[j] = (__bfloat162float(mk[j]) > 0.f) ? f[j] * prm.mask_scale : 0.f;
+            }
+        }
         if (prm.out_hi != nullptr) {
             __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
             __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
@@ -460,52 +492,6 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 2-D bf16 row-major (rows, cols) matrix, box (box_rows, box_cols), swizzle matching box_cols*2 bytes.
-static int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                       uint32_t box_cols) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return MV3D_ERR_DRIVER;
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                            : box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? MV3D_OK : MV3D_ERR_DRIVER;
-}
-
-static int num_sms() {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
-    return n_sm;
-}
-
 static int tap_reuse_mode() {  // MV3D_TAP_REUSE=0 selects the plain nine-box kernel (A/B comparisons); default on
     static int mode = -1;
     if (mode < 0) {
@@ -542,6 +528,8 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_lo = static_cast<__nv_bfloat16*>(d->d_out_lo);
     p.ld_out = d->ld_out;
     p.out_f32 = d->d_out_f32; p.ld_f32 = d->ld_f32; p.f32_dense = d->f32_dense;
+    p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
+    p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -589,6 +577,8 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_lo = static_cast<__nv_bfloat16*>(d->d_out_lo);
     p.ld_out = d->ld_out;
     p.out_f32 = d->d_out_f32; p.ld_f32 = d->ld_f32; p.f32_dense = d->f32_dense;
+    p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
+    p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
@@ -636,6 +626,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(d->d_out_hi || d->d_out_f32);
     MV3D_REQUIRE(d->split_k <= 1 || d->d_out_f32);
     MV3D_REQUIRE(!d->f32_dense || d->Hp > 0);
+    MV3D_REQUIRE(d->split_k <= 1 || (!d->d_mask_hi && !d->d_addend_f32));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool kc64 = (d->Cin % 64 == 0);
     if (d->passes == 3) return kc64 ? dispatch_bn<64, 3>(d, s) : dispatch_bn<16, 3>(d, s);

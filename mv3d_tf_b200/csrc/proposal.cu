@@ -11,6 +11,7 @@
 //   7 gather   : blob_bv / blob_img / blob_3d rows
 // All float arithmetic mirrors numpy's dtype pipeline; compiled with --fmad=false.
 #include "common.cuh"
+#include "geom.cuh"
 
 extern "C" size_t mv3d_nms_workspace_bytes(int n_boxes);
 extern "C" int mv3d_nms(const float*, int, int, const int*, double, int, int, int*, int*, void*, size_t, void*);
@@ -51,12 +52,6 @@ __device__ __forceinline__ float clip_np(float v, float hi) {
     if (v != v) return v;
     v = v < hi ? v : hi;
     return v > 0.f ? v : 0.f;
-}
-
-// C cast double -> int32 as x86 cvttsd2si does it (numpy astype(int32)): out of range / NaN -> INT_MIN.
-__device__ __forceinline__ int cast_i32_x86(double v) {
-    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
-    return (int)v;
 }
 
 __device__ __forceinline__ unsigned int orderable(float s) {
@@ -110,36 +105,7 @@ __device__ __forceinline__ Decoded decode_one(const float* __restrict__ prob, co
     const float ws = __fadd_rn(__fsub_rn(x2, x1), 1.f), hs = __fadd_rn(__fsub_rn(y2, y1), 1.f);
     const bool keep_size = (ws >= k.min_size) && (hs >= k.min_size);           // _filter_boxes :336-341
     // lidar_3d_to_corners (transform.py:305-313) + lidar_cnr_to_img (:483-500, :369-386)
-    double umin = 0, umax = 0, vmin = 0, vmax = 0;
-    bool nan_u = false, nan_v = false;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const bool sx = (c == 0 || c == 1 || c == 4 || c == 5);
-        const bool sy = (c == 0 || c == 3 || c == 4 || c == 7);
-        const bool sz = (c >= 4);
-        const double X = sx ? xp : xm, Y = sy ? yp : ym, Z = sz ? zp : zm;
-        double r[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            double acc = __dmul_rn((double)k.M[4 * q], X);
-            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 1], Y));
-            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 2], Z));
-            acc = __dadd_rn(acc, __dmul_rn((double)k.M[4 * q + 3], 0.0));
-            r[q] = acc;
-        }
-        const double u = r[0] / r[2], v = r[1] / r[2];
-        nan_u |= (u != u);
-        nan_v |= (v != v);
-        if (c == 0) { umin = umax = u; vmin = vmax = v; }
-        else {
-            umin = u < umin ? u : umin; umax = u > umax ? u : umax;
-            vmin = v < vmin ? v : vmin; vmax = v > vmax ? v : vmax;
-        }
-    }
-    if (nan_u) umin = umax = nan("");
-    if (nan_v) vmin = vmax = nan("");
-    o.img[0] = cast_i32_x86(umin); o.img[1] = cast_i32_x86(vmin);
-    o.img[2] = cast_i32_x86(umax); o.img[3] = cast_i32_x86(vmax);
+    corners_to_img_box(k.M, xp, xm, yp, ym, zp, zm, o.img);
     const bool keep_img = (-50 <= o.img[0]) && (o.img[2] <= k.img_x_max) && (-50 <= o.img[1]) &&
                           (o.img[3] <= k.img_y_max);                            // _filter_img_boxes :343-352
     o.keep = keep_size && keep_img;

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, check, current_stream, lib, ptr
+from ._lib import GemmDesc, WgradDesc, check, current_stream, lib, ptr
 
 BF16 = torch.bfloat16
 
@@ -126,8 +126,10 @@ def _run_gemm(**kw):
 
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
-         out_f32_dense: bool = False):
-    """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None)."""
+         out_f32_dense: bool = False, mask: Optional["PadAct"] = None, mask_scale: float = 1.0,
+         addend: Optional[torch.Tensor] = None, use_bias: bool = True):
+    """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None).
+    mask / addend: the backward-data epilogue (out = (acc + addend) gated by mask > 0), see mv3d_gemm_desc."""
     assert w.cin_pad == a.c_pad, (w.cin_pad, a.c_pad)
     assert (not precise) or a.lo is not None
     dev = a.hi.device
@@ -142,14 +144,19 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
         out = PadAct(hi, lo, a.B, a.H, a.W, w.cout)
     dense = torch.empty((a.B, a.H, a.W, w.cout), dtype=torch.float32, device=dev) if out_f32_dense else None
     _run_gemm(M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=3 if precise else 1,
-              d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias),
+              d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo),
+              d_bias=ptr(w.bias) if use_bias else None,
               relu=int(relu), d_out_hi=ptr(out.hi) if out else None, d_out_lo=ptr(out.lo) if out else None,
-              ld_out=n_pad, d_out_f32=ptr(dense), ld_f32=w.cout, f32_dense=1 if out_f32_dense else 0, split_k=1)
+              ld_out=n_pad, d_out_f32=ptr(dense), ld_f32=w.cout, f32_dense=1 if out_f32_dense else 0, split_k=1,
+              d_mask_hi=ptr(mask.hi) if mask is not None else None, ld_mask=mask.c_pad if mask is not None else 0,
+              mask_scale=float(mask_scale), d_addend_f32=ptr(addend),
+              ld_addend=addend.shape[-1] if addend is not None else 0)
     return out, dense
 
 
 def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, relu: bool, precise: bool = True,
-           out_bf16: bool = True, out_f32: bool = False, split_k: int = 1):
+           out_bf16: bool = True, out_f32: bool = False, split_k: int = 1, mask_hi: Optional[torch.Tensor] = None,
+           mask_scale: float = 1.0, use_bias: bool = True):
     """Network.fc: (M,K) bf16 hi/lo rows x PackedWeight -> (hi, lo, f32).  K must equal w.cin_pad."""
     M, K = a_hi.shape
     assert K == w.cin_pad and w.taps == 1
@@ -159,7 +166,7 @@ def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, re
     if out_bf16:
         hi = torch.zeros((M, n_pad), dtype=BF16, device=dev)
         lo = torch.zeros_like(hi) if precise else None
-    if split_k > 1:
+    if split_k > 1 and mask_hi is None:
         acc = torch.zeros((M, w.cout), dtype=torch.float32, device=dev)
         _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
                   d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=None, relu=0, d_out_hi=None,
@@ -172,9 +179,10 @@ def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, re
     if out_f32:
         f32 = torch.empty((M, w.cout), dtype=torch.float32, device=dev)
     _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
-              d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias), relu=int(relu),
-              d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad, d_out_f32=ptr(f32), ld_f32=w.cout, f32_dense=0,
-              split_k=1)
+              d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias) if use_bias else None,
+              relu=int(relu), d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad, d_out_f32=ptr(f32), ld_f32=w.cout,
+              f32_dense=0, split_k=1, d_mask_hi=ptr(mask_hi), ld_mask=mask_hi.stride(0) if mask_hi is not None else 0,
+              mask_scale=float(mask_scale))
     return hi, lo, f32
 
 
@@ -189,3 +197,81 @@ def softmax_pairs(x: torch.Tensor, n_pairs: int) -> torch.Tensor:
     check(lib().mv3d_softmax_pairs(ptr(x2), x2.shape[0], ld, n_pairs, ptr(out), out.shape[1],
                                    current_stream()), "mv3d_softmax_pairs")
     return out.view(x.shape)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training-side wrappers (backward data / backward filter / pooling / bias)
+# ----------------------------------------------------------------------------------------------------------------
+def pack_weights_dgrad(w_hwio: torch.Tensor, cout_pad: Optional[int] = None) -> PackedWeight:
+    """HWIO (kh,kw,Cin,Cout) or (Cin,Cout) float32 -> the backward-data operand: rows = Cin, K = taps*cout_pad with the
+    taps flipped, so that `conv(G, packed)` / `linear(G, packed)` yields dLoss/dInput."""
+    w = w_hwio.contiguous()
+    if w.dim() == 2:
+        w = w.view(1, 1, *w.shape)
+    kh, kw, cin, cout = w.shape
+    taps = kh * kw
+    cp = cout_pad or pad_channels(cout)
+    hi = torch.empty((cin, taps * cp), dtype=BF16, device=w.device)
+    lo = torch.empty_like(hi)
+    check(lib().mv3d_pack_weights_dgrad(ptr(w), taps, cin, cout, cp, ptr(hi), ptr(lo), current_stream()),
+          "mv3d_pack_weights_dgrad")
+    return PackedWeight(hi, lo, None, taps, cout, cp, cin)
+
+
+def _run_wgrad(**kw):
+    d = WgradDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    if GEMM_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+    check(lib().mv3d_conv_wgrad(C.byref(d), current_stream()), "mv3d_conv_wgrad")
+    if GEMM_EVENTS is not None:
+        e1.record(torch.cuda.current_stream())
+        GEMM_EVENTS.append((e0, e1))
+
+
+def conv_wgrad(x: PadAct, g: PadAct, dw: torch.Tensor, precise: bool = True, accumulate: bool = True,
+               tap_window: bool = True, split_rows: int = 0) -> None:
+    """dw (taps, cin, cout) float32 (+)= sum_p x[p + shift_tap] (x) g[p]   (x: layer input, g: gated output gradient)."""
+    taps, cin, cout = (dw.shape[0] * dw.shape[1], dw.shape[2], dw.shape[3]) if dw.dim() == 4 else dw.shape
+    assert dw.is_contiguous() and dw.dtype == torch.float32
+    assert x.rows == g.rows and (x.H, x.W) == (g.H, g.W)
+    _run_wgrad(P=x.rows, Cx=x.c_pad, Cg=g.c_pad, cin=cin, cout=cout, taps=taps, Wp=x.W + 1, passes=3 if precise else 1,
+               d_x_hi=ptr(x.hi), d_x_lo=ptr(x.lo), d_g_hi=ptr(g.hi), d_g_lo=ptr(g.lo), d_dw=ptr(dw), ld_dw=cout,
+               accumulate=int(accumulate), split_rows=split_rows, tap_window=int(tap_window))
+
+
+def linear_wgrad(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], g_hi: torch.Tensor, g_lo: Optional[torch.Tensor],
+                 dw: torch.Tensor, precise: bool = True, accumulate: bool = True) -> None:
+    """dw (in, out) float32 (+)= x^T g for row-major bf16 hi/lo x (R, in_pad), g (R, out_pad)."""
+    R, kin = x_hi.shape
+    assert g_hi.shape[0] == R and dw.dim() == 2 and dw.is_contiguous()
+    _run_wgrad(P=R, Cx=kin, Cg=g_hi.shape[1], cin=dw.shape[0], cout=dw.shape[1], taps=1, Wp=0,
+               passes=3 if precise else 1, d_x_hi=ptr(x_hi), d_x_lo=ptr(x_lo), d_g_hi=ptr(g_hi), d_g_lo=ptr(g_lo),
+               d_dw=ptr(dw), ld_dw=dw.shape[1], accumulate=int(accumulate), split_rows=0, tap_window=0)
+
+
+def maxpool2x2_bwd(x: PadAct, g: PadAct) -> PadAct:
+    """Gradient of maxpool2x2(x) routed to the arg-max positions and gated by x > 0 (the producing conv's ReLU)."""
+    assert (g.H, g.W) == (x.H // 2, x.W // 2) and g.c_pad == x.c_pad
+    hi, lo = _new_pad(x.B, x.H, x.W, x.c_pad, x.lo is not None, x.hi.device)
+    check(lib().mv3d_maxpool2x2_bwd_pad(ptr(x.hi), ptr(x.lo), ptr(g.hi), ptr(g.lo), x.B, x.H, x.W, x.c_pad, ptr(hi),
+                                        ptr(lo), current_stream()), "mv3d_maxpool2x2_bwd_pad")
+    return PadAct(hi, lo, x.B, x.H, x.W, x.C)
+
+
+def bias_grad(g_hi: torch.Tensor, g_lo: Optional[torch.Tensor], n: int, db: torch.Tensor) -> None:
+    """db (n) float32 += column sums of the bf16 hi/lo gradient (any leading shape, last dim = row pitch)."""
+    ld = g_hi.shape[-1]
+    rows = g_hi.numel() // ld
+    check(lib().mv3d_bias_grad(ptr(g_hi), ptr(g_lo), rows, ld, n, ptr(db), current_stream()), "mv3d_bias_grad")
+
+
+def pad_nhwc_masked(x: torch.Tensor, mask: Optional[PadAct], precise: bool = True) -> PadAct:
+    B, H, W, Cc = x.shape
+    cp = mask.c_pad if mask is not None else pad_channels(Cc)
+    hi, lo = _new_pad(B, H, W, cp, precise, x.device)
+    check(lib().mv3d_pad_nhwc_masked(ptr(x), B, H, W, Cc, cp, ptr(mask.hi) if mask is not None else None, ptr(hi),
+                                     ptr(lo), current_stream()), "mv3d_pad_nhwc_masked")
+    return PadAct(hi, lo, B, H, W, Cc)
