@@ -1,0 +1,311 @@
+"""Training entry points with the reference's names (lib/fast_rcnn/train_mv.py): SolverWrapper, train_net.
+
+The reference builds the loss graph (train_mv.py:94-139) and lets TensorFlow differentiate it and apply
+`tf.train.AdamOptimizer(1e-5)` (:144-146).  Here `SolverWrapper.train_step` plays the same step explicitly on the
+current CUDA stream through the C ABI: the forward program of `MV3D_train`, the two loss kernels, a hand-written
+backward pass (tcgen05 backward-data / backward-filter GEMMs, ROI-pool / max-pool / bias kernels), one optional NCCL
+all-reduce of the flat gradient buffer (data-parallel training) and one fused Adam kernel over the flat
+parameter buffer.  PyTorch tensors are containers; no torch math touches activations, gradients or weights.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .. import kernels as K
+from .._lib import check, current_stream, lib, ptr
+from ..networks.network import Node, Val
+
+RPN_SIGMA = 3.0    # train_mv.py:113,131
+
+
+def _node(net, name) -> Node:
+    n = net.layers[name]
+    return n[0] if isinstance(n, tuple) else n
+
+
+class SolverWrapper(object):
+    """train_mv.py:27-219.  `network` is an MV3D_train; `imdb` / `roidb` are accepted for signature compatibility
+    (`roidb` may be any iterable of blob dicts, the output of RoIDataLayer.forward() in the reference)."""
+
+    def __init__(self, sess=None, saver=None, network=None, imdb=None, roidb=None, output_dir=None,
+                 pretrained_model=None, lr=0.00001, beta1=0.9, beta2=0.999, epsilon=1e-8, keep_prob=0.5,
+                 process_group=None):
+        self.net = network
+        self.imdb = imdb
+        self.roidb = roidb
+        self.output_dir = output_dir
+        self.pretrained_model = pretrained_model
+        self.lr, self.beta1, self.beta2, self.epsilon = lr, beta1, beta2, epsilon
+        self.keep_prob = keep_prob
+        self.pg = process_group
+        self.step = 0
+        net = self.net
+        net.training = True
+        if not net.params:
+            net.init_weights()
+        if pretrained_model is not None:
+            net.load(pretrained_model, None, None, True)
+        self._flatten_parameters()
+        self._dpacked: Dict[str, K.PackedWeight] = {}
+        self.loss = torch.zeros(4, dtype=torch.float32, device=net.device)  # rpn_cls, rpn_box, cls, box
+        self.last_grad_events = None
+
+    # ------------------------------------------------------------------ parameters
+    def _flatten_parameters(self):
+        """One flat fp32 buffer each for parameters, gradients and the two Adam moments (Adam and the gradient
+        all-reduce are then single launches).  fc layers that follow roi_pool keep their rows in the kernel-native
+        (H,W,C) order inside the buffer; `export_params` converts back to the reference's (C,H,W) row order."""
+        net = self.net
+        self.names = list(net.param_specs)
+        total = 0
+        self.slices = {}
+        for name in self.names:
+            shape = net.param_specs[name]['shape']
+            nw, nb = int(np.prod(shape)), int(shape[-1])
+            self.slices[name] = (total, nw, nb, shape)
+            total += (nw + nb + 3) // 4 * 4
+        dev = net.device
+        self.theta = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.perm = {}
+        for n in net._program:
+            if n.kind == 'fc' and 'flatten_chw' in n.attrs:
+                self.perm[n.name] = n.attrs['flatten_chw']
+        self.gviews = {}
+        for name in self.names:
+            off, nw, nb, shape = self.slices[name]
+            w = net.params[name]['weights']
+            if name in self.perm and not net.native_fc_layout:
+                cc, ph, pw = self.perm[name]
+                w = w.view(cc, ph * pw, shape[-1]).permute(1, 0, 2).reshape(shape)
+            self.theta[off:off + nw].view(shape).copy_(w)
+            self.theta[off + nw:off + nw + nb].copy_(net.params[name]['biases'])
+            net.params[name] = dict(weights=self.theta[off:off + nw].view(shape),
+                                    biases=self.theta[off + nw:off + nw + nb])
+            self.gviews[name] = dict(weights=self.grad[off:off + nw].view(shape),
+                                     biases=self.grad[off + nw:off + nw + nb])
+        net.native_fc_layout = True
+        net._packed.clear()
+
+    def export_params(self):
+        """{layer: {'weights', 'biases'}} numpy dict in the reference's variable layouts (the `.npy` format of
+        network.py:45-64)."""
+        out = {}
+        for name in self.names:
+            off, nw, nb, shape = self.slices[name]
+            w = self.theta[off:off + nw].view(shape)
+            if name in self.perm:
+                cc, ph, pw = self.perm[name]
+                w = w.view(ph * pw, cc, shape[-1]).permute(1, 0, 2).reshape(shape)
+            out[name] = dict(weights=w.cpu().numpy().copy(), biases=self.theta[off + nw:off + nw + nb].cpu().numpy().copy())
+        return out
+
+    def export_grads(self):
+        out = {}
+        for name in self.names:
+            off, nw, nb, shape = self.slices[name]
+            w = self.grad[off:off + nw].view(shape)
+            if name in self.perm:
+                cc, ph, pw = self.perm[name]
+                w = w.view(ph * pw, cc, shape[-1]).permute(1, 0, 2).reshape(shape)
+            out[name] = dict(weights=w.cpu().numpy().copy(), biases=self.grad[off + nw:off + nw + nb].cpu().numpy().copy())
+        return out
+
+    def snapshot(self, sess=None, iter=0):
+        """train_mv.py:49-65: write the weights (as the reference-format .npy dict instead of a TF checkpoint)."""
+        if self.output_dir is None:
+            return None
+        os.makedirs(self.output_dir, exist_ok=True)
+        filename = os.path.join(self.output_dir, 'MV3D_iter_{:d}.npy'.format(iter + 1))
+        np.save(filename, self.export_params(), allow_pickle=True)
+        print('Wrote snapshot to: {:s}'.format(filename))
+        return filename
+
+    def _dweight(self, key, names) -> K.PackedWeight:
+        """Backward-data operand of one layer (or of sibling heads concatenated along the output axis)."""
+        pw = self._dpacked.get(key)
+        if pw is None:
+            ws = [self.net.params[n]['weights'] for n in names]
+            w = ws[0] if len(ws) == 1 else torch.cat(ws, dim=-1).contiguous()
+            pw = self._dpacked[key] = K.pack_weights_dgrad(w)
+        return pw
+
+    # ------------------------------------------------------------------ one training step
+    def train_step(self, blobs, keep_prob=None, apply_update=True):
+        """blobs: the reference's feed (train_mv.py:168-176): 'image_data', 'lidar_bv_data' (dense (B,H,W,C), or a
+        kernels.PadAct from BevRasterizer.to_pad), 'im_info', 'gt_boxes_bv', 'gt_boxes_3d', 'gt_boxes_corners', 'calib'
+        (GT entries: one array, or a list with one array per frame).  Returns the four loss values as a device
+        tensor [rpn_loss_cls, rpn_loss_box, loss_cls, loss_box] (no host sync)."""
+        net = self.net
+        kp = self.keep_prob if keep_prob is None else keep_prob
+        feed = {net.image_data: blobs['image_data'], net.lidar_bv_data: blobs['lidar_bv_data'],
+                net.im_info: blobs['im_info'], net.keep_prob: kp, net.gt_boxes_bv: blobs['gt_boxes_bv'],
+                net.gt_boxes_3d: blobs['gt_boxes_3d'], net.gt_boxes_corners: blobs['gt_boxes_corners'],
+                net.calib: blobs['calib']}
+        fetch = ['cls_score', 'bbox_pred', 'rpn_cls_score', 'rpn_bbox_pred', 'rpn_data', 'roi_data_3d']
+        net.training = True
+        net.run([_node(net, f) for f in fetch], feed)
+        vals = net.last_vals
+        self.grad.zero_()
+        self.loss.zero_()
+        self._backward(vals, kp)
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, group=self.pg)          # ONE exchange step
+            world = dist.get_world_size(self.pg)
+        else:
+            world = 1
+        if apply_update:
+            self.step += 1
+            check(lib().mv3d_adam(ptr(self.theta), ptr(self.grad), ptr(self.m), ptr(self.v), self.theta.numel(),
+                                  self.lr, self.beta1, self.beta2, self.epsilon, self.step, 1.0 / world,
+                                  current_stream()), 'mv3d_adam')
+            net._packed.clear()
+            self._dpacked.clear()
+        return self.loss
+
+    # ------------------------------------------------------------------ backward pass
+    def _backward(self, vals, kp):
+        net, precise = self.net, self.net.precise
+        g = self.gviews
+        stream = current_stream()
+        L = lib()
+
+        # ---------------- R-CNN head losses (train_mv.py:121-133) ----------------
+        cls_v, box_v = vals[_node(net, 'cls_score')].dense, vals[_node(net, 'bbox_pred')].dense
+        rd = vals[_node(net, 'roi_data_3d')].extra
+        R, nb, B = cls_v.shape[0], box_v.shape[1], rd['B']
+        gh = torch.empty((R, 64), dtype=K.BF16, device=net.device)
+        gl = torch.empty_like(gh) if precise else None
+        check(L.mv3d_rcnn_loss(ptr(cls_v), cls_v.stride(0), ptr(box_v), box_v.stride(0), ptr(rd['labels']),
+                               ptr(rd['targets']), nb, ptr(rd['bv']), ptr(rd['frame_counts']), B, R, 64, RPN_SIGMA,
+                               ptr(gh), ptr(gl), ptr(self.loss[2:]), stream), 'mv3d_rcnn_loss')
+        # fused [cls_score | bbox_pred] head on the dropped-out concat (MV3D_train.py:175-182)
+        xin = vals[_node(net, 'drop7')]                      # (R,4096) after both dropouts
+        n_cls = net.param_specs['cls_score']['shape'][1]
+        dwc = torch.empty((xin.hi.shape[1], n_cls + nb), dtype=torch.float32, device=net.device)
+        K.linear_wgrad(xin.hi, xin.lo, gh, gl, dwc, precise=precise, accumulate=False)
+        g['cls_score']['weights'].copy_(dwc[:, :n_cls])
+        g['bbox_pred']['weights'].copy_(dwc[:, n_cls:])
+        dbc = torch.zeros(n_cls + nb, dtype=torch.float32, device=net.device)
+        K.bias_grad(gh, gl, n_cls + nb, dbc)
+        g['cls_score']['biases'].copy_(dbc[:n_cls])
+        g['bbox_pred']['biases'].copy_(dbc[n_cls:])
+        scale2 = 1.0 / (kp * kp) if kp < 1.0 else 1.0       # drop7 (per branch) and drop7 (fused) between fc7 and here
+        d7h, d7l, _ = K.linear(gh, gl, self._dweight('head', ['cls_score', 'bbox_pred']), relu=False, precise=precise,
+                               out_bf16=True, out_f32=False, mask_hi=xin.hi, mask_scale=scale2, use_bias=False)
+        half = xin.hi.shape[1] // 2
+        scale1 = 1.0 / kp if kp < 1.0 else 1.0
+        for bi, (suffix, drop6, pool) in enumerate((('_1', 'drop6', 'pool_5'), ('_2', 'drop6_2', 'pool_5_2'))):
+            g7h = d7h[:, bi * half:(bi + 1) * half].contiguous()
+            g7l = d7l[:, bi * half:(bi + 1) * half].contiguous() if d7l is not None else None
+            x6 = vals[_node(net, drop6)]                     # fc6 output after dropout: input of fc7
+            K.linear_wgrad(x6.hi, x6.lo, g7h, g7l, g['fc7' + suffix]['weights'], precise=precise, accumulate=False)
+            K.bias_grad(g7h, g7l, half, g['fc7' + suffix]['biases'])
+            g6h, g6l, _ = K.linear(g7h, g7l, self._dweight('fc7' + suffix, ['fc7' + suffix]), relu=False,
+                                   precise=precise, out_bf16=True, out_f32=False, mask_hi=x6.hi, mask_scale=scale1,
+                                   use_bias=False)
+            xp = vals[_node(net, pool)]                      # pooled features (R, 7*7*512), rows in (H,W,C) order
+            K.linear_wgrad(xp.hi, xp.lo, g6h, g6l, g['fc6' + suffix]['weights'], precise=precise, accumulate=False)
+            K.bias_grad(g6h, g6l, g6h.shape[1], g['fc6' + suffix]['biases'])
+            _, _, dpool = K.linear(g6h, g6l, self._dweight('fc6' + suffix, ['fc6' + suffix]), relu=False,
+                                   precise=precise, out_bf16=False, out_f32=True, use_bias=False)
+            e = xp.extra
+            feat = e['feat']
+            dfeat = torch.empty_like(feat)
+            ph, pw, _sc = _node(net, pool).attrs['cfg']
+            check(L.mv3d_roi_pool_backward(ptr(dpool), e['scale'], feat.shape[0], R, feat.shape[1], feat.shape[2],
+                                           feat.shape[3], ph, pw, ptr(e['rois']), ptr(dfeat), ptr(e['argmax']),
+                                           stream), 'mv3d_roi_pool_backward')
+            vals[_node(net, pool)].extra['dfeat'] = dfeat
+
+        # ---------------- RPN losses (train_mv.py:94-119) ----------------
+        rcls, rbox = vals[_node(net, 'rpn_cls_score')].dense, vals[_node(net, 'rpn_bbox_pred')].dense
+        ad = vals[_node(net, 'rpn_data')].extra
+        Bq, Hf, Wf = rcls.shape[0], rcls.shape[1], rcls.shape[2]
+        A = ad['A']
+        ghd_hi, ghd_lo = K._new_pad(Bq, Hf, Wf, 64, precise, net.device)
+        check(L.mv3d_rpn_loss(ptr(rcls), ptr(rbox), ptr(ad['labels']), ptr(ad['targets']), ptr(ad['counts']), Bq, Hf,
+                              Wf, A, 64, RPN_SIGMA, ptr(ghd_hi), ptr(ghd_lo), ptr(self.loss), stream), 'mv3d_rpn_loss')
+        ghd = K.PadAct(ghd_hi, ghd_lo, Bq, Hf, Wf, 8 * A)
+        rc = vals[_node(net, 'rpn_conv/3x3')].pad
+        dwh = torch.zeros((1, rc.C, 8 * A), dtype=torch.float32, device=net.device)
+        K.conv_wgrad(rc, ghd, dwh, precise=precise, accumulate=True)
+        g['rpn_cls_score']['weights'].view(rc.C, 2 * A).copy_(dwh[0, :, :2 * A])
+        g['rpn_bbox_pred']['weights'].view(rc.C, 6 * A).copy_(dwh[0, :, 2 * A:])
+        dbh = torch.zeros(8 * A, dtype=torch.float32, device=net.device)
+        K.bias_grad(ghd.hi, ghd.lo, 8 * A, dbh)
+        g['rpn_cls_score']['biases'].copy_(dbh[:2 * A])
+        g['rpn_bbox_pred']['biases'].copy_(dbh[2 * A:])
+        grc, _ = K.conv(ghd, self._dweight('rpn_heads', ['rpn_cls_score', 'rpn_bbox_pred']), relu=False,
+                        precise=precise, out_pad=True, mask=rc, use_bias=False)
+
+        # ---------------- trunks, last layer first ----------------
+        grads: Dict[Node, K.PadAct] = {_node(net, 'rpn_conv/3x3'): grc}
+        dense_in: Dict[Node, torch.Tensor] = {_node(net, 'conv5_3'): vals[_node(net, 'pool_5')].extra['dfeat'],
+                                              _node(net, 'conv5_3_2'): vals[_node(net, 'pool_5_2')].extra['dfeat']}
+        for node in reversed(net._program):
+            if node.kind == 'max_pool':
+                gp = grads.pop(node, None)
+                if gp is None:
+                    continue
+                src = node.inputs[0]
+                grads[src] = K.maxpool2x2_bwd(vals[src].pad, gp)   # routed + gated by the producing conv's ReLU
+                continue
+            if node.kind != 'conv' or node.name in ('rpn_cls_score', 'rpn_bbox_pred'):
+                continue
+            gn = grads.pop(node, None)
+            if gn is None:
+                d = dense_in.pop(node, None)
+                if d is None:
+                    continue
+                gn = K.pad_nhwc_masked(d, vals[node].pad, precise=precise)   # only the ROI path feeds this layer
+            src = node.inputs[0]
+            x = vals[src].pad
+            K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
+            K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
+            if src.kind == 'placeholder':
+                continue
+            gated = src.kind == 'conv'   # the dgrad epilogue applies the ReLU gate of the producing conv
+            gsrc, _ = K.conv(gn, self._dweight(node.name, [node.name]), relu=False, precise=precise, out_pad=True,
+                             mask=x if gated else None, addend=dense_in.pop(src, None), use_bias=False)
+            grads[src] = gsrc
+
+    # ------------------------------------------------------------------ reference-shaped loop
+    def train_model(self, sess=None, max_iters=10000, data=None, display=10):
+        """train_mv.py:87-219: loop over blobs, one Adam step each, periodic loss print + snapshot."""
+        from .config import cfg
+        data = self.roidb if data is None else data
+        it = iter(data)
+        last = None
+        for i in range(max_iters):
+            try:
+                blobs = next(it)
+            except StopIteration:
+                it = iter(data)
+                blobs = next(it)
+            loss = self.train_step(blobs)
+            if (i + 1) % display == 0:
+                v = loss.tolist()
+                print('iter: %d / %d, total loss: %.4f, rpn_loss_cls: %.4f, rpn_loss_box: %.4f, loss_cls: %.4f, '
+                      'loss_box: %.4f, lr: %f' % (i + 1, max_iters, sum(v), v[0], v[1], v[2], v[3], self.lr))
+            if (i + 1) % cfg.TRAIN.SNAPSHOT_ITERS == 0:
+                last = i
+                self.snapshot(None, i)
+        if last != max_iters - 1 and max_iters > 0:
+            self.snapshot(None, max_iters - 1)
+
+
+def train_net(network, imdb, roidb, output_dir, pretrained_model=None, max_iters=10000):
+    """train_mv.py:373-381."""
+    sw = SolverWrapper(None, None, network, imdb, roidb, output_dir, pretrained_model=pretrained_model)
+    print('Solving...')
+    sw.train_model(None, max_iters)
+    print('done solving')
+    return sw

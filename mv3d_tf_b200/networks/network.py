@@ -17,7 +17,9 @@ import torch
 from .. import kernels as K
 from .._lib import RoiView, check, current_stream, lib, ptr
 from ..fast_rcnn.config import cfg
+from ..rpn_msr.anchor_target_layer_tf import AnchorTargetLayer
 from ..rpn_msr.proposal_layer_tf import ProposalLayer3D
+from ..rpn_msr.proposal_target_layer_tf import ProposalTargetLayer3D
 from ..utils.transform import REF_GEOMETRY, BevGeometry
 
 DEFAULT_PADDING = 'SAME'
@@ -80,8 +82,14 @@ class Network(object):
         self._packed: Dict[str, K.PackedWeight] = {}
         self._program: List[Node] = []
         self._proposal_layers: Dict[tuple, ProposalLayer3D] = {}
+        self._anchor_target_layers: Dict[tuple, AnchorTargetLayer] = {}
+        self._proposal_target_layer: Optional[ProposalTargetLayer3D] = None
         self._roi_nodes: List[Node] = []
         self.last_num_rois = None
+        self.training = False           # True: roi_pool keeps argmax, dropout draws masks (set by the solver)
+        self.native_fc_layout = False   # True: fc-after-roi_pool weights are stored with rows already in (H,W,C) order
+        self.dropout_seed = 0
+        self.last_vals = None
         self.setup()
 
     def setup(self):
@@ -173,7 +181,7 @@ class Network(object):
         if pw is None:
             p = self.params[name]
             w = p['weights']
-            if transform is not None:
+            if transform is not None and not self.native_fc_layout:
                 w = transform(w)
             pw = self._packed[name] = K.pack_weights(w, p['biases'])
         return pw
@@ -192,7 +200,7 @@ class Network(object):
             v = vals[node.inputs[0]]
             if v.pad is None:
                 v.pad = K.pad_nhwc(v.dense, precise=self.precise)
-            want_pad = any(c in ('conv', 'max_pool') for c in node.consumers)
+            want_pad = any(c in ('conv', 'max_pool') for c in node.consumers) or self.training
             want_dense = (not want_pad) or any(c not in ('conv', 'max_pool') for c in node.consumers) \
                 or node.attrs.get('fetched', False)
             out, dense = K.conv(v.pad, self._weight(name), relu=relu, precise=self.precise, out_pad=want_pad,
@@ -297,13 +305,14 @@ class Network(object):
                 top = None
                 if m.attrs.get('fetched', False):
                     top = torch.empty((R, ph, pw, Cc), dtype=torch.float32, device=feat.device)
+                arg = torch.empty((R, ph, pw, Cc), dtype=torch.int32, device=feat.device) if self.training else None
                 v = views[k]
                 v.d_data, v.d_rois, v.height, v.width = ptr(feat), ptr(r), feat.shape[1], feat.shape[2]
-                v.spatial_scale, v.d_top, v.d_argmax, v.d_top_hi, v.d_top_lo = sc, ptr(top), None, ptr(hi), ptr(lo)
-                results.append(Val(dense=top, hi=hi, lo=lo, extra=(feat, r)))
+                v.spatial_scale, v.d_top, v.d_argmax, v.d_top_hi, v.d_top_lo = sc, ptr(top), ptr(arg), ptr(hi), ptr(lo)
+                results.append(Val(dense=top, hi=hi, lo=lo, extra=dict(feat=feat, rois=r, argmax=arg, scale=sc)))
             ph, pw, _ = node.attrs['cfg']
             e = vals[node.inputs[1]].extra
-            num = e['num'] if (isinstance(e, dict) and e['num'].numel() == 1) else None
+            num = e['num'] if (isinstance(e, dict) and e.get('num') is not None and e['num'].numel() == 1) else None
             check(lib().mv3d_roi_pool_multiview(views, len(group), R, ptr(num), group[0].channels, ph, pw,
                                                 current_stream()), 'mv3d_roi_pool_multiview')
             mine = None
@@ -375,6 +384,8 @@ class Network(object):
             return Val(hi=hi, lo=lo, dense=f32)
         n = self._node(name, 'fc', [input], run, channels=num_out)
         n.attrs['relu'] = relu
+        if input.pooled is not None:   # rows of the reference weight are in (C,H,W) order (network.py:381)
+            n.attrs['flatten_chw'] = (input.channels, input.pooled[0], input.pooled[1])
         # fusion planning: an earlier fc without ReLU fed by the same tensors (directly or through identical concats)
         if not relu:
             def src(x):
@@ -400,9 +411,89 @@ class Network(object):
 
     @layer
     def dropout(self, input, keep_prob, name):
-        def run(vals, node):  # inference / parity runs use keep_prob = 1 (identity)
-            return vals[node.inputs[0]]
+        if isinstance(input, tuple):
+            input = input[0]
+
+        def run(vals, node):
+            v = vals[node.inputs[0]]
+            kp = keep_prob
+            if isinstance(kp, Node):   # the keep_prob placeholder (MV3D_train.py:19)
+                kv = vals.get(kp)
+                kp = 1.0 if kv is None else float(np.asarray(kv.extra).reshape(-1)[0])
+            node.attrs['keep_prob_value'] = float(kp)
+            if not self.training or kp >= 1.0:
+                return v   # inference / parity runs: identity
+            hi = v.hi.clone()
+            lo = v.lo.clone() if v.lo is not None else None
+            self.dropout_seed += 1
+            check(lib().mv3d_dropout(ptr(hi), ptr(lo), hi.shape[0], node.channels, hi.shape[1], float(kp),
+                                     int(self.dropout_seed) * 0x9E3779B97F4A7C15 % (1 << 64), current_stream()),
+                  'mv3d_dropout')
+            return Val(hi=hi, lo=lo)
         return self._node(name, 'dropout', [input], run, channels=input.channels, pooled=input.pooled)
+
+    # ------------------------------------------------------------------ training-only layers (MV3D_train.py)
+    @staticmethod
+    def _per_frame(x, B):
+        """Ground-truth feeds: one array for the reference's single-frame batch, or a list with one array per frame."""
+        if isinstance(x, (list, tuple)):
+            assert len(x) == B
+            return list(x)
+        assert B == 1, 'feed a list with one array per frame for multi-frame batches'
+        return [x]
+
+    @layer
+    def anchor_target_layer(self, input, _feat_stride, anchor_scales, name):
+        """network.py:237-253 -> (rpn_labels, rpn_bbox_targets, rois_bv, rois_3d)."""
+        def run(vals, node):
+            score = vals[node.inputs[0]].dense
+            B, H, W = score.shape[0], score.shape[1], score.shape[2]
+            gt_bv = self._per_frame(vals[node.inputs[1]].extra, B)
+            gt_3d = self._per_frame(vals[node.inputs[2]].extra, B)
+            im_info = np.asarray(vals[node.inputs[3]].extra, dtype=np.float32).reshape(-1, 3)
+            key = (H, W, int(_feat_stride))
+            al = self._anchor_target_layers.get(key)
+            if al is None:
+                al = self._anchor_target_layers[key] = AnchorTargetLayer(H, W, int(_feat_stride), geom=self.geometry,
+                                                                         device=self.device)
+            outs = [al(self._dev(gt_bv[b]), self._dev(gt_3d[b]), im_info[min(b, im_info.shape[0] - 1)],
+                       want_rois=node.attrs.get('fetched', False)) for b in range(B)]
+            return Val(extra=dict(labels=torch.stack([o['labels'] for o in outs]),
+                                  targets=torch.stack([o['targets'] for o in outs]),
+                                  counts=torch.stack([o['counts'] for o in outs]), outs=outs, A=al.N // (H * W)))
+        n = self._node(name, 'anchor_target', list(input), run)
+        return (n, n, n, n)
+
+    @layer
+    def proposal_target_layer_3d(self, input, classes, name):
+        """network.py:256-273 -> (rois_bv, rois_img, labels, bbox_targets, rois_3d)."""
+        def run(vals, node):
+            e = vals[node.inputs[0]].extra
+            outs = e['outs']
+            B = len(outs)
+            gt_bv = self._per_frame(vals[node.inputs[1]].extra, B)
+            gt_3d = self._per_frame(vals[node.inputs[2]].extra, B)
+            gt_cnr = self._per_frame(vals[node.inputs[3]].extra, B)
+            calib = np.asarray(vals[node.inputs[4]].extra, dtype=np.float32)
+            if self._proposal_target_layer is None:
+                self._proposal_target_layer = ProposalTargetLayer3D(device=self.device)
+            res = []
+            for b in range(B):
+                cb = calib.reshape(-1, 4, 12)[b if calib.size > 48 else 0]
+                res.append(self._proposal_target_layer(outs[b]['bv'], outs[b]['p3d'], outs[b]['num'],
+                                                       self._dev(gt_bv[b]), self._dev(gt_3d[b]), self._dev(gt_cnr[b]),
+                                                       cb, int(classes), batch_index=float(b)))
+            cat = (lambda k: res[0][k]) if B == 1 else (lambda k: torch.cat([r[k] for r in res]))
+            counts = torch.tensor([r['bv'].shape[0] for r in res], dtype=torch.int32).to(self.device)
+            return Val(extra=dict(bv=cat('bv'), img=cat('img'), p3d=cat('p3d'), labels=cat('labels'),
+                                  targets=cat('targets'), num=None, frame_counts=counts, B=B))
+        n = self._node(name, 'proposal_target', list(i[0] if isinstance(i, tuple) else i for i in input), run)
+        return (n, n, n, n, n)
+
+    def _dev(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device, dtype=torch.float32)
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
 
     # ------------------------------------------------------------------ execution (the sess.run analogue)
     def run(self, fetches, feed_dict):
@@ -421,7 +512,9 @@ class Network(object):
             node = self.layers[k] if isinstance(k, str) else k
             if isinstance(v, K.PadAct):  # already in the trunk's input layout (BevRasterizer.to_pad)
                 vals[node] = Val(pad=v)
-            elif node.name in ('im_info', 'calib', 'keep_prob') or node.name.startswith('gt_'):
+            elif node.name.startswith('gt_'):
+                vals[node] = Val(extra=v)   # numpy / tensor, or a list with one array per frame
+            elif node.name in ('im_info', 'calib', 'keep_prob'):
                 vals[node] = Val(extra=v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
             else:
                 t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
@@ -430,10 +523,13 @@ class Network(object):
         for n in self._program:
             if n in needed:
                 vals[n] = n.fn(vals, n)
+        self.last_vals = vals if self.training else None
         out = []
         for n in fetch_nodes:
             v = vals[n]
-            if v.dense is not None:
+            if v.dense is None and v.pad is None and v.hi is None:
+                out.append(v.extra)   # host-layer outputs (target layers): the dict of device tensors
+            elif v.dense is not None:
                 out.append(v.dense)
             elif v.pad is not None:
                 out.append(K.unpad_nhwc(v.pad))

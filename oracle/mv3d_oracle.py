@@ -398,6 +398,153 @@ def roi_pool_bwd(data_shape, rois, argmax, dtop, pooled_h=7, pooled_w=7, spatial
 
 
 # ----------------------------------------------------------------------------------------
+# a13-a14. training target layers
+# ----------------------------------------------------------------------------------------
+TRAIN_CFG = dict(RPN_POSITIVE_OVERLAP=0.7, RPN_NEGATIVE_OVERLAP=0.5, RPN_CLOBBER_POSITIVES=False,
+                 RPN_FG_FRACTION=0.25, RPN_BATCHSIZE=128, BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.7,
+                 BG_THRESH_HI=0.5, BG_THRESH_LO=0.0)   # config.py defaults + faster_rcnn_end2end.yml overlay
+
+
+def anchor_target_layer(rpn_cls_score, gt_boxes, gt_boxes_3d, im_info, _feat_stride=(8,), anchor_scales=(1.0, 1.0),
+                        cfg=None, geom: BevGeometry = REF_GEOMETRY, rng=None, return_stages=False):
+    """anchor_target_layer_tf.py:21-250.  `rng`: the numpy RandomState-like module/object whose `.choice` is drawn
+    from (the reference uses the global numpy.random).  Returns (labels (N,), bbox_targets (N,6), anchors (<=128,5),
+    anchors_3d (<=128,7)) float32; with return_stages also the pre-sampling labels / max_overlaps / argmax."""
+    c = dict(TRAIN_CFG)
+    if cfg:
+        c.update(cfg)
+    npr = np.random if rng is None else rng
+    im_info = np.asarray(im_info).reshape(-1, 3)[0]
+    assert rpn_cls_score.shape[0] == 1
+    height, width = rpn_cls_score.shape[1:3]
+    all_anchors = enumerate_anchors(height, width, int(np.ravel(_feat_stride)[0]))           # :76-89
+    total = all_anchors.shape[0]
+    inds_inside = np.where((all_anchors[:, 0] >= 0) & (all_anchors[:, 1] >= 0) &
+                           (all_anchors[:, 2] < im_info[1]) & (all_anchors[:, 3] < im_info[0]))[0]   # :93-98
+    anchors = all_anchors[inds_inside, :]
+    labels = np.empty((len(inds_inside),), dtype=np.float32)
+    labels.fill(-1)
+    overlaps = bbox_overlaps(np.ascontiguousarray(anchors, dtype=np.float64),
+                             np.ascontiguousarray(gt_boxes[:, :4], dtype=np.float64))        # :113-115 (cols 0-3 are read)
+    argmax_overlaps = overlaps.argmax(axis=1)
+    max_overlaps = overlaps[np.arange(len(inds_inside)), argmax_overlaps]
+    gt_argmax_overlaps = overlaps.argmax(axis=0)
+    gt_max_overlaps = overlaps[gt_argmax_overlaps, np.arange(overlaps.shape[1])]
+    gt_argmax_overlaps = np.where(overlaps == gt_max_overlaps)[0]                            # :123
+    if not c["RPN_CLOBBER_POSITIVES"]:
+        labels[np.logical_and(0 < max_overlaps, max_overlaps < c["RPN_NEGATIVE_OVERLAP"])] = 0   # :129-130
+    labels[gt_argmax_overlaps] = 1                                                           # :133
+    labels[max_overlaps >= c["RPN_POSITIVE_OVERLAP"]] = 1                                    # :139
+    if c["RPN_CLOBBER_POSITIVES"]:
+        labels[max_overlaps < c["RPN_NEGATIVE_OVERLAP"]] = 0
+    pre_labels = labels.copy()
+    num_fg = int(c["RPN_FG_FRACTION"] * c["RPN_BATCHSIZE"])                                  # :146-151
+    fg_inds = np.where(labels == 1)[0]
+    if len(fg_inds) > num_fg:
+        labels[npr.choice(fg_inds, size=(len(fg_inds) - num_fg), replace=False)] = -1
+    num_bg = c["RPN_BATCHSIZE"] - np.sum(labels == 1)                                        # :154-159
+    bg_inds = np.where(labels == 0)[0]
+    if len(bg_inds) > num_bg:
+        labels[npr.choice(bg_inds, size=(len(bg_inds) - num_bg), replace=False)] = -1
+    anchors_3d = bv_anchor_to_lidar(anchors, geom)                                           # :164
+    bbox_targets = bbox_transform_3d(anchors_3d, gt_boxes_3d[argmax_overlaps, :][:, :6]).astype(np.float32, copy=False)
+    all_inds = np.where(labels != -1)                                                        # :169-174
+    zeros = np.zeros((labels[all_inds].shape[0], 1), dtype=np.float32)
+    out_anchors = np.hstack((zeros, anchors[all_inds])).astype(np.float32)
+    out_anchors_3d = np.hstack((zeros, anchors_3d[all_inds])).astype(np.float32)
+    labels[max_overlaps < c["RPN_NEGATIVE_OVERLAP"]] = 0                                     # :176
+    num_bg = c["RPN_BATCHSIZE"] - np.sum(labels == 1)
+    bg_inds = np.where(labels == 0)[0]
+    if len(bg_inds) > num_bg:
+        labels[npr.choice(bg_inds, size=(len(bg_inds) - num_bg), replace=False)] = -1
+
+    def unmap(data, fill):                                                                   # :254-265
+        ret = np.empty((total,) + data.shape[1:], dtype=np.float32)
+        ret.fill(fill)
+        ret[inds_inside] = data
+        return ret
+    out = (unmap(labels, -1), unmap(bbox_targets, 0), out_anchors, out_anchors_3d)
+    if return_stages:
+        return out + (dict(inds_inside=inds_inside, pre_labels=unmap(pre_labels, -1), max_overlaps=unmap(max_overlaps, -1),
+                           argmax=argmax_overlaps),)
+    return out
+
+
+def bbox_transform_cnr(ex_cnr, gt_cnr):
+    """bbox_transform.py:61-72."""
+    diag = np.linalg.norm(gt_cnr[:, 0::8] - gt_cnr[:, 6::8], axis=1)
+    return np.divide(gt_cnr - ex_cnr, diag.reshape((-1, 1)))
+
+
+def proposal_target_layer_3d(rpn_rois_bv, rpn_rois_3d, gt_boxes_bv, gt_boxes_3d, gt_boxes_corners, calib, _num_classes,
+                             cfg=None, rng=None, return_stages=False):
+    """proposal_target_layer_tf.py:19-94 with _sample_rois_3d :227-298 -> (rois_bv (K,5), rois_img (K,5),
+    labels (K,1) int32, bbox_targets (K,24*nc), rois_3d (K,7))."""
+    c = dict(TRAIN_CFG)
+    if cfg:
+        c.update(cfg)
+    npr = np.random if rng is None else rng
+    zeros = np.zeros((gt_boxes_bv.shape[0], 1), dtype=gt_boxes_bv.dtype)
+    all_rois = np.vstack((rpn_rois_bv, np.hstack((zeros, gt_boxes_bv[:, :-1]))))             # :38-41
+    all_rois_3d = np.vstack((rpn_rois_3d, np.hstack((zeros, gt_boxes_3d[:, :-1]))))          # :42-44
+    assert np.all(all_rois[:, 0] == 0)
+    rois_per_image = c["BATCH_SIZE"] // 1
+    fg_rois_per_image = np.round(c["FG_FRACTION"] * rois_per_image)
+    overlaps = bbox_overlaps(np.ascontiguousarray(all_rois[:, 1:5], dtype=np.float64),
+                             np.ascontiguousarray(gt_boxes_bv[:, :4], dtype=np.float64))     # :232-234
+    gt_assignment = overlaps.argmax(axis=1)
+    max_overlaps = overlaps.max(axis=1)
+    labels = gt_boxes_bv[gt_assignment, 4]
+    fg_inds = np.where(max_overlaps >= c["FG_THRESH"])[0]                                    # :244
+    fg_n = int(min(fg_rois_per_image, fg_inds.size))
+    if fg_inds.size > 0:
+        fg_inds = npr.choice(fg_inds, size=fg_n, replace=False)
+    bg_inds = np.where((max_overlaps < c["BG_THRESH_HI"]) & (max_overlaps >= c["BG_THRESH_LO"]))[0]   # :258-259
+    bg_n = min(rois_per_image - fg_n, bg_inds.size)
+    if bg_inds.size > 0:
+        bg_inds = npr.choice(bg_inds, size=bg_n, replace=False)
+    keep_inds = np.append(fg_inds, bg_inds).astype(np.int64)                                 # :272
+    labels = labels[keep_inds]
+    labels[fg_n:] = 0
+    rois_bv = all_rois[keep_inds]
+    rois_3d = all_rois_3d[keep_inds]
+    rois_cnr = lidar_3d_to_corners(rois_3d[:, 1:7])                                          # :283
+    targets = bbox_transform_cnr(rois_cnr, gt_boxes_corners[gt_assignment[keep_inds], :24])  # :293-294
+    data = np.hstack((labels[:, np.newaxis], targets)).astype(np.float32, copy=False)
+    clss = np.array(data[:, 0], dtype=np.uint16, copy=True)                                  # :184-192
+    bbox_targets = np.zeros((clss.size, 24 * _num_classes), dtype=np.float32)
+    for ind in np.where(clss > 0)[0]:
+        bbox_targets[ind, 24 * clss[ind]:24 * clss[ind] + 24] = data[ind, 1:]
+    calib = np.asarray(calib)
+    rois_img = lidar_cnr_to_img(rois_cnr, calib[3], calib[2], calib[0])                      # :77-79
+    rois_img = np.hstack((rois_bv[:, 0].reshape(-1, 1), rois_img))
+    out = (rois_bv.reshape(-1, 5).astype(np.float32), rois_img.reshape(-1, 5).astype(np.float32),
+           labels.reshape(-1, 1).astype(np.int32), bbox_targets.reshape(-1, _num_classes * 24).astype(np.float32),
+           rois_3d.reshape(-1, 7).astype(np.float32))
+    if return_stages:
+        return out + (dict(keep_inds=keep_inds, fg_n=fg_n, max_overlaps=max_overlaps, gt_assignment=gt_assignment),)
+    return out
+
+
+def synth_gt(n_gt=6, seed=1234, geom: BevGeometry = REF_GEOMETRY):
+    """SURVEY 8d synthetic ground truth: cars inside the BEV extent -> (gt_boxes_bv (G,5), gt_boxes_3d (G,7),
+    gt_boxes_corners (G,25)) float32, class 1."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(geom.x_min + 5, geom.x_max - 5, n_gt)
+    y = rng.uniform(geom.y_min + 5, geom.y_max - 5, n_gt)
+    z = np.full(n_gt, -0.95)
+    lwh = np.array([3.9, 1.6, 1.56]) * rng.uniform(0.9, 1.1, (n_gt, 3))
+    if n_gt > 1:  # half of the cars are rotated by 90 degrees (length along y) so both anchor shapes get positives
+        lwh[::2, [0, 1]] = lwh[::2, [1, 0]]
+    p3d = np.column_stack((x, y, z, lwh)).astype(np.float32)
+    bv = lidar_3d_to_bv(p3d, geom)
+    cnr = lidar_3d_to_corners(p3d)
+    ones = np.ones((n_gt, 1), np.float32)
+    return np.hstack((bv, ones)).astype(np.float32), np.hstack((p3d, ones)).astype(np.float32), \
+        np.hstack((cnr, ones)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d) -- shared by tests, golden generator and bench
 # ----------------------------------------------------------------------------------------
 # KITTI 000008-like calibration, rows P2, P3, R0_rect (9 values, zero padded), Tr_velo_to_cam

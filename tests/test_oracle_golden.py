@@ -117,3 +117,20 @@ def test_roi_pool_oracle_small(oracle):
     ref = np.zeros(data.size, np.float64)
     np.add.at(ref, arg[m], g[m].astype(np.float64))
     assert np.allclose(dd.reshape(-1), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_target_layers_golden(oracle, golden_dir):
+    """anchor_target_layer / proposal_target_layer_3d restatements against vectors made by the reference itself
+    (tests/golden/make_golden_targets.py), consuming numpy's global RandomState exactly as the reference does."""
+    g = np.load(os.path.join(golden_dir, "targets.npz"))
+    hf, wf = int(g["hf"]), int(g["wf"])
+    cls = np.zeros((1, hf, wf, 8), np.float32)
+    np.random.seed(int(g["seed"]))
+    labels, targets, anchors, anchors_3d = oracle.anchor_target_layer(cls, g["gt_bv"], g["gt_3d"], g["im_info"])
+    assert np.array_equal(labels, g["at_labels"])
+    assert np.array_equal(targets, g["at_targets"])
+    assert np.array_equal(anchors, g["at_anchors"]) and np.array_equal(anchors_3d, g["at_anchors_3d"])
+    np.random.seed(int(g["seed"]) + 1)
+    out = oracle.proposal_target_layer_3d(g["rois_bv"], g["rois_3d"], g["gt_bv"], g["gt_3d"], g["gt_cnr"], g["calib"], 2)
+    for got, key in zip(out, ("pt_rois_bv", "pt_rois_img", "pt_labels", "pt_targets", "pt_rois_3d")):
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key

@@ -51,3 +51,28 @@ def test_nms_and_iou_random(oracle, ref):
     b = d[:500, :4].astype(np.float64)
     q = d[500:530, :4].astype(np.float64)
     assert np.array_equal(ref.cython_bbox.bbox_overlaps(b, q), oracle.bbox_overlaps(b, q))
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_target_layers_full_shape(oracle, ref, seed):
+    """anchor_target_layer + proposal_target_layer_3d at the reference shape (75x75 map, 22 500 anchors), both sides
+    drawing from numpy's global RandomState with the same seed."""
+    gt_bv, gt_3d, gt_cnr = oracle.synth_gt(6, seed=seed)
+    cls = np.zeros((1, 75, 75, 8), np.float32)
+    im_info = np.array([[601, 601, 1]], dtype=np.float32)
+    np.random.seed(seed)
+    want = ref.anchor_target_layer_tf.anchor_target_layer(cls, gt_bv, gt_3d, im_info, [8, ], [1.0, 1.0])
+    np.random.seed(seed)
+    got = oracle.anchor_target_layer(cls, gt_bv, gt_3d, im_info)
+    for w, g in zip(want, got):
+        assert w.dtype == g.dtype and np.array_equal(w, g)
+    prob, deltas = oracle.synth_rpn_outputs(75, 75, seed=seed + 40)
+    rois_bv, _, rois_3d = ref.proposal_layer_tf.proposal_layer_3d(prob, deltas, im_info, oracle.KITTI_CALIB, "TRAIN",
+                                                                 [8, ], [1.0, 1.0])
+    np.random.seed(seed + 1)
+    want = ref.proposal_target_layer_tf.proposal_target_layer_3d(rois_bv, rois_3d, gt_bv, gt_3d, gt_cnr,
+                                                                 oracle.KITTI_CALIB, 2)
+    np.random.seed(seed + 1)
+    got = oracle.proposal_target_layer_3d(rois_bv, rois_3d, gt_bv, gt_3d, gt_cnr, oracle.KITTI_CALIB, 2)
+    for w, g in zip(want, got):
+        assert w.dtype == g.dtype and np.array_equal(w, g)
