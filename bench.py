@@ -169,9 +169,84 @@ def run_cpu_reference(steps, warmup, frames):
 CONFIG = {"workload": "configs[1]: full MV3D inference batch=1 per GPU: 120k-pt LiDAR -> BEV 701x801x36 raster, "
                       "BEV+RGB(375x1242) VGG16 trunks, 3D-RPN + proposal layer (6000/300, NMS 0.7), fused 2-view ROI "
                       "pool, fc fusion head; FV view absent from the reference (network.py:313-315) and not built",
-          "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective",
+          "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective", "execution": "one CUDA graph per frame (FrameRunner), "
+          "BEV and RGB trunks on two captured streams",
           "l2_policy": "per-frame working set (144 MB/activation at conv1, 411 MB fc6 weights) exceeds the 126 MB L2; "
                        "4 distinct frames rotate"}
+
+
+def run_train_bench(args, rank, world, local_rank):
+    """BASELINE configs[2]: MV3D train step fwd+bwd+Adam, batch = 2 frames per GPU (N>1: one NCCL all-reduce of the flat
+    gradient buffer per step).  Returns the dict that goes under "train_step" (and is the main line with --workload train)."""
+    import torch
+    import torch.distributed as dist
+
+    from mv3d_tf_b200 import _lib, kernels
+    from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
+    from mv3d_tf_b200.fast_rcnn.train_mv import SolverWrapper
+    from mv3d_tf_b200.networks.factory import get_network
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+    from mv3d_tf_b200.utils.transform import CFG_GEOMETRY
+    from oracle import mv3d_oracle as orc  # synthetic GT generator + calib constants only
+
+    cfg_from_end2end_yml()
+    cfg.USE_GPU_NMS = False
+    B = args.train_batch
+    precise = args.mode == "precise"
+    net = get_network("MV3D_train", bv_channels=36, precise=precise, geometry=CFG_GEOMETRY)
+    net.init_weights(seed=7, mode="he")
+    sw = SolverWrapper(network=net, keep_prob=0.5, process_group=dist.group.WORLD if world > 1 else None)
+    raster = BevRasterizer(**BEV)
+    n_sets = 2
+    sets = []
+    for sidx in range(n_sets):
+        fr = [synth_frame(100 + 16 * rank + sidx * B + b) for b in range(B)]
+        gts = [orc.synth_gt(6, seed=500 + 16 * rank + sidx * B + b, geom=orc.CFG_GEOMETRY) for b in range(B)]
+        sets.append(dict(pts=[torch.from_numpy(f[0]).cuda() for f in fr],
+                         img=torch.from_numpy(np.concatenate([f[1] for f in fr])).cuda(),
+                         gt_bv=[g[0] for g in gts], gt_3d=[g[1] for g in gts], gt_cnr=[g[2] for g in gts]))
+    im_info = np.array([[701, 801, 1]], np.float32)
+    np.random.seed(3 + rank)   # tools/train_net.py:78-80 seeds numpy with cfg.RNG_SEED = 3
+
+    def step(i):
+        s_ = sets[i % n_sets]
+        bv = raster.to_pad(s_["pts"], precise=precise)
+        return sw.train_step(dict(image_data=s_["img"], lidar_bv_data=bv, im_info=im_info, gt_boxes_bv=s_["gt_bv"],
+                                  gt_boxes_3d=s_["gt_3d"], gt_boxes_corners=s_["gt_cnr"], calib=orc.KITTI_CALIB))
+
+    stream = torch.cuda.current_stream()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.train_steps):
+        loss = step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.train_steps
+    launches = _lib.launch_count() // args.train_steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    # per-GEMM-launch events: forward GEMMs, backward-data GEMMs, backward-filter GEMMs
+    kernels.GEMM_EVENTS = []
+    step(0)
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for a, b in kernels.GEMM_EVENTS)
+    n_gemm = len(kernels.GEMM_EVENTS)
+    kernels.GEMM_EVENTS = None
+    return {"ms": ms, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
+            "n_gpus": world, "gpu_launches_per_step": launches, "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
+            "loss": [float(x) for x in loss.tolist()], "optimizer": "Adam lr=1e-5 (TF-1.0 defaults), keep_prob 0.5",
+            "grad_allreduce": "NCCL all-reduce of the flat fp32 gradient buffer (%.0f MB)" % (sw.grad.numel() * 4 / 1e6)
+            if world > 1 else "off (single GPU)", "mode": args.mode,
+            "workload": "configs[2]: MV3D train step fwd+bwd+Adam, %d frames/GPU: 120k-pt LiDAR -> BEV 701x801x36, RGB "
+                        "375x1242, 6 GT cars/frame, RPN 12000/2000 proposals, 128 sampled rois/frame" % B}
 
 
 def main():
@@ -182,6 +257,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="precise", choices=["precise", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: configs[1] frames/s (the headline); train: configs[2] train-step ms only")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed train steps reported under train_step")
+    ap.add_argument("--train-batch", type=int, default=2)
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step leg of the default run")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,6 +300,18 @@ def main():
     from mv3d_tf_b200.utils.transform import CFG_GEOMETRY
     from oracle import mv3d_oracle as orc  # KITTI_CALIB constants + synthetic generators only
 
+    if args.workload == "train":
+        tr = run_train_bench(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps({"metric": "MV3D train-step ms", "value": tr["ms"], "unit": "ms", "n_gpus": world,
+                              "steps": tr["steps"], "warmup": max(args.warmup, 3), "ms_per_step": tr["ms"],
+                              "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
+                              "data": "synthetic", "config": {"workload": tr["workload"], "mode": args.mode},
+                              "gpu_launches": tr["gpu_launches_per_step"] * tr["steps"], "train_step": tr}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False  # reproduce the DEVICE=cpu rule (cpu_nms `>=`), the parity target
     net = get_network("MV3D_test", bv_channels=36, precise=(args.mode == "precise"), geometry=CFG_GEOMETRY)
@@ -234,26 +327,24 @@ def main():
 
     precise = args.mode == "precise"
 
+    from mv3d_tf_b200.fast_rcnn.test_mv import FrameRunner
+
+    # The product call: the whole frame captured once as a CUDA graph (FrameRunner), replayed per frame.
+    runner = FrameRunner(net, raster, N_POINTS, IMG_HW, im_info, fetch=("cls_prob", "bbox_pred", "roi_data_bv"),
+                         use_graph=not args.no_graph)
+    runner.load_device(dev_frames[0][0], dev_frames[0][1], calib)
+    _lib.reset_launch_count()
+    runner.capture()
+    launches_per_frame = _lib.launch_count() // (3 if not args.no_graph else 2)
+
     def step_device(i):
         pts, img = dev_frames[i % n_frames]
-        bv = raster.to_pad(pts, precise=precise)  # LiDAR -> BEV directly in the trunk's input layout
-        return net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: calib})
-
-    host_out = None
+        runner.load_device(pts, img)      # D2D into the graph's static inputs (4 distinct frames rotate)
+        return runner.replay()
 
     def step_e2e(i):
-        nonlocal host_out
         pts_h, img_h = pin_frames[i % n_frames]
-        pts = pts_h.cuda(non_blocking=True)
-        img = img_h.cuda(non_blocking=True)
-        bv = raster.to_pad(pts, precise=precise)
-        outs = net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: calib})
-        if host_out is None:
-            host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-        for h, o in zip(host_out, outs):
-            h.copy_(o, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller holds the frame's detections before the next frame
-        return outs
+        return runner(pts_h, img_h, calib)   # pinned host in -> H2D, graph, D2H -> pinned host out, one sync
 
     def barrier():
         if world > 1:
@@ -278,24 +369,25 @@ def main():
 
     for i in range(warmup):
         step_device(i)
-    _lib.reset_launch_count()
     with ClockSampler(local_rank) as clk:
         ms_dev, _ = timed(step_device, args.steps)
-        launches = _lib.launch_count()
+        launches = launches_per_frame * args.steps
         for i in range(warmup):
             step_e2e(i)
         _, ms_e2e_wall = timed(step_e2e, args.steps)
     value = world * args.steps / (ms_dev * 1e-3)
     e2e = world * args.steps / (ms_e2e_wall * 1e-3)
     h2d = sum(int(t.numel() * t.element_size()) for t in pin_frames[0])
-    d2h = sum(int(t.numel() * t.element_size()) for t in host_out)
+    d2h = sum(int(t.numel() * t.element_size()) for t in runner.host)
 
     # ---- roofline of the dominant kernel (conv/fc tcgen05 GEMM): per-launch CUDA events on the launch stream
     kernels.GEMM_EVENTS = []
-    other_ms = None
+    net.use_side_stream = False   # serialise the two trunks so that every event pair brackets exactly one kernel
     for i in range(3):
-        step_device(i)
+        runner.load_device(*dev_frames[i % n_frames])
+        runner._forward()             # eager replay of the same program (events cannot be read inside a graph)
     torch.cuda.synchronize()
+    net.use_side_stream = True
     gemm_ms = sum(a.elapsed_time(b) for a, b in kernels.GEMM_EVENTS) / 3.0
     n_gemm = len(kernels.GEMM_EVENTS) // 3
     kernels.GEMM_EVENTS = None
@@ -324,6 +416,13 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
 
+    if not args.no_train:
+        del net
+        torch.cuda.empty_cache()
+        try:
+            line["train_step"] = run_train_bench(args, rank, world, local_rank)
+        except Exception as e:  # the inference headline must survive a failure of the secondary leg
+            line["train_step"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, ms, cores = run_cpu_reference(2, 1, frames)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",

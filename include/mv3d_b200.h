@@ -104,6 +104,8 @@ typedef struct {
     double nms_thresh;
     int nms_rule_ge;
     float batch_index;
+    const float* d_proj; /* optional DEVICE copy of the 12 projection floats; when set it overrides h_proj (which may
+                            then be NULL) so that a captured CUDA graph can be replayed with a per-frame calib */
 } mv3d_proposal_params;
 
 size_t mv3d_proposal_workspace_bytes(const mv3d_proposal_params* p);

@@ -20,7 +20,7 @@ class ProposalParams(C.Structure):
                 ("im_h", c_float), ("im_w", c_float), ("im_scale", c_float),
                 ("img_h", c_float), ("img_w", c_float), ("min_size", c_float),
                 ("pre_nms_top_n", c_int), ("post_nms_top_n", c_int),
-                ("nms_thresh", c_double), ("nms_rule_ge", c_int), ("batch_index", c_float)]
+                ("nms_thresh", c_double), ("nms_rule_ge", c_int), ("batch_index", c_float), ("d_proj", c_void_p)]
 
 
 class RoiView(C.Structure):

@@ -22,6 +22,7 @@ constexpr int kBins = 4096;
 
 struct DecodeConst {
     float M[12];  // (P2.R0).Tr, float32 row-major 3x4
+    const float* dM;  // optional: the same 12 floats in DEVICE memory (CUDA-graph replay with a per-frame calib)
     double xn, yn, x_min, y_min, res;
     float clip_x, clip_y;  // im_w - 1, im_h - 1 (float32)
     float min_size;        // RPN_MIN_SIZE * im_scale (float32)
@@ -105,7 +106,10 @@ __device__ __forceinline__ Decoded decode_one(const float* __restrict__ prob, co
     const float ws = __fadd_rn(__fsub_rn(x2, x1), 1.f), hs = __fadd_rn(__fsub_rn(y2, y1), 1.f);
     const bool keep_size = (ws >= k.min_size) && (hs >= k.min_size);           // _filter_boxes :336-341
     // lidar_3d_to_corners (transform.py:305-313) + lidar_cnr_to_img (:483-500, :369-386)
-    corners_to_img_box(k.M, xp, xm, yp, ym, zp, zm, o.img);
+    float Mloc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) Mloc[q] = k.dM ? __ldg(k.dM + q) : k.M[q];
+    corners_to_img_box(Mloc, xp, xm, yp, ym, zp, zm, o.img);
     const bool keep_img = (-50 <= o.img[0]) && (o.img[2] <= k.img_x_max) && (-50 <= o.img[1]) &&
                           (o.img[3] <= k.img_y_max);                            // _filter_img_boxes :343-352
     o.keep = keep_size && keep_img;
@@ -248,8 +252,9 @@ static ProposalWs proposal_layout(const mv3d_proposal_params* p) {
 }
 
 static int make_decode_const(const mv3d_proposal_params* p, const float* h_proj, DecodeConst* k) {
-    if (!p || !h_proj || p->Hf <= 0 || p->Wf <= 0 || p->A <= 0) return MV3D_ERR_ARG;
-    for (int i = 0; i < 12; ++i) k->M[i] = h_proj[i];
+    if (!p || (!h_proj && !p->d_proj) || p->Hf <= 0 || p->Wf <= 0 || p->A <= 0) return MV3D_ERR_ARG;
+    for (int i = 0; i < 12; ++i) k->M[i] = h_proj ? h_proj[i] : 0.f;
+    k->dM = p->d_proj;
     k->xn = p->xn; k->yn = p->yn; k->x_min = p->x_min; k->y_min = p->y_min; k->res = p->res;
     k->clip_x = p->im_w - 1.0f;  // im_shape[1] - 1 on a float32 array element
     k->clip_y = p->im_h - 1.0f;

@@ -23,8 +23,9 @@ class MV3D_test(Network):
                   'gt_boxes_3d': self.gt_boxes_3d, 'gt_boxes_corners': self.gt_boxes_corners}
         super().__init__(inputs, trainable=trainable, **kw)
 
-    def _vgg_trunk(self, source, suffix):
+    def _vgg_trunk(self, source, suffix, side=False):
         s = suffix
+        first = len(self._program)
         (self.feed(source)
              .conv(3, 3, 64, 1, 1, name='conv1_1' + s)
              .conv(3, 3, 64, 1, 1, name='conv1_2' + s)
@@ -42,10 +43,13 @@ class MV3D_test(Network):
              .conv(3, 3, 512, 1, 1, name='conv5_1' + s)
              .conv(3, 3, 512, 1, 1, name='conv5_2' + s)
              .conv(3, 3, 512, 1, 1, name='conv5_3' + s))
+        if side:  # independent of the other trunk until roi_pool: eligible for the second stream
+            for n in self._program[first:]:
+                n.attrs['side'] = True
 
     def setup(self):
         self._vgg_trunk('lidar_bv_data', '')     # MV3D_test.py:33-49
-        self._vgg_trunk('image_data', '_2')      # :51-67
+        self._vgg_trunk('image_data', '_2', side=True)      # :51-67
         # ========= RPN ============  (:70-86)
         (self.feed('conv5_3')
              .conv(3, 3, 512, 1, 1, name='rpn_conv/3x3')

@@ -90,6 +90,8 @@ class Network(object):
         self.native_fc_layout = False   # True: fc-after-roi_pool weights are stored with rows already in (H,W,C) order
         self.dropout_seed = 0
         self.last_vals = None
+        self.use_side_stream = True     # independent branches marked 'side' (the RGB trunk) run on a second stream
+        self._side_stream = None
         self.setup()
 
     def setup(self):
@@ -239,7 +241,9 @@ class Network(object):
             prob = vals[node.inputs[0]].dense
             deltas = vals[node.inputs[1]].dense
             im_info = np.asarray(vals[node.inputs[2]].extra, dtype=np.float32).reshape(-1, 3)
-            calib = np.asarray(vals[node.inputs[3]].extra, dtype=np.float32)
+            calib = vals[node.inputs[3]].extra
+            if not isinstance(calib, torch.Tensor):
+                calib = np.asarray(calib, dtype=np.float32)
             B, H, W = prob.shape[0], prob.shape[1], prob.shape[2]
             info = tuple(float(x) for x in im_info[0])
             key = (H, W, cfg_key, int(_feat_stride), info, cfg[cfg_key].RPN_PRE_NMS_TOP_N,
@@ -251,7 +255,10 @@ class Network(object):
                                                                   device=self.device)
             outs = []
             for b in range(B):  # the reference asserts B == 1; frames of a batch are independent
-                cb = calib.reshape(-1, 4, 12)[b if calib.size > 48 else 0]
+                if isinstance(calib, torch.Tensor):
+                    cb = calib.view(-1, 12)[b if calib.numel() > 12 else 0]
+                else:
+                    cb = calib.reshape(-1, 4, 12)[b if calib.size > 48 else 0]
                 outs.append(pl(prob[b], deltas[b], cb, batch_index=float(b)))
             if B == 1:
                 o = outs[0]
@@ -514,15 +521,39 @@ class Network(object):
                 vals[node] = Val(pad=v)
             elif node.name.startswith('gt_'):
                 vals[node] = Val(extra=v)   # numpy / tensor, or a list with one array per frame
+            elif node.name == 'calib' and isinstance(v, torch.Tensor) and v.is_cuda:
+                vals[node] = Val(extra=v)   # (12,) / (B,12) projection floats already on the device (graph replay)
             elif node.name in ('im_info', 'calib', 'keep_prob'):
                 vals[node] = Val(extra=v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
             else:
                 t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
                 vals[node] = Val(dense=t.to(self.device, dtype=torch.float32).contiguous())
         needed = self._needed(fetch_nodes)
+        main = torch.cuda.current_stream()
+        side = None
+        if self.use_side_stream and not self.training and any(n.attrs.get('side') for n in needed):
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            side = self._side_stream
+        forked = joined = False
         for n in self._program:
-            if n in needed:
-                vals[n] = n.fn(vals, n)
+            if n not in needed:
+                continue
+            if side is not None and n.attrs.get('side'):
+                if not forked:
+                    side.wait_stream(main)   # the branch input (fed before the loop) is ready
+                    forked = True
+                with torch.cuda.stream(side):
+                    vals[n] = n.fn(vals, n)
+                continue
+            # (roi_pool launches are fused across views, so any roi_pool node may read the side branch's output)
+            if forked and not joined and (n.kind == 'roi_pool' or
+                                          any(isinstance(i, Node) and i.attrs.get('side') for i in n.inputs)):
+                main.wait_stream(side)
+                joined = True
+            vals[n] = n.fn(vals, n)
+        if forked and not joined:
+            main.wait_stream(side)
         self.last_vals = vals if self.training else None
         out = []
         for n in fetch_nodes:

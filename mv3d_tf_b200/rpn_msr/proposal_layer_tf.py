@@ -47,13 +47,18 @@ class ProposalLayer3D:
         self.anchors3d = torch.from_numpy(np.ascontiguousarray(a3d)).to(self.device)
         self._ws = torch.empty(lib().mv3d_proposal_workspace_bytes(C.byref(p)), dtype=torch.uint8, device=self.device)
 
-    def __call__(self, prob: torch.Tensor, deltas: torch.Tensor, calib: np.ndarray, batch_index: float = 0.0):
-        """prob (Hf,Wf,2A) / deltas (Hf,Wf,6A) float32 CUDA.  Returns dict of device tensors (capacity rows,
-        rows >= num are zero) and `num` (int32[1], device)."""
+    def __call__(self, prob: torch.Tensor, deltas: torch.Tensor, calib, batch_index: float = 0.0):
+        """prob (Hf,Wf,2A) / deltas (Hf,Wf,6A) float32 CUDA.  `calib`: the (4,12) host array, or a float32 CUDA tensor
+        with the 12 projection floats (P2.R0).Tr already on the device (CUDA-graph replay).  Returns dict of device
+        tensors (capacity rows, rows >= num are zero) and `num` (int32[1], device)."""
         assert prob.is_cuda and prob.dtype == torch.float32 and prob.numel() == self.N * 2
         assert deltas.is_cuda and deltas.dtype == torch.float32 and deltas.numel() == self.N * 6
         prob, deltas = prob.contiguous(), deltas.contiguous()
-        proj = projection_matrix(calib)
+        if isinstance(calib, torch.Tensor):
+            assert calib.is_cuda and calib.dtype == torch.float32 and calib.numel() == 12
+            proj, self.params.d_proj = None, calib.data_ptr()
+        else:
+            proj, self.params.d_proj = projection_matrix(calib), None
         R, dev = self.capacity, self.device
         out = dict(bv=torch.empty((R, 5), dtype=torch.float32, device=dev),
                    img=torch.empty((R, 5), dtype=torch.float32, device=dev),
