@@ -40,9 +40,30 @@ __device__ __forceinline__ bool point_cell(const RasterGeom& g, float x, float y
     return true;
 }
 
-__global__ void raster_count_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
-                                    int* __restrict__ tile_count) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// Pass 1: zero-fill the whole output at streaming-store speed AND count the points per tile, in one launch (the fill
+// is the HBM-bound part of the rasteriser: 4*H*W*C bytes; ~99 % of the cells stay zero).
+// Slices that can contain z: lo[i] = h0 + i*zres (np.arange) and hi[i] = lo[i] + zres, so every i with
+// lo[i] <= z < hi[i] lies within one of floor((z - lo[0]) / zres); the exact float64 test is still applied to each.
+__device__ __forceinline__ void slice_window(const RasterGeom& g, double z, int& s_lo, int& s_hi) {
+    if (g.nslices <= 0) { s_lo = 0; s_hi = -1; return; }
+    const double step = g.hi[0] - g.lo[0];
+    const double c = floor((z - g.lo[0]) / step);
+    if (!(c >= -2.0 && c <= (double)g.nslices + 1.0)) { s_lo = 0; s_hi = -1; return; }  // also rejects NaN
+    s_lo = max(0, (int)c - 1);
+    s_hi = min(g.nslices - 1, (int)c + 1);
+}
+
+__global__ void raster_fill_count_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                         int* __restrict__ tile_count, uint4* __restrict__ out_a, long long vec_a,
+                                         uint4* __restrict__ out_b, long long vec_b, float* __restrict__ tail,
+                                         int n_tail) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long i = tid; i < vec_a; i += nthr) __stcs(out_a + i, z);
+    for (long long i = tid; i < vec_b; i += nthr) __stcs(out_b + i, z);
+    if (tid < n_tail) tail[tid] = 0.f;
+    for (long long i = tid; i < n; i += nthr) {
         const float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1];
         int row, col;
         if (point_cell(g, x, y, row, col)) atomicAdd(&tile_count[(row / kTile) * g.tiles_x + col / kTile], 1);
@@ -112,10 +133,11 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
     const int tile = blockIdx.x;
     const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
     const int row0 = ty * kTile, col0 = tx * kTile;
+    const int beg = offset[tile], end = offset[tile + 1];
+    if (beg == end) return;  // no point in this tile: pass 1 already wrote its zeros
     for (int i = threadIdx.x; i < kTile * kTile * ns; i += blockDim.x) tab[i] = 0;
     __syncthreads();
 
-    const int beg = offset[tile], end = offset[tile + 1];
     for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
         const int idx = sorted_idx[i];
         const float* p = pts + (size_t)idx * stride;
@@ -124,7 +146,9 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
         int row, col;
         point_cell(g, x, y, row, col);  // true by construction
         int* cell = tab + ((row - row0) * kTile + (col - col0)) * ns;
-        for (int s = 0; s < ns; ++s)
+        int s_lo, s_hi;
+        slice_window(g, z, s_lo, s_hi);
+        for (int s = s_lo; s <= s_hi; ++s)
             if (z >= g.lo[s] && z < g.hi[s]) atomicMax(&cell[s], idx + 1);  // read_lidar.py:82-83, last index wins
     }
     __syncthreads();
@@ -139,58 +163,40 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
     }
     __syncthreads();
 
-    auto value = [&](int cell, int ch) -> float {
-        if (ch == g.C - 1) {
-            const int w = top_winner[cell];
-            return w ? pts[(size_t)(w - 1) * stride + 3] : 0.f;                                   // :113
-        }
-        if (ch < ns) {
-            const int w = tab[cell * ns + ch];
-            return w ? __fsub_rn(pts[(size_t)(w - 1) * stride + 2], g.h0) : 0.f;                  // :106,110
-        }
-        return 0.f;
-    };
-    const int cols = min(kTile, g.Wout - col0);
-    if (g.pad) {
-        // PAD bf16 hi/lo: 8 channels (16 B) per thread and plane; halo cells hold no points -> zeros
-        const int vpc = g.c_pad / 8;
-        const int run = cols * vpc;
-        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
-            const size_t base = ((size_t)(row0 + r) * g.Wout + col0) * g.c_pad;
-            for (int j = threadIdx.x; j < run; j += blockDim.x) {
-                const int cl = j / vpc, v8 = j - cl * vpc;
-                const int cell = r * kTile + cl;
-                __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int ch = v8 * 8 + e;
-                    split_bf16(ch < g.C ? value(cell, ch) : 0.f, hi[e], lo[e]);
-                }
-                *reinterpret_cast<uint4*>(pad_hi + base + (size_t)cl * g.c_pad + v8 * 8) = *reinterpret_cast<uint4*>(hi);
-                if (pad_lo)
-                    *reinterpret_cast<uint4*>(pad_lo + base + (size_t)cl * g.c_pad + v8 * 8) = *reinterpret_cast<uint4*>(lo);
+    // Store phase: the output was zero-filled by pass 1.  Every point checks whether it is the last writer of its
+    // (cell, slice) entries / of its cell's intensity and, if so, stores that one value: work ~ points, not cells.
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        const int idx = sorted_idx[i];
+        const float* p = pts + (size_t)idx * stride;
+        const float x = p[0], y = p[1], zf = p[2];
+        const double z = (double)zf;
+        int row, col;
+        point_cell(g, x, y, row, col);
+        const int cell = (row - row0) * kTile + (col - col0);
+        const size_t pix = (size_t)row * g.Wout + col;
+        int s_lo, s_hi;
+        slice_window(g, z, s_lo, s_hi);
+        for (int sl = s_lo; sl <= s_hi; ++sl) {
+            if (!(z >= g.lo[sl] && z < g.hi[sl]) || tab[cell * ns + sl] != idx + 1 || sl == g.C - 1) continue;
+            const float v = __fsub_rn(zf, g.h0);                                                  // :106,110
+            if (g.pad) {
+                __nv_bfloat16 h, l;
+                split_bf16(v, h, l);
+                pad_hi[pix * g.c_pad + sl] = h;
+                if (pad_lo) pad_lo[pix * g.c_pad + sl] = l;
+            } else {
+                top[pix * g.C + sl] = v;
             }
         }
-    } else if (g.C % 4 == 0) {
-        const int vpc = g.C / 4;
-        const int run = cols * vpc;
-        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
-            float* out = top + ((size_t)(row0 + r) * g.Wout + col0) * g.C;
-            for (int j = threadIdx.x; j < run; j += blockDim.x) {
-                const int cl = j / vpc, v4 = j - cl * vpc;
-                const int cell = r * kTile + cl;
-                const float4 v = make_float4(value(cell, v4 * 4), value(cell, v4 * 4 + 1), value(cell, v4 * 4 + 2),
-                                             value(cell, v4 * 4 + 3));
-                *reinterpret_cast<float4*>(out + (size_t)cl * g.C + v4 * 4) = v;
-            }
-        }
-    } else {
-        const int run = cols * g.C;  // contiguous floats of one output row inside this tile
-        for (int r = 0; r < kTile && row0 + r < g.Hout; ++r) {
-            float* out = top + ((size_t)(row0 + r) * g.Wout + col0) * g.C;
-            for (int j = threadIdx.x; j < run; j += blockDim.x) {
-                const int cl = j / g.C, ch = j - cl * g.C;
-                out[j] = value(r * kTile + cl, ch);
+        if (top_winner[cell] == idx + 1) {                                                       // :113
+            const float v = p[3];
+            if (g.pad) {
+                __nv_bfloat16 h, l;
+                split_bf16(v, h, l);
+                pad_hi[pix * g.c_pad + g.C - 1] = h;
+                if (pad_lo) pad_lo[pix * g.c_pad + g.C - 1] = l;
+            } else {
+                top[pix * g.C + g.C - 1] = v;
             }
         }
     }
@@ -240,7 +246,28 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(n_tiles + 1), s);
     if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
     const int pgrid = n_points > 0 ? min(ceil_div(n_points, 256), 148 * 8) : 1;
-    if (n_points > 0) raster_count_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, count);
+    {
+        // output planes as 16-byte vectors (+ a scalar tail when the float32 map's size is not a multiple of 4)
+        uint4 *va = nullptr, *vb = nullptr;
+        long long na = 0, nb = 0;
+        float* tail = nullptr;
+        int n_tail = 0;
+        if (pad) {
+            const long long elems = (long long)g.Hout * g.Wout * c_pad;  // c_pad % 8 == 0 -> whole uint4s
+            va = static_cast<uint4*>(d_pad_hi); na = elems / 8;
+            if (d_pad_lo) { vb = static_cast<uint4*>(d_pad_lo); nb = elems / 8; }
+        } else {
+            const long long elems = (long long)H * W * C;
+            if ((reinterpret_cast<uintptr_t>(d_top) & 15) == 0) {
+                va = reinterpret_cast<uint4*>(d_top); na = elems / 4;
+                tail = d_top + na * 4; n_tail = (int)(elems - na * 4);
+            } else {
+                return MV3D_ERR_ARG;  // torch allocations are 256-byte aligned; unaligned views are not supported
+            }
+        }
+        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, n_points, point_stride, g, count, va, na, vb, nb,
+                                                        tail, n_tail);
+    }
     raster_scan_kernel<<<1, 1024, 0, s>>>(count, n_tiles, offset, cursor);
     if (n_points > 0)
         raster_scatter_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, offset, cursor, sorted);

@@ -42,6 +42,8 @@ class SolverWrapper(object):
         self.lr, self.beta1, self.beta2, self.epsilon = lr, beta1, beta2, epsilon
         self.keep_prob = keep_prob
         self.pg = process_group
+        from ..sharding import FlatGradExchange
+        self.exchange = FlatGradExchange(process_group) if process_group is not None else None
         self.step = 0
         net = self.net
         net.training = True
@@ -92,6 +94,10 @@ class SolverWrapper(object):
                                      biases=self.grad[off + nw:off + nw + nb])
         net.native_fc_layout = True
         net._packed.clear()
+        # parameters are declared trunks -> RPN -> fusion head, so the head (fc6_1 ... bbox_pred) is the buffer's tail
+        self._head_off = self.slices['fc6_1'][0] if 'fc6_1' in self.slices else total
+        assert all(self.slices[n][0] >= self._head_off for n in self.names if n.startswith(('fc', 'cls_score', 'bbox_pred')))
+        assert all(self.slices[n][0] < self._head_off for n in self.names if n.startswith(('conv', 'rpn')))
 
     def export_params(self):
         """{layer: {'weights', 'biases'}} numpy dict in the reference's variable layouts (the `.npy` format of
@@ -155,16 +161,13 @@ class SolverWrapper(object):
         self.grad.zero_()
         self.loss.zero_()
         self._backward(vals, kp)
-        if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.grad, group=self.pg)          # ONE exchange step
-            world = dist.get_world_size(self.pg)
-        else:
-            world = 1
+        # the exchange step: one sum over the flat gradient buffer, issued as two NCCL calls so that the
+        # head's 78 % of the bytes (fc6/fc7, finished first) travel while the trunks are still in backward
+        grad_scale = self.exchange.finish(self.grad, self._head_off) if self.exchange is not None else 1.0
         if apply_update:
             self.step += 1
             check(lib().mv3d_adam(ptr(self.theta), ptr(self.grad), ptr(self.m), ptr(self.v), self.theta.numel(),
-                                  self.lr, self.beta1, self.beta2, self.epsilon, self.step, 1.0 / world,
+                                  self.lr, self.beta1, self.beta2, self.epsilon, self.step, grad_scale,
                                   current_stream()), 'mv3d_adam')
             net._packed.clear()
             self._dpacked.clear()
@@ -224,6 +227,9 @@ class SolverWrapper(object):
                                            feat.shape[3], ph, pw, ptr(e['rois']), ptr(dfeat), ptr(e['argmax']),
                                            stream), 'mv3d_roi_pool_backward')
             vals[_node(net, pool)].extra['dfeat'] = dfeat
+
+        if self.exchange is not None:   # head gradients are final: start their all-reduce under the trunk backward
+            self.exchange.start_tail(self.grad, self._head_off)
 
         # ---------------- RPN losses (train_mv.py:94-119) ----------------
         rcls, rbox = vals[_node(net, 'rpn_cls_score')].dense, vals[_node(net, 'rpn_bbox_pred')].dense

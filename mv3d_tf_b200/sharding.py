@@ -43,3 +43,31 @@ def gather_rows(rows: torch.Tensor, dst: int = 0) -> List[torch.Tensor]:
 
 def assign(frames: Sequence, rank: int, world: int) -> list:
     return [frames[i] for i in shard_range(len(frames), rank, world)]
+
+
+class FlatGradExchange:
+    """The training path's one exchange step: a sum over the flat fp32 gradient buffer, issued as two
+    collectives so that the tail of the buffer (the fusion head: fc6/fc7, finished first in backward) travels while the
+    trunks are still being differentiated.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self._pending = None
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def start_tail(self, buf: torch.Tensor, off: int) -> None:
+        if self.world > 1 and off < buf.numel():
+            self._pending = dist.all_reduce(buf[off:], group=self.group, async_op=True)
+
+    def finish(self, buf: torch.Tensor, off: int) -> float:
+        """Reduce the head of the buffer, wait for the tail; returns the 1/world factor the optimizer applies."""
+        if self.world > 1:
+            if off > 0:
+                dist.all_reduce(buf[:off], group=self.group)
+            if self._pending is not None:
+                self._pending.wait()
+                self._pending = None
+        return 1.0 / self.world

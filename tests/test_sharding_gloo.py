@@ -55,3 +55,37 @@ def test_shard_range_properties():
             parts = [list(shard_range(n, r, world)) for r in range(world)]
             assert sum(parts, []) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _exchange_worker(rank, world, port, q):
+    from mv3d_tf_b200.sharding import FlatGradExchange
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = FlatGradExchange(dist.group.WORLD)
+    n, off = 1000, 300
+    buf = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    ex.start_tail(buf, off)                  # the head's gradients travel first ...
+    buf[:off] += 0.5                         # ... while the "trunk backward" still writes its part
+    scale = ex.finish(buf, off)
+    if rank == 0:
+        q.put((buf.clone(), scale))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_exchange_two_ranks():
+    """Training exchange step: sum over ranks of the flat buffer in two collectives; the optimizer's 1/world factor."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 77) % 500
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    buf, scale = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.arange(1000, dtype=torch.float32) * 3
+    want[:300] += 1.0
+    assert torch.equal(buf, want) and scale == 0.5
