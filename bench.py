@@ -58,8 +58,12 @@ def gemm_flops(net, hb, wb, hi, wi, R):
     tb, hf, wf = trunk(hb, wb, net.lidar_bv_data.channels)
     ti, _, _ = trunk(hi, wi, 3)
     total += tb + ti
+    views = 2
+    if getattr(net, "with_fv", False):
+        total += trunk(net.fv_geometry.H, net.fv_geometry.W, 3)[0]
+        views = 3
     total += 2 * 9 * 512 * 512 * hf * wf + 2 * 512 * (8 + 24) * hf * wf          # RPN head
-    total += 2 * (2 * R * 25088 * 2048 + 2 * R * 2048 * 2048) + 2 * R * 4096 * 50  # fusion head
+    total += views * (2 * R * 25088 * 2048 + 2 * R * 2048 * 2048) + 2 * R * (2048 * views) * 50  # fusion head
     return total
 
 
@@ -100,7 +104,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg):
+def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg, views=3):
     """One frame of the reference's CPU path: the oracle port (numpy/C restatement + torch-CPU fp32 graph),
     with the per-box projection loop in the reference's own shape (transform.py:483-500)."""
     bv = orc.point_cloud_2_top(pts, **BEV)[None]
@@ -110,15 +114,20 @@ def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg):
         c5 = net_oracle.trunk(bv, params, "")
         c5_2 = net_oracle.trunk(img, params, "_2")
         prob, bbox = net_oracle.rpn_head(c5, params)
-        rois_bv, rois_img, _ = orc.proposal_layer_3d(prob.numpy(), bbox.numpy(), im_info, calib, "TEST", cfg=cfg,
-                                                     geom=orc.CFG_GEOMETRY, project="loop")
+        rois_bv, rois_img, rois_3d = orc.proposal_layer_3d(prob.numpy(), bbox.numpy(), im_info, calib, "TEST", cfg=cfg,
+                                                           geom=orc.CFG_GEOMETRY, project="loop")
         p1, _ = orc.roi_pool_fwd(c5.numpy(), rois_bv)
         p2, _ = orc.roi_pool_fwd(c5_2.numpy(), rois_img)
-        cls, bb = net_oracle.fusion_head(p1, p2, params)
+        p3 = None
+        if views == 3:   # front view: our specification (the reference has none), same oracle port
+            c5_3 = net_oracle.trunk(orc.point_cloud_2_front(pts)[None], params, "_3")
+            rois_fv = np.hstack((rois_3d[:, :1], orc.lidar_3d_to_fv(rois_3d[:, 1:7]))).astype(np.float32)
+            p3, _ = orc.roi_pool_fwd(c5_3.numpy(), rois_fv)
+        cls, bb = net_oracle.fusion_head(p1, p2, params, pool_fv=p3)
     return cls, bb
 
 
-def make_cpu_params(seed=7):
+def make_cpu_params(seed=7, views=3):
     """Same architecture, random init, built directly on the host (no GPU needed for the reference arm)."""
     import torch
 
@@ -130,7 +139,7 @@ def make_cpu_params(seed=7):
         w = torch.empty(shape)
         torch.nn.init.trunc_normal_(w, 0.0, 1.0, -2.0, 2.0, generator=g)
         params[name] = dict(weights=(w * (2.0 / fan_in) ** 0.5).numpy(), biases=np.zeros(shape[-1], np.float32))
-    for suffix, cin in (("", 36), ("_2", 3)):
+    for suffix, cin in (("", 36), ("_2", 3), ("_3", 3))[:views]:
         c = cin
         for item in ("conv1_1", 64), ("conv1_2", 64), ("conv2_1", 128), ("conv2_2", 128), ("conv3_1", 256), \
                 ("conv3_2", 256), ("conv3_3", 256), ("conv4_1", 512), ("conv4_2", 512), ("conv4_3", 512), \
@@ -138,13 +147,13 @@ def make_cpu_params(seed=7):
             add(item[0] + suffix, (3, 3, c, item[1]))
             c = item[1]
     add("rpn_conv/3x3", (3, 3, 512, 512)); add("rpn_cls_score", (1, 1, 512, 8)); add("rpn_bbox_pred", (1, 1, 512, 24))
-    for b in ("_1", "_2"):
+    for b in ("_1", "_2", "_3")[:views]:
         add("fc6" + b, (25088, 2048)); add("fc7" + b, (2048, 2048))
-    add("cls_score", (4096, 2)); add("bbox_pred", (4096, 48))
+    add("cls_score", (2048 * views, 2)); add("bbox_pred", (2048 * views, 48))
     return params
 
 
-def run_cpu_reference(steps, warmup, frames):
+def run_cpu_reference(steps, warmup, frames, views=3):
     import torch
 
     from oracle import build as ob
@@ -154,21 +163,22 @@ def run_cpu_reference(steps, warmup, frames):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = make_cpu_params()
+    params = make_cpu_params(views=views)
     cfg = {"TEST": dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5)}
     im_info = np.array([[701, 801, 1]], np.float32)
     for i in range(warmup):
-        cpu_frame(orc, net_oracle, params, *frames[i % len(frames)], im_info, orc.KITTI_CALIB, cfg)
+        cpu_frame(orc, net_oracle, params, *frames[i % len(frames)], im_info, orc.KITTI_CALIB, cfg, views)
     t0 = time.perf_counter()
     for i in range(steps):
-        cpu_frame(orc, net_oracle, params, *frames[i % len(frames)], im_info, orc.KITTI_CALIB, cfg)
+        cpu_frame(orc, net_oracle, params, *frames[i % len(frames)], im_info, orc.KITTI_CALIB, cfg, views)
     dt = time.perf_counter() - t0
     return steps / dt, dt / steps * 1e3, cores
 
 
-CONFIG = {"workload": "configs[1]: full MV3D inference batch=1 per GPU: 120k-pt LiDAR -> BEV 701x801x36 raster, "
-                      "BEV+RGB(375x1242) VGG16 trunks, 3D-RPN + proposal layer (6000/300, NMS 0.7), fused 2-view ROI "
-                      "pool, fc fusion head; FV view absent from the reference (network.py:313-315) and not built",
+CONFIG = {"workload": "configs[1]: full MV3D inference batch=1 per GPU: 120k-pt LiDAR -> BEV 701x801x36 + FV 64x512x3 "
+                      "rasters, BEV+FV+RGB(375x1242) VGG16 trunks, 3D-RPN + proposal layer (6000/300, NMS 0.7), fused "
+                      "3-view ROI pool, fc fusion head (the FV view has no reference counterpart, network.py:313-315: "
+                      "it follows this repo's written spec; --views 2 runs the reference's exact two-view network)",
           "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective", "execution": "one CUDA graph per frame (FrameRunner), "
           "BEV and RGB trunks on two captured streams",
           "l2_policy": "per-frame working set (144 MB/activation at conv1, 411 MB fc6 weights) exceeds the 126 MB L2; "
@@ -263,6 +273,8 @@ def main():
     ap.add_argument("--train-batch", type=int, default=2)
     ap.add_argument("--no-train", action="store_true", help="skip the train_step leg of the default run")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--views", type=int, default=3, choices=[2, 3],
+                    help="3: BEV+FV+RGB (BASELINE configs[1]); 2: the reference's own BEV+RGB network")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,11 +286,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        fps, ms, cores = run_cpu_reference(args.steps, max(1, min(args.warmup, 1)), frames)
+        fps, ms, cores = run_cpu_reference(args.steps, max(1, min(args.warmup, 1)), frames, args.views)
         line = {"impl": "reference", "metric": "MV3D inference frames/sec", "value": fps, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, min(args.warmup, 1)), "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": CONFIG,
+                "config": dict(CONFIG, mode="f32", views=args.views),
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d whole frames, 1 per step (numpy/C oracle port of the reference's "
                                            "host layers incl. its per-box projection loop; conv/fc via torch-CPU "
@@ -314,7 +326,8 @@ def main():
 
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False  # reproduce the DEVICE=cpu rule (cpu_nms `>=`), the parity target
-    net = get_network("MV3D_test", bv_channels=36, precise=(args.mode == "precise"), geometry=CFG_GEOMETRY)
+    net = get_network("MV3D_test", bv_channels=36, precise=(args.mode == "precise"), geometry=CFG_GEOMETRY,
+                      fv=(args.views == 3))
     net.init_weights(seed=7, mode="he")
     raster = BevRasterizer(**BEV)
     im_info = np.array([[701, 801, 1]], np.float32)
@@ -412,7 +425,7 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)" if args.mode == "precise" else "bf16",
-            "data": "synthetic", "config": dict(CONFIG, mode=args.mode),
+            "data": "synthetic", "config": dict(CONFIG, mode=args.mode, views=args.views),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
 
@@ -424,7 +437,7 @@ def main():
         except Exception as e:  # the inference headline must survive a failure of the secondary leg
             line["train_step"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, ms, cores = run_cpu_reference(2, 1, frames)
+        fps, ms, cores = run_cpu_reference(2, 1, frames, args.views)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "2 whole frames after 1 warm-up (oracle port; conv/fc torch-CPU fp32)"}
     if rank == 0:

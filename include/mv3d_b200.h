@@ -287,6 +287,22 @@ int mv3d_proposal_targets(const float* d_rois_bv, const float* d_rois_3d, int R,
                           float* d_out_bv, float* d_out_img, int* d_out_labels, float* d_out_targets, float* d_out_3d,
                           void* stream);
 
+/* =============================================================================================
+ * Front view (FV).  No reference counterpart: lib/networks/network.py:313-315 returns None for target='fv'.  The
+ * semantics are this project's specification (oracle/mv3d_oracle.py: FvGeometry, point_cloud_2_front,
+ * lidar_3d_to_fv), after the MV3D paper linked from the reference's README.md:5.
+ *   mv3d_fv_raster: points -> (H,W,3) float32 [z, range, reflectance] and/or the PAD bf16 hi/lo trunk input
+ *     (H+1,W+1,c_pad); cell = floor((atan2(y,x)-theta_min)/dtheta), floor((phi_max-atan2(z,hypot(x,y)))/dphi) in
+ *     float64, x > 0 only, last point in file order wins.  Workspace: mv3d_fv_raster_workspace_bytes(H,W).
+ *   mv3d_rois_to_fv: rois_3d (R,7) -> rois_fv (R,5) [batch,col_min,row_min,col_max,row_max] from the 8 corners.
+ * ============================================================================================= */
+size_t mv3d_fv_raster_workspace_bytes(int H, int W);
+int mv3d_fv_raster(const float* d_points, int n_points, int point_stride, int H, int W, double theta_min_rad,
+                   double dtheta_rad, double phi_max_rad, double dphi_rad, float* d_top, void* d_pad_hi, void* d_pad_lo,
+                   int c_pad, void* d_workspace, size_t workspace_bytes, void* stream);
+int mv3d_rois_to_fv(const float* d_rois_3d, int R, const int* d_num_valid, int H, int W, double theta_min_rad,
+                    double dtheta_rad, double phi_max_rad, double dphi_rad, float* d_rois_fv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,11 @@ SIGNATURES = {
     "mv3d_proposal_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    "mv3d_fv_raster_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mv3d_fv_raster": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "mv3d_rois_to_fv": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_double, c_double, c_double,
+                                c_void_p, c_void_p]),
     "mv3d_bias_act": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                               c_int, c_void_p]),
 }
@@ -137,7 +142,7 @@ KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_nms": 
                     "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1,
                     "mv3d_maxpool2x2_bwd_pad": 1, "mv3d_bias_grad": 1, "mv3d_pack_weights_dgrad": 1,
                     "mv3d_pad_nhwc_masked": 1, "mv3d_dropout": 1, "mv3d_rpn_loss": 1, "mv3d_rcnn_loss": 1,
-                    "mv3d_adam": 1, "mv3d_anchor_targets": 2, "mv3d_roi_overlaps": 1, "mv3d_proposal_targets": 1}
+                    "mv3d_adam": 1, "mv3d_fv_raster": 2, "mv3d_rois_to_fv": 1, "mv3d_anchor_targets": 2, "mv3d_roi_overlaps": 1, "mv3d_proposal_targets": 1}
 _launches = 0
 
 

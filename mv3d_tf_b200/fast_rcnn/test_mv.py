@@ -30,6 +30,10 @@ class FrameRunner:
                  fetch=("cls_prob", "bbox_pred", "roi_data_bv", "roi_data_img"), use_graph=True, device="cuda"):
         self.net, self.raster = net, raster
         self.device = torch.device(device)
+        self.fv_raster = None
+        if getattr(net, 'with_fv', False):   # third view: rasterised from the same (padded) cloud
+            from ..utils.read_lidar import FvRasterizer
+            self.fv_raster = FvRasterizer(net.fv_geometry, device=device)
         self.max_points = int(max_points)
         self.im_info = np.asarray(im_info, np.float32).reshape(-1, 3)
         self.pts = torch.full((self.max_points, 4), FAR, dtype=torch.float32, device=self.device)
@@ -47,8 +51,11 @@ class FrameRunner:
     # ------------------------------------------------------------------
     def _forward(self):
         bv = self.raster.to_pad(self.pts, precise=self.net.precise)
-        outs = self.net.run(self.fetch, {self.net.lidar_bv_data: bv, self.net.image_data: self.img,
-                                          self.net.im_info: self.im_info, self.net.calib: self.proj})
+        feed = {self.net.lidar_bv_data: bv, self.net.image_data: self.img, self.net.im_info: self.im_info,
+                self.net.calib: self.proj}
+        if self.fv_raster is not None:
+            feed[self.net.lidar_fv_data] = self.fv_raster.to_pad(self.pts, precise=self.net.precise)
+        outs = self.net.run(self.fetch, feed)
         return list(outs) + [self.net.last_num_rois]
 
     def capture(self):

@@ -69,13 +69,14 @@ def layer(op):
 
 class Network(object):
     def __init__(self, inputs, trainable=True, precise=True, geometry: BevGeometry = REF_GEOMETRY,
-                 img_size=(375, 1242), device='cuda'):
+                 img_size=(375, 1242), device='cuda', fv_geometry=None):
         self.inputs = []
         self.layers = dict(inputs)
         self.trainable = trainable
         self.precise = precise          # True: 3-pass bf16 hi/lo GEMMs (parity mode); False: single pass
         self.geometry = geometry
         self.img_size = img_size
+        self.fv_geometry = fv_geometry   # None: two-view network exactly as the reference (network.py:313-315)
         self.device = torch.device(device)
         self.params: Dict[str, Dict[str, torch.Tensor]] = {}
         self.param_specs: Dict[str, dict] = {}
@@ -275,12 +276,20 @@ class Network(object):
     @layer
     def proposal_transform(self, input, name, target='bv'):
         assert target in ('bv', 'img', 'fv')
-        if target == 'fv':
+        if target == 'fv' and self.fv_geometry is None:
             return None  # as the reference (network.py:313-315)
         src = input[0] if isinstance(input, (tuple, list)) else input
 
         def run(vals, node):
             e = vals[node.inputs[0]].extra
+            if target == 'fv' and 'fv' not in e:   # project the 3-D proposals into the front-view map
+                p3d = e['p3d'].contiguous()
+                fv = torch.empty((p3d.shape[0], 5), dtype=torch.float32, device=p3d.device)
+                num = e['num'] if (e.get('num') is not None and e['num'].numel() == 1) else None
+                H, W, t0, dt, p1, dp = self.fv_geometry.c_args()
+                check(lib().mv3d_rois_to_fv(ptr(p3d), p3d.shape[0], ptr(num), H, W, t0, dt, p1, dp, ptr(fv),
+                                            current_stream()), 'mv3d_rois_to_fv')
+                e['fv'] = fv
             return Val(dense=e[target], extra=e)
         return self._node(name, 'rois', [src], run)
 
@@ -530,30 +539,38 @@ class Network(object):
                 vals[node] = Val(dense=t.to(self.device, dtype=torch.float32).contiguous())
         needed = self._needed(fetch_nodes)
         main = torch.cuda.current_stream()
-        side = None
-        if self.use_side_stream and not self.training and any(n.attrs.get('side') for n in needed):
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream()
-            side = self._side_stream
-        forked = joined = False
+        # independent branches (attrs['side'] = k > 0: the RGB and FV trunks) run on their own streams, forked when first
+        # reached and joined before the first node that may consume any of them
+        use_side = self.use_side_stream and not self.training
+        forked, joined = {}, set()
+
+        def join_all():
+            for k, st in forked.items():
+                if k not in joined:
+                    main.wait_stream(st)
+                    joined.add(k)
         for n in self._program:
             if n not in needed:
                 continue
-            if side is not None and n.attrs.get('side'):
-                if not forked:
-                    side.wait_stream(main)   # the branch input (fed before the loop) is ready
-                    forked = True
-                with torch.cuda.stream(side):
+            k = n.attrs.get('side') if use_side else None
+            if k:
+                st = forked.get(k)
+                if st is None:
+                    if self._side_stream is None:
+                        self._side_stream = {}
+                    st = self._side_stream.get(k)
+                    if st is None:
+                        st = self._side_stream[k] = torch.cuda.Stream()
+                    st.wait_stream(main)   # the branch input (fed before the loop) is ready
+                    forked[k] = st
+                with torch.cuda.stream(st):
                     vals[n] = n.fn(vals, n)
                 continue
-            # (roi_pool launches are fused across views, so any roi_pool node may read the side branch's output)
-            if forked and not joined and (n.kind == 'roi_pool' or
-                                          any(isinstance(i, Node) and i.attrs.get('side') for i in n.inputs)):
-                main.wait_stream(side)
-                joined = True
+            # (roi_pool launches are fused across views, so any roi_pool node may read a side branch's output)
+            if forked and (n.kind == 'roi_pool' or any(isinstance(i, Node) and i.attrs.get('side') for i in n.inputs)):
+                join_all()
             vals[n] = n.fn(vals, n)
-        if forked and not joined:
-            main.wait_stream(side)
+        join_all()
         self.last_vals = vals if self.training else None
         out = []
         for n in fetch_nodes:

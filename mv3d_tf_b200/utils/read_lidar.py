@@ -92,3 +92,52 @@ def point_cloud_2_top(points, res=0.1, zres=0.3, side_range=(-10., 10.), fwd_ran
     pts = torch.from_numpy(np.ascontiguousarray(points[:, :4], dtype=np.float32)).cuda()
     r = BevRasterizer(res, zres, side_range, fwd_range, height_range, device=pts.device)
     return r(pts).cpu().numpy()
+
+
+class FvRasterizer:
+    """LiDAR -> cylindrical front-view map (H,W,3) [z, range, reflectance] (csrc/front_view.cu).  The reference has no
+    front view; see utils.transform.FvGeometry."""
+
+    def __init__(self, geom=None, device="cuda"):
+        from .transform import FV_GEOMETRY
+
+        self.g = geom or FV_GEOMETRY
+        self.device = torch.device(device)
+        self._ws = torch.empty(lib().mv3d_fv_raster_workspace_bytes(self.g.H, self.g.W), dtype=torch.uint8,
+                               device=self.device)
+
+    @property
+    def shape(self):
+        return (self.g.H, self.g.W, 3)
+
+    def _call(self, pts, top, hi, lo, c_pad):
+        assert pts.is_cuda and pts.dtype == torch.float32 and pts.dim() == 2 and pts.shape[1] >= 4
+        pts = pts.contiguous()
+        H, W, t0, dt, p1, dp = self.g.c_args()
+        check(lib().mv3d_fv_raster(ptr(pts), pts.shape[0], pts.shape[1], H, W, t0, dt, p1, dp, ptr(top), ptr(hi),
+                                   ptr(lo), c_pad, ptr(self._ws), self._ws.numel(), current_stream()), "mv3d_fv_raster")
+
+    def __call__(self, points: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.shape, dtype=torch.float32, device=points.device)
+        self._call(points, out, None, None, 0)
+        return out
+
+    def to_pad(self, clouds, precise: bool = True):
+        """One cloud per frame -> the trunk's PAD input (bf16 hi/lo, zero halo, 16 channels)."""
+        from ..kernels import BF16, PadAct, pad_channels
+
+        if isinstance(clouds, torch.Tensor):
+            clouds = [clouds]
+        cp = pad_channels(3)
+        dev = clouds[0].device
+        hi = torch.empty((len(clouds), self.g.H + 1, self.g.W + 1, cp), dtype=BF16, device=dev)
+        lo = torch.empty_like(hi) if precise else None
+        for b, pts in enumerate(clouds):
+            self._call(pts, None, hi[b], lo[b] if lo is not None else None, cp)
+        return PadAct(hi, lo, len(clouds), self.g.H, self.g.W, 3)
+
+
+def point_cloud_2_front(points, geom=None):
+    """numpy (N,>=4) in, numpy (H,W,3) float32 out."""
+    pts = torch.from_numpy(np.ascontiguousarray(points[:, :4], dtype=np.float32)).cuda()
+    return FvRasterizer(geom, device=pts.device)(pts).cpu().numpy()

@@ -62,3 +62,31 @@ def projection_matrix(calib: np.ndarray) -> np.ndarray:
     calib = np.asarray(calib)
     tr, r0, p2 = calib[3].reshape(3, 4), calib[2].reshape(4, 3), calib[0].reshape(3, 4)
     return np.ascontiguousarray(np.dot(np.dot(p2, r0), tr), dtype=np.float32)
+
+
+@dataclass(frozen=True)
+class FvGeometry:
+    """Cylindrical front-view map (no reference counterpart; specification in oracle/mv3d_oracle.py FvGeometry):
+    H rows over elevation [phi_min, phi_max] degrees (row 0 = top), W columns over azimuth [theta_min, theta_max)."""
+
+    H: int = 64
+    W: int = 512
+    theta_min: float = -45.0
+    theta_max: float = 45.0
+    phi_min: float = -24.9
+    phi_max: float = 2.0
+
+    @property
+    def dtheta(self) -> float:
+        return float(np.deg2rad(self.theta_max - self.theta_min) / self.W)
+
+    @property
+    def dphi(self) -> float:
+        return float(np.deg2rad(self.phi_max - self.phi_min) / self.H)
+
+    def c_args(self):
+        """(H, W, theta_min_rad, dtheta, phi_max_rad, dphi) in the order the C ABI takes them."""
+        return (self.H, self.W, float(np.deg2rad(self.theta_min)), self.dtheta, float(np.deg2rad(self.phi_max)), self.dphi)
+
+
+FV_GEOMETRY = FvGeometry()

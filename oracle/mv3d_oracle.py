@@ -545,6 +545,79 @@ def synth_gt(n_gt=6, seed=1234, geom: BevGeometry = REF_GEOMETRY):
 
 
 # ----------------------------------------------------------------------------------------
+# Front view (FV).  NOT in the reference: `proposal_transform(target='fv')` returns None (network.py:313-315) and there
+# is no FV raster / trunk / ROI anywhere in its tree.  BASELINE.json's north star asks for the paper's third view, so
+# the functions below ARE the specification (SURVEY 8f "Front view"), written down once here and implemented in
+# csrc/front_view.cu; parity for the FV branch is against this file only.
+# ----------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class FvGeometry:
+    """Cylindrical front-view map: H rows over elevation [phi_min, phi_max] (row 0 = top), W columns over azimuth
+    [theta_min, theta_max) (column 0 = theta_min), angles in degrees; 64 beams x 512 columns over a 90 degree fan."""
+    H: int = 64
+    W: int = 512
+    theta_min: float = -45.0
+    theta_max: float = 45.0
+    phi_min: float = -24.9
+    phi_max: float = 2.0
+
+    @property
+    def dtheta(self) -> float:
+        return np.deg2rad(self.theta_max - self.theta_min) / self.W
+
+    @property
+    def dphi(self) -> float:
+        return np.deg2rad(self.phi_max - self.phi_min) / self.H
+
+
+FV_GEOMETRY = FvGeometry()
+
+
+def fv_coords(x, y, z, g: FvGeometry = FV_GEOMETRY):
+    """float64 (col, row) of LiDAR points in the FV map (unfloored)."""
+    x, y, z = (np.asarray(a, dtype=np.float64) for a in (x, y, z))
+    col = (np.arctan2(y, x) - np.deg2rad(g.theta_min)) / g.dtheta
+    row = (np.deg2rad(g.phi_max) - np.arctan2(z, np.sqrt(x * x + y * y))) / g.dphi
+    return col, row
+
+
+def point_cloud_2_front(points, g: FvGeometry = FV_GEOMETRY):
+    """(N,>=4) float32 [x,y,z,r] -> (H,W,3) float32 [height z, distance sqrt(x^2+y^2+z^2), reflectance]; cell =
+    floor of fv_coords (float64); points with x <= 0 or outside the map are dropped; LAST point in file order wins,
+    as in the BEV rasteriser (tools/read_lidar.py:106-113 semantics)."""
+    p = np.asarray(points, dtype=np.float32)
+    out = np.zeros((g.H, g.W, 3), dtype=np.float32)
+    if p.shape[0] == 0:
+        return out
+    x, y, z = p[:, 0].astype(np.float64), p[:, 1].astype(np.float64), p[:, 2].astype(np.float64)
+    col, row = fv_coords(x, y, z, g)
+    c, r = np.floor(col), np.floor(row)
+    ok = (x > 0) & (c >= 0) & (c < g.W) & (r >= 0) & (r < g.H)
+    ci, ri = c[ok].astype(np.int64), r[ok].astype(np.int64)
+    q = p[ok]
+    dist = np.sqrt(x[ok] * x[ok] + y[ok] * y[ok] + z[ok] * z[ok]).astype(np.float32)
+    out[ri, ci, 0] = q[:, 2]          # numpy fancy assignment: the last duplicate wins
+    out[ri, ci, 1] = dist
+    out[ri, ci, 2] = q[:, 3]
+    return out
+
+
+def lidar_3d_to_fv(rois_3d, g: FvGeometry = FV_GEOMETRY):
+    """(N,6) [x,y,z,l,w,h] float32 -> (N,4) float32 [col_min,row_min,col_max,row_max]: floor of the FV coordinates of
+    the 8 corners (lidar_3d_to_corners), min / max, clamped to the map.  Corners behind the sensor (x <= 0) keep their
+    atan2 value; NaN inputs give a zero box."""
+    c = lidar_3d_to_corners(np.asarray(rois_3d, dtype=np.float32)).astype(np.float64)
+    with np.errstate(all="ignore"):
+        col, row = fv_coords(c[:, 0:8], c[:, 8:16], c[:, 16:24], g)
+        col, row = np.floor(col), np.floor(row)
+        bad = ~(np.isfinite(col).all(axis=1) & np.isfinite(row).all(axis=1))
+        out = np.stack((np.clip(col.min(axis=1), 0, g.W - 1), np.clip(row.min(axis=1), 0, g.H - 1),
+                        np.clip(col.max(axis=1), 0, g.W - 1), np.clip(row.max(axis=1), 0, g.H - 1)), axis=1)
+    out[bad] = 0
+    return out.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8d) -- shared by tests, golden generator and bench
 # ----------------------------------------------------------------------------------------
 # KITTI 000008-like calibration, rows P2, P3, R0_rect (9 values, zero padded), Tr_velo_to_cam

@@ -71,20 +71,25 @@ def rpn_head(conv5_3, params, dtype=torch.float32):
     return prob, bbox
 
 
-def fusion_head(pool_bv, pool_img, params, dtype=torch.float32):
-    """MV3D_test.py:103-123 -> (cls_prob (R,2), bbox_pred (R,48)); pooled inputs (R,7,7,512) NHWC."""
+def fusion_head(pool_bv, pool_img, params, dtype=torch.float32, pool_fv=None):
+    """MV3D_test.py:103-123 -> (cls_prob (R,2), bbox_pred (R,48)); pooled inputs (R,7,7,512) NHWC.  `pool_fv` adds the
+    front-view branch fc6_3/fc7_3 (this project's extension; the reference has two branches)."""
     f1 = fc(fc(pool_bv, params["fc6_1"]["weights"], params["fc6_1"]["biases"], True, dtype),
             params["fc7_1"]["weights"], params["fc7_1"]["biases"], True, dtype)
     f2 = fc(fc(pool_img, params["fc6_2"]["weights"], params["fc6_2"]["biases"], True, dtype),
             params["fc7_2"]["weights"], params["fc7_2"]["biases"], True, dtype)
-    cat = torch.cat([f1, f2], dim=1)
+    feats = [f1, f2]
+    if pool_fv is not None:
+        feats.append(fc(fc(pool_fv, params["fc6_3"]["weights"], params["fc6_3"]["biases"], True, dtype),
+                        params["fc7_3"]["weights"], params["fc7_3"]["biases"], True, dtype))
+    cat = torch.cat(feats, dim=1)
     cls = torch.softmax(fc(cat, params["cls_score"]["weights"], params["cls_score"]["biases"], False, dtype), dim=-1)
     bbox = fc(cat, params["bbox_pred"]["weights"], params["bbox_pred"]["biases"], False, dtype)
     return cls, bbox
 
 
 def mv3d_test_forward(bv, image, im_info, calib, params, cfg=None, geom=orc.REF_GEOMETRY, dtype=torch.float32,
-                      keep=None, teacher=None):
+                      keep=None, teacher=None, fv=None, fv_geom=orc.FV_GEOMETRY):
     """Whole MV3D_test graph on the CPU.  `teacher` (optional dict) overrides stage inputs so that later stages
     can be compared on identical inputs: keys 'conv5_3', 'conv5_3_2', 'rois'."""
     teacher = teacher or {}
@@ -100,9 +105,17 @@ def mv3d_test_forward(bv, image, im_info, calib, params, cfg=None, geom=orc.REF_
                 cfg=cfg, geom=geom)
         p1, _ = orc.roi_pool_fwd(c5.float().numpy(), rois_bv)
         p2, _ = orc.roi_pool_fwd(c5_2.float().numpy(), rois_img)
-        cls, bb = fusion_head(p1, p2, params, dtype)
-    return dict(conv5_3=c5, conv5_3_2=c5_2, rpn_cls_prob_reshape=prob, rpn_bbox_pred=bbox, rois_bv=rois_bv,
-                rois_img=rois_img, rois_3d=rois_3d, pool_5=p1, pool_5_2=p2, cls_prob=cls, bbox_pred=bb)
+        out = {}
+        p3 = None
+        if fv is not None:   # front-view branch (extension): third trunk, FV rois from the 3-D proposals
+            c5_3 = _t(teacher["conv5_3_3"], dtype) if "conv5_3_3" in teacher else trunk(fv, params, "_3", dtype, keep)
+            rois_fv = np.hstack((np.asarray(rois_3d)[:, :1], orc.lidar_3d_to_fv(np.asarray(rois_3d)[:, 1:7], fv_geom)))
+            p3, _ = orc.roi_pool_fwd(c5_3.float().numpy(), rois_fv.astype(np.float32))
+            out.update(conv5_3_3=c5_3, rois_fv=rois_fv.astype(np.float32), pool_5_3=p3)
+        cls, bb = fusion_head(p1, p2, params, dtype, pool_fv=p3)
+    out.update(conv5_3=c5, conv5_3_2=c5_2, rpn_cls_prob_reshape=prob, rpn_bbox_pred=bbox, rois_bv=rois_bv,
+               rois_img=rois_img, rois_3d=rois_3d, pool_5=p1, pool_5_2=p2, cls_prob=cls, bbox_pred=bb)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
