@@ -1,7 +1,7 @@
 // Front-view (FV) branch: cylindrical LiDAR raster and the FV region of interest of a 3-D proposal.
 // The reference has NO front view (lib/networks/network.py:313-315 returns None for target='fv'); the semantics
-// implemented here are this project's own specification, stated in oracle/mv3d_oracle.py (FvGeometry,
-// point_cloud_2_front, lidar_3d_to_fv) after the MV3D paper the reference's README.md:5 links.  All index math is
+// implemented here are this project's own specification (DESIGN.md, section 'Front view'; the CPU checker restates
+// it as point_cloud_2_front / lidar_3d_to_fv) after the MV3D paper the reference's README.md:5 links.  All index math is
 // float64 so that the device and the numpy specification agree bit for bit away from measure-zero cell edges.
 #include "common.cuh"
 

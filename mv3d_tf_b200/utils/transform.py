@@ -66,7 +66,7 @@ def projection_matrix(calib: np.ndarray) -> np.ndarray:
 
 @dataclass(frozen=True)
 class FvGeometry:
-    """Cylindrical front-view map (no reference counterpart; specification in oracle/mv3d_oracle.py FvGeometry):
+    """Cylindrical front-view map (no reference counterpart; specification: DESIGN.md, section 'Front view'):
     H rows over elevation [phi_min, phi_max] degrees (row 0 = top), W columns over azimuth [theta_min, theta_max)."""
 
     H: int = 64
