@@ -68,39 +68,50 @@ def gemm_flops(net, hb, wb, hi, wi, R):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling guide recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling guide recipe): one nvidia-smi
+    process in loop mode (-lms 50), its lines collected by a reader thread."""
 
     def __init__(self, index):
-        self.rows, self.stop_flag, self.index = [], False, index
+        self.rows, self.index, self.proc = [], index, None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in o.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.strip().split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.15)   # let the first sample land before the timed region starts
         return self
 
     def __exit__(self, *a):
-        self.stop_flag = True
-        self.th.join(timeout=6)
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+        except Exception:
+            pass
+        self.th.join(timeout=3)
 
     def summary(self):
         sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[6]))
+            except Exception:
+                pass
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -179,8 +190,8 @@ CONFIG = {"workload": "configs[1]: full MV3D inference batch=1 per GPU: 120k-pt 
                       "rasters, BEV+FV+RGB(375x1242) VGG16 trunks, 3D-RPN + proposal layer (6000/300, NMS 0.7), fused "
                       "3-view ROI pool, fc fusion head (the FV view has no reference counterpart, network.py:313-315: "
                       "it follows this repo's written spec; --views 2 runs the reference's exact two-view network)",
-          "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective", "execution": "one CUDA graph per frame (FrameRunner), "
-          "BEV and RGB trunks on two captured streams",
+          "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective", "execution": "one CUDA graph per frame (FrameRunner: the trunks on separate captured "
+          "streams), independent batch-1 frames replayed round-robin on separate streams (FramePipeline)",
           "l2_policy": "per-frame working set (144 MB/activation at conv1, 411 MB fc6 weights) exceeds the 126 MB L2; "
                        "4 distinct frames rotate"}
 
@@ -262,7 +273,7 @@ def run_train_bench(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="precise", choices=["precise", "fast"])
@@ -273,6 +284,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=2)
     ap.add_argument("--no-train", action="store_true", help="skip the train_step leg of the default run")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--in-flight", type=int, default=2, help="independent batch-1 frames in flight per GPU (streams)")
     ap.add_argument("--views", type=int, default=3, choices=[2, 3],
                     help="3: BEV+FV+RGB (BASELINE configs[1]); 2: the reference's own BEV+RGB network")
     args = ap.parse_args()
@@ -340,24 +352,32 @@ def main():
 
     precise = args.mode == "precise"
 
-    from mv3d_tf_b200.fast_rcnn.test_mv import FrameRunner
+    from mv3d_tf_b200.fast_rcnn.test_mv import FramePipeline, FrameRunner
 
-    # The product call: the whole frame captured once as a CUDA graph (FrameRunner), replayed per frame.
-    runner = FrameRunner(net, raster, N_POINTS, IMG_HW, im_info, fetch=("cls_prob", "bbox_pred", "roi_data_bv"),
-                         use_graph=not args.no_graph)
-    runner.load_device(dev_frames[0][0], dev_frames[0][1], calib)
+    # The product call: each frame is one captured CUDA graph (FrameRunner); `--in-flight` of them are replayed
+    # round-robin on separate streams (FramePipeline) so that one frame's serial tail overlaps the next frame's trunks.
+    def make_runner():
+        r = FrameRunner(net, BevRasterizer(**BEV), N_POINTS, IMG_HW, im_info, fetch=("cls_prob", "bbox_pred", "roi_data_bv"),
+                        use_graph=not args.no_graph)
+        r.load_device(dev_frames[0][0], dev_frames[0][1], calib)
+        return r
     _lib.reset_launch_count()
-    runner.capture()
+    runner = make_runner().capture()
     launches_per_frame = _lib.launch_count() // (3 if not args.no_graph else 2)
+    depth = max(1, args.in_flight)
+    pipe = FramePipeline(make_runner, depth=depth)
 
     def step_device(i):
         pts, img = dev_frames[i % n_frames]
-        runner.load_device(pts, img)      # D2D into the graph's static inputs (4 distinct frames rotate)
-        return runner.replay()
+        if pipe.head - pipe.tail >= depth:
+            pipe.tail += 1                      # device-resident leg: nothing to collect on the host
+        pipe.submit(pts, img, None, device_inputs=True)   # D2D into the graph's static inputs (4 distinct frames rotate)
 
     def step_e2e(i):
         pts_h, img_h = pin_frames[i % n_frames]
-        return runner(pts_h, img_h, calib)   # pinned host in -> H2D, graph, D2H -> pinned host out, one sync
+        if pipe.head - pipe.tail >= depth:
+            pipe.collect()                      # the oldest frame's detections are on the host (pinned) here
+        pipe.submit(pts_h, img_h, calib)        # pinned host in -> H2D, graph, D2H -> pinned host out
 
     def barrier():
         if world > 1:
@@ -371,6 +391,9 @@ def main():
         e0.record(stream)
         for i in range(steps):
             fn(i)
+        while pipe.tail < pipe.head and fn is step_e2e:
+            pipe.collect()                      # the last frames' detections reach the host inside the timed region
+        pipe.drain()                            # device-side join of the per-frame streams
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -413,8 +436,14 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    try:   # per-launch DRAM bytes of the GEMM kernels from the committed ncu capture of this same command
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")))
+        traffic = tj.get("views%d" % args.views, {}).get("mean_dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM; %d launches/frame, %.3f ms/frame summed; "
                           "algorithmic %.1f GFLOP/frame counted 1x, the %s mode issues %dx the MMAs)"
                           % (n_gemm, gemm_ms, flops / 1e9, args.mode, 3 if args.mode == "precise" else 1),
@@ -425,7 +454,7 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)" if args.mode == "precise" else "bf16",
-            "data": "synthetic", "config": dict(CONFIG, mode=args.mode, views=args.views),
+            "data": "synthetic", "config": dict(CONFIG, mode=args.mode, views=args.views, frames_in_flight=depth),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
 

@@ -112,6 +112,55 @@ class FrameRunner:
         return res
 
 
+class FramePipeline:
+    """`depth` FrameRunners (each its own CUDA graph and static buffers, same network weights) replayed round-robin on
+    `depth` streams: while one frame sits in its serial tail (proposal sort, the NMS keep-chain, weight-streaming fc6)
+    the next frame's trunks fill the SMs.  Every frame is still an independent batch-1 inference.
+
+        pipe = FramePipeline(lambda: FrameRunner(net, BevRasterizer(...), ...), depth=2)
+        pipe.submit(points_pinned, image_pinned, calib)      # returns immediately
+        out = pipe.collect()                                  # oldest frame in flight: dict of pinned host tensors
+    """
+
+    def __init__(self, make_runner, depth=2):
+        self.runners = [make_runner().capture() for _ in range(depth)]
+        self.streams = [torch.cuda.Stream() for _ in range(depth)]
+        self.done = [None] * depth
+        self.head = 0      # next slot to submit into
+        self.tail = 0      # oldest slot not yet collected
+        self.depth = depth
+
+    def submit(self, points, image, calib=None, device_inputs=False):
+        k = self.head % self.depth
+        assert self.head - self.tail < self.depth, "collect() the oldest frame first"
+        r, st = self.runners[k], self.streams[k]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            r.load_device(points, image, calib)
+            outs = r.replay()
+            if not device_inputs:
+                for h, o in zip(r.host, outs):
+                    h.copy_(o, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self.done[k] = ev
+        self.head += 1
+
+    def collect(self):
+        assert self.tail < self.head, "nothing in flight"
+        k = self.tail % self.depth
+        self.done[k].synchronize()
+        self.tail += 1
+        r = self.runners[k]
+        return dict(zip(r.fetch_names + ["num_rois"], r.host))
+
+    def drain(self):
+        """Make the current stream wait for everything in flight (device-side join, no host sync)."""
+        for st in self.streams:
+            torch.cuda.current_stream().wait_stream(st)
+        self.tail = self.head
+
+
 def box_detect(sess, net, im, bv, calib, boxes=None):
     """test_mv.py:149-264: one frame -> (scores (R,2), pred_boxes_bv (R,8), pred_boxes_cnr (R,48), pred_boxes_cnr_r
     (R,48)).  `im` is the raw BGR image (PIXEL_MEANS are subtracted here, :163), `bv` the (H,W,C) BEV map.

@@ -45,7 +45,9 @@ class ProposalLayer3D:
         self.capacity = cap if p.post_nms_top_n <= 0 else min(cap, p.post_nms_top_n)
         a3d = bv_anchor_to_lidar(all_anchors(self.Hf, self.Wf, feat_stride), geom).astype(np.float32)
         self.anchors3d = torch.from_numpy(np.ascontiguousarray(a3d)).to(self.device)
-        self._ws = torch.empty(lib().mv3d_proposal_workspace_bytes(C.byref(p)), dtype=torch.uint8, device=self.device)
+        # scratch is taken per call from torch's caching allocator (free inside a captured graph): several frames may
+        # be in flight on different streams through the same layer object
+        self._ws_bytes = int(lib().mv3d_proposal_workspace_bytes(C.byref(p)))
 
     def __call__(self, prob: torch.Tensor, deltas: torch.Tensor, calib, batch_index: float = 0.0):
         """prob (Hf,Wf,2A) / deltas (Hf,Wf,6A) float32 CUDA.  `calib`: the (4,12) host array, or a float32 CUDA tensor
@@ -67,10 +69,11 @@ class ProposalLayer3D:
                    anchor=torch.empty((R,), dtype=torch.int32, device=dev),
                    num=torch.empty((1,), dtype=torch.int32, device=dev))
         self.params.batch_index = float(batch_index)
+        ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
         check(lib().mv3d_proposal_layer_3d(ptr(prob), ptr(deltas), ptr(self.anchors3d), ptr(proj),
                                            C.byref(self.params), ptr(out["bv"]), ptr(out["img"]), ptr(out["p3d"]),
-                                           ptr(out["scores"]), ptr(out["anchor"]), ptr(out["num"]), ptr(self._ws),
-                                           self._ws.numel(), current_stream()), "mv3d_proposal_layer_3d")
+                                           ptr(out["scores"]), ptr(out["anchor"]), ptr(out["num"]), ptr(ws),
+                                           ws.numel(), current_stream()), "mv3d_proposal_layer_3d")
         return out
 
     def decode(self, prob: torch.Tensor, deltas: torch.Tensor, calib: np.ndarray):

@@ -169,3 +169,50 @@ def test_box_detect_matches_oracle_postprocessing(small_net, oracle):
     bvb = oracle.lidar_3d_to_bv(rois3d)                       # same corners -> same BEV box
     assert np.array_equal(boxes_bv[:, :4].astype(np.float32), bvb) or np.abs(boxes_bv[:, :4] - bvb).max() <= 1
     assert np.isfinite(cnr_r).all()
+
+
+def test_frame_pipeline_two_in_flight_equals_sequential(oracle):
+    """FramePipeline: two batch-1 frames in flight on two streams give the same detections as one frame at a time."""
+    from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
+    from mv3d_tf_b200.fast_rcnn.test_mv import FramePipeline, FrameRunner
+    from mv3d_tf_b200.networks.factory import get_network
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+
+    cfg_from_end2end_yml()
+    cfg.USE_GPU_NMS = False
+    net = get_network("MV3D_test", bv_channels=9, precise=True, fv=True)
+    net.init_weights(seed=7, mode="he")
+    rk = dict(res=0.1, zres=0.3, side_range=(-8., 8.), fwd_range=(0., 16.), height_range=(-2, 0.4))
+    im_info = np.array([[161, 161, 1]], np.float32)
+    fetch = ("cls_prob", "bbox_pred", "roi_data_bv", "roi_data_img", "roi_data_fv")
+
+    def make():
+        return FrameRunner(net, BevRasterizer(**rk), 40000, (96, 320), im_info, fetch=fetch)
+    single = make().capture()
+    pipe = FramePipeline(make, depth=2)
+    rng = np.random.default_rng(6)
+    frames = []
+    for k in range(5):
+        pts = oracle.synth_points(30000 + 2000 * k, seed=40 + k)
+        pts[:, 0] *= 0.2
+        pts[:, 1] *= 0.17
+        frames.append((torch.from_numpy(pts).pin_memory(),
+                       torch.from_numpy(rng.normal(0, 40, (1, 96, 320, 3)).astype(np.float32)).pin_memory()))
+    want = []
+    for pts, img in frames:
+        want.append({k2: v.clone() for k2, v in single(pts, img, oracle.KITTI_CALIB).items()})
+    got = []
+    for i, (pts, img) in enumerate(frames):
+        if pipe.head - pipe.tail >= 2:
+            got.append({k2: v.clone() for k2, v in pipe.collect().items()})
+        pipe.submit(pts, img, oracle.KITTI_CALIB)
+    while pipe.tail < pipe.head:
+        got.append({k2: v.clone() for k2, v in pipe.collect().items()})
+    assert len(got) == len(want) == 5
+    for w, g in zip(want, got):
+        assert int(w["num_rois"][0]) == int(g["num_rois"][0]) > 0
+        for name in fetch:
+            if name.startswith("roi_"):
+                assert torch.equal(w[name], g[name]), name
+            else:
+                assert torch.allclose(w[name], g[name], rtol=1e-4, atol=1e-5), name
