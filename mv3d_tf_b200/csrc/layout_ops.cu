@@ -23,6 +23,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int taps, int c
     }
 }
 
+// Same packing as a 32x32 shared-memory transpose: reads run along cout (contiguous in HWIO), writes along the packed K
+// axis (contiguous in the output) -- both coalesced.  Used when cout >= 32 (every layer but the tiny heads).
+__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_pad,
+                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int kdim = taps * cin_pad;
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // j: packed-K row of the tile, threadIdx.x: cout lane
+        const int k = k0 + j, n = n0 + threadIdx.x;
+        float x = 0.f;
+        if (k < kdim && n < cout) {
+            const int t = k / cin_pad, c = k - t * cin_pad;
+            if (c < cin) x = w[((long long)t * cin + c) * cout + n];
+        }
+        tile[j][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // j: cout row of the output, threadIdx.x: packed-K lane
+        const int n = n0 + j, k = k0 + threadIdx.x;
+        if (n < cout && k < kdim) {
+            __nv_bfloat16 h, l;
+            split_bf16(tile[threadIdx.x][j], h, l);
+            hi[(long long)n * kdim + k] = h;
+            if (lo) lo[(long long)n * kdim + k] = l;
+        }
+    }
+}
+
 // (B,H,W,C) fp32 -> PAD (B,H+1,W+1,c_pad) bf16 hi/lo.  One thread per 8 output channels (16-byte stores).
 __global__ void pad_nhwc_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -168,8 +196,14 @@ extern "C" __attribute__((visibility("default"))) int mv3d_pack_weights(const fl
                                  void* stream) {
     MV3D_REQUIRE(d_w && d_hi && taps > 0 && cin > 0 && cout > 0 && cin_pad >= cin);
     const long long total = (long long)cout * taps * cin_pad;
-    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    if (cout >= 32 && (long long)taps * cin_pad <= 65535LL * 32) {
+        dim3 grid(ceil_div(cout, 32), ceil_div(taps * cin_pad, 32));
+        pack_weights_tiled_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    } else {
+        pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    }
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -114,6 +114,39 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ gh, const __n
     }
 }
 
+// Vectorised form for row pitches that are multiples of 8 and <= 2048: a thread owns 8 consecutive channels (16-byte
+// loads) of every (blockDim.x / (ld/8))-th row; partial sums meet in shared memory, one atomicAdd per channel and CTA.
+__global__ void bias_grad_vec_kernel(const __nv_bfloat16* __restrict__ gh, const __nv_bfloat16* __restrict__ gl,
+                                     long long rows, int ld, int n, float* __restrict__ db) {
+    extern __shared__ float sm[];   // [row_lanes][ld]
+    const int cv = ld / 8;
+    const int row_lanes = blockDim.x / cv;
+    const int v = threadIdx.x % cv, rl = threadIdx.x / cv;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rl < row_lanes) {
+        for (long long r = (long long)blockIdx.x * row_lanes + rl; r < rows; r += (long long)gridDim.x * row_lanes) {
+            const uint4 a = *reinterpret_cast<const uint4*>(gh + r * ld + v * 8);
+            const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(pa[e]);
+            if (gl) {
+                const uint4 b = *reinterpret_cast<const uint4*>(gl + r * ld + v * 8);
+                const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(pb[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm[rl * ld + v * 8 + e] = acc[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < row_lanes; ++k) s += sm[k * ld + c];
+        atomicAdd(db + c, s);
+    }
+}
+
 // Backward-data weight: HWIO fp32 (taps, cin, cout) -> bf16 hi/lo (cin, taps*cout_pad) with the taps FLIPPED
 // (tap' = taps-1-tap): dX[p, c] = sum_{t'} sum_n G[p + shift_{t'}, n] * W[taps-1-t', c, n].
 __global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cout_pad,
@@ -376,6 +409,18 @@ MV3D_API int mv3d_maxpool2x2_bwd_pad(const void* d_x_hi, const void* d_x_lo, con
 MV3D_API int mv3d_bias_grad(const void* d_g_hi, const void* d_g_lo, long long rows, int ld, int n, float* d_db,
                             void* stream) {
     MV3D_REQUIRE(d_g_hi && d_db && rows > 0 && n > 0 && ld >= n && ld % 2 == 0);
+    if (ld % 8 == 0 && ld / 8 <= 256 && ((uintptr_t)d_g_hi & 15) == 0 && (!d_g_lo || ((uintptr_t)d_g_lo & 15) == 0)) {
+        const int cv = ld / 8;
+        const int threads = 256 / cv * cv;
+        const int row_lanes = threads / cv;
+        long long blocks = (rows + row_lanes * 16 - 1) / (row_lanes * 16);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        if (blocks < 1) blocks = 1;
+        bias_grad_vec_kernel<<<(int)blocks, threads, sizeof(float) * (size_t)row_lanes * ld, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)d_g_hi, (const __nv_bfloat16*)d_g_lo, rows, ld, n, d_db);
+        MV3D_CHECK_LAUNCH();
+        return MV3D_OK;
+    }
     long long blocks = (rows + 63) / 64;
     if (blocks > 148 * 8) blocks = 148 * 8;
     bias_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_g_hi,
