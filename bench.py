@@ -262,10 +262,16 @@ def run_train_bench(args, rank, world, local_rank):
     kernels.GEMM_EVENTS = []
     step(0)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b in kernels.GEMM_EVENTS)
+    gemm_ms = sum(ev[0].elapsed_time(ev[1]) for ev in kernels.GEMM_EVENTS)
     n_gemm = len(kernels.GEMM_EVENTS)
+    per_kernel = {}
+    for ev in kernels.GEMM_EVENTS:
+        k = per_kernel.setdefault(ev[2], [0, 0.0, 0.0])
+        k[0] += 1; k[1] += ev[0].elapsed_time(ev[1]); k[2] += ev[3]
     kernels.GEMM_EVENTS = None
-    return {"ms": ms, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
+    gemm_by_kernel = {k: {"launches": v[0], "ms": v[1], "tflops_1x": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
+                      for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
+    return {"ms": ms, "gemm_by_kernel": gemm_by_kernel, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
             "n_gpus": world, "gpu_launches_per_step": launches, "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
             "loss": [float(x) for x in loss.tolist()], "optimizer": "Adam lr=1e-5 (TF-1.0 defaults), keep_prob 0.5",
             "grad_allreduce": "NCCL all-reduce of the flat fp32 gradient buffer (%.0f MB)" % (sw.grad.numel() * 4 / 1e6)
@@ -429,9 +435,14 @@ def main():
         runner._forward()             # eager replay of the same program (events cannot be read inside a graph)
     torch.cuda.synchronize()
     net.use_side_stream = True
-    gemm_ms = sum(a.elapsed_time(b) for a, b in kernels.GEMM_EVENTS) / 3.0
-    n_gemm = len(kernels.GEMM_EVENTS) // 3
+    evs = kernels.GEMM_EVENTS
     kernels.GEMM_EVENTS = None
+    gemm_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs) / 3.0
+    n_gemm = len(evs) // 3
+    per_kernel = {}
+    for ev in evs:
+        k = per_kernel.setdefault(ev[2], [0, 0.0, 0.0])
+        k[0] += 1; k[1] += ev[0].elapsed_time(ev[1]); k[2] += ev[3]
     R = 300
     flops = gemm_flops(net, 701, 801, IMG_HW[0], IMG_HW[1], R)
     peaks = {}
@@ -440,19 +451,32 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    achieved_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    all_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # the dominant kernel = the template instantiation with the largest share of the GEMM time
+    dom = max(per_kernel.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_n, dom_ms, dom_flops) = dom[0], dom[1]
+    dom_tf = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     traffic = None
-    try:   # per-launch DRAM bytes of the GEMM kernels from the committed ncu capture of this same command
+    try:   # per-launch DRAM bytes of that kernel from the committed ncu capture of this same command
         tj = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")))
-        traffic = tj.get("views%d" % args.views, {}).get("mean_dram_bytes_per_launch")
+        rows = [r for r in tj["views%d" % args.views]["per_launch"] if dom_name.split("<")[0] in r["kernel"]
+                and ("<%s," % dom_name.split("<")[1].split(",")[0]) in r["kernel"].replace(" ", "")]
+        if rows:
+            traffic = sum(r["dram_MB"] for r in rows) * 1e6 / len(rows)
     except Exception:
         pass
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM; %d launches/frame, %.3f ms/frame summed; "
-                          "algorithmic %.1f GFLOP/frame counted 1x, the %s mode issues %dx the MMAs)"
-                          % (n_gemm, gemm_ms, flops / 1e9, args.mode, 3 if args.mode == "precise" else 1),
+    mult = 3 if args.mode == "precise" else 1
+    roofline = {"bound": "tensor", "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
+                "traffic": traffic,
+                "kernel": "%s: %d launches/frame, %.3f ms/frame, %.1f%% of the GEMM time; algorithmic FLOPs counted 1x "
+                          "(the %s mode issues %dx the MMAs: %.0f TFLOP/s issued)"
+                          % (dom_name, dom_n // 3, dom_ms / 3.0, 100.0 * dom_ms / (gemm_ms * 3.0), args.mode, mult, dom_tf * mult),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "all_gemm_kernels": {"launches_per_frame": n_gemm, "ms_per_frame": gemm_ms, "algorithmic_gflop_per_frame": flops / 1e9,
+                                     "achieved": all_tf, "frac": all_tf / peak_tf,
+                                     "by_kernel": {k: {"launches": v[0] // 3, "ms": v[1] / 3.0,
+                                                       "tflops_1x": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
+                                                   for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}},
                 "gemm_share_of_step": gemm_ms / (ms_dev / args.steps) if ms_dev > 0 else None}
 
     line = {"metric": "MV3D inference frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,

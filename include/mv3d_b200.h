@@ -214,6 +214,10 @@ int mv3d_pack_weights(const float* d_w_hwio, int taps, int cin, int cout, int ci
                       void* stream);
 /* (B,H,W,C) float32 NHWC -> PAD bf16 hi/lo (B,H+1,W+1,c_pad), halos and channel padding zeroed. */
 int mv3d_pad_nhwc(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi, void* d_lo, void* stream);
+/* First-layer im2col for tiny channel counts (C = 3: RGB, front view): dense float32 (B,H,W,C) -> PAD rows
+ * (B,H+1,W+1,k_pad) with K index tap*C + c (tap = kh*3+kw, SAME zero padding; k >= 9*C and halo rows zero), so that
+ * Network.conv(3,3,...) on the input image (network.py:108-132) is ONE taps=1 GEMM with K = k_pad = 32. */
+int mv3d_im2col3x3_pad(const float* d_in, int B, int H, int W, int C, int k_pad, void* d_hi, void* d_lo, void* stream);
 /* PAD -> dense float32 (B,H,W,C) (hi+lo). */
 int mv3d_unpad_nhwc(const void* d_hi, const void* d_lo, int B, int H, int W, int C, int c_pad, float* d_out,
                     void* stream);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mv3d_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "mv3d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_pad_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_im2col3x3_pad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_unpad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mv3d_maxpool2x2_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_softmax_pairs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
@@ -138,7 +139,7 @@ def lib() -> C.CDLL:
 # kernels launched by one successful call of each entry point (memsets not counted) -- bench.py's gpu_launches
 KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
                     "mv3d_roi_pool_forward": 1, "mv3d_roi_pool_backward": 1, "mv3d_roi_pool_multiview": 1,
-                    "mv3d_conv_gemm": 1, "mv3d_conv_wgrad": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_unpad_nhwc": 1,
+                    "mv3d_conv_gemm": 1, "mv3d_conv_wgrad": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_im2col3x3_pad": 1, "mv3d_unpad_nhwc": 1,
                     "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1,
                     "mv3d_maxpool2x2_bwd_pad": 1, "mv3d_bias_grad": 1, "mv3d_pack_weights_dgrad": 1,
                     "mv3d_pad_nhwc_masked": 1, "mv3d_dropout": 1, "mv3d_rpn_loss": 1, "mv3d_rcnn_loss": 1,

@@ -629,6 +629,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(d->split_k <= 1 || (!d->d_mask_hi && !d->d_addend_f32));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool kc64 = (d->Cin % 64 == 0);
-    if (d->passes == 3) return kc64 ? dispatch_bn<64, 3>(d, s) : dispatch_bn<16, 3>(d, s);
-    return kc64 ? dispatch_bn<64, 1>(d, s) : dispatch_bn<16, 1>(d, s);
+    const bool kc32 = !kc64 && (d->Cin % 32 == 0);   // K step 32 -> SWIZZLE_64B boxes (the im2col'd first layers, K = 32)
+    if (d->passes == 3) return kc64 ? dispatch_bn<64, 3>(d, s) : (kc32 ? dispatch_bn<32, 3>(d, s) : dispatch_bn<16, 3>(d, s));
+    return kc64 ? dispatch_bn<64, 1>(d, s) : (kc32 ? dispatch_bn<32, 1>(d, s) : dispatch_bn<16, 1>(d, s));
 }

@@ -77,6 +77,39 @@ __global__ void pad_nhwc_kernel(const float* __restrict__ in, int B, int H, int 
     }
 }
 
+// First-layer im2col for tiny channel counts (RGB / front view, C = 3): dense fp32 (B,H,W,C) -> PAD rows
+// (B,H+1,W+1,k_pad) whose K index is tap*C + c (tap = kh*3 + kw, SAME zero padding), so that conv1_1 becomes ONE K=32
+// GEMM instead of nine K=16 taps that are 13/16 zero padding.  Halo rows and k >= 9*C are zero.
+__global__ void im2col3x3_pad_kernel(const float* __restrict__ in, int B, int H, int W, int C, int k_pad,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int Hp = H + 1, Wp = W + 1, kv = k_pad / 8;
+    const long long total = (long long)B * Hp * Wp * kv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k8 = (int)(i % kv);
+        long long r = i / kv;
+        const int wp = (int)(r % Wp);
+        r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        __nv_bfloat16 vh[8], vl[8];
+        const bool inside = wp > 0 && hp < H;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k8 * 8 + e;
+            float x = 0.f;
+            if (inside && k < 9 * C) {
+                const int tap = k / C, c = k - tap * C;
+                const int hh = hp + tap / 3 - 1, ww = (wp - 1) + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) x = in[(((long long)b * H + hh) * W + ww) * C + c];
+            }
+            split_bf16(x, vh[e], vl[e]);
+        }
+        *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<uint4*>(vh);
+        if (lo) *reinterpret_cast<uint4*>(lo + i * 8) = *reinterpret_cast<uint4*>(vl);
+    }
+}
+
 __global__ void unpad_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int B,
                                   int H, int W, int C, int c_pad, float* __restrict__ out) {
     const int Hp = H + 1, Wp = W + 1;
@@ -214,6 +247,16 @@ extern "C" __attribute__((visibility("default"))) int mv3d_pad_nhwc(const float*
     const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
     pad_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, c_pad,
                                                                              (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_im2col3x3_pad(const float* d_in, int B, int H, int W, int C, int k_pad,
+                                                                          void* d_hi, void* d_lo, void* stream) {
+    MV3D_REQUIRE(d_in && d_hi && B > 0 && H > 0 && W > 0 && C > 0 && k_pad >= 9 * C && k_pad % 8 == 0);
+    const long long total = (long long)B * (H + 1) * (W + 1) * (k_pad / 8);
+    im2col3x3_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, k_pad,
+                                                                                  (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -54,7 +54,7 @@ class FrameRunner:
         feed = {self.net.lidar_bv_data: bv, self.net.image_data: self.img, self.net.im_info: self.im_info,
                 self.net.calib: self.proj}
         if self.fv_raster is not None:
-            feed[self.net.lidar_fv_data] = self.fv_raster.to_pad(self.pts, precise=self.net.precise)
+            feed[self.net.lidar_fv_data] = self.fv_raster(self.pts)[None]   # dense (1,H,W,3): conv1_1_3 takes the im2col path
         outs = self.net.run(self.fetch, feed)
         return list(outs) + [self.net.last_num_rois]
 
@@ -224,3 +224,49 @@ def corners_to_bv(corners, geom):
         out[:, 4 * k + 2] = geom.yn - (ymin - geom.y_min) // geom.res
         out[:, 4 * k + 3] = geom.xn - (xmin - geom.x_min) // geom.res
     return out
+
+
+def collect_detections(scores, boxes_bv, boxes_cnr, num_classes, thresh=0.05, nms_thresh=None, max_per_image=300):
+    """The per-frame tail of test_net (test_mv.py:420-444, 492-501): per foreground class keep scores > thresh, NMS on
+    the BEV boxes with cfg.TEST.NMS (lib/utils/nms.pyx:17-68, the `>=` rule -- run on the GPU by nms.cpu_nms), then cap
+    the frame at `max_per_image` detections over all classes.  Returns ({cls: (n,5) [x1,y1,x2,y2,score]},
+    {cls: (n,25) [24 corner coords, score]})."""
+    from ..nms.gpu_nms import cpu_nms as nms   # utils.cython_nms.nms == cpu_nms.pyx arithmetic
+
+    nms_thresh = cfg.TEST.NMS if nms_thresh is None else nms_thresh
+    dets, dets_cnr = {}, {}
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > thresh)[0]
+        cls_scores = scores[inds, j]
+        cls_dets = np.hstack((boxes_bv[inds, j * 4:(j + 1) * 4], cls_scores[:, np.newaxis])).astype(np.float32, copy=False)
+        cls_dets_cnr = np.hstack((boxes_cnr[inds, j * 24:(j + 1) * 24], cls_scores[:, np.newaxis])).astype(np.float32, copy=False)
+        keep = nms(cls_dets, nms_thresh)
+        dets[j] = cls_dets[keep, :]
+        dets_cnr[j] = cls_dets_cnr[keep, :]
+    if max_per_image > 0 and num_classes > 1:
+        image_scores = np.hstack([dets[j][:, -1] for j in range(1, num_classes)])
+        if len(image_scores) > max_per_image:
+            image_thresh = np.sort(image_scores)[-max_per_image]
+            for j in range(1, num_classes):
+                keep = np.where(dets[j][:, -1] >= image_thresh)[0]
+                dets[j] = dets[j][keep, :]
+                dets_cnr[j] = dets_cnr[j][keep, :]
+    return dets, dets_cnr
+
+
+def test_net(sess, net, imdb, weights_filename=None, max_per_image=300, thresh=0.05, vis=False):
+    """test_mv.py:321-517 without the disk / plotting parts: `imdb` needs `num_classes`, `image_index` and
+    `frame_at(i) -> (image HxWx3 raw BGR, bv HxWxC, calib 4x12)` (the reference reads the three from disk,
+    :398-403).  Returns (all_boxes[cls][image], all_boxes_cnr[cls][image]) as the reference pickles them (:503-509)."""
+    n = len(imdb.image_index)
+    all_boxes = [[[] for _ in range(n)] for _ in range(imdb.num_classes)]
+    all_boxes_cnr = [[[] for _ in range(n)] for _ in range(imdb.num_classes)]
+    for i in range(n):
+        im, bv, calib = imdb.frame_at(i)
+        scores, boxes_bv, boxes_cnr, _ = box_detect(sess, net, im, bv, calib)
+        dets, dets_cnr = collect_detections(scores, boxes_bv, boxes_cnr, imdb.num_classes, thresh=thresh,
+                                            max_per_image=max_per_image)
+        for j in range(1, imdb.num_classes):
+            all_boxes[j][i] = dets[j]
+            all_boxes_cnr[j][i] = dets_cnr[j]
+    return all_boxes, all_boxes_cnr

@@ -64,6 +64,16 @@ def pad_nhwc(x: torch.Tensor, precise: bool = True) -> PadAct:
     return PadAct(hi, lo, B, H, W, Cc)
 
 
+def im2col3x3(x: torch.Tensor, precise: bool = True, k_pad: int = 32) -> PadAct:
+    """(B,H,W,C<=3) float32 -> PAD rows whose 'channels' are the 9*C im2col taps (see mv3d_im2col3x3_pad)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    assert 9 * Cc <= k_pad
+    hi, lo = _new_pad(B, H, W, k_pad, precise, x.device)
+    check(lib().mv3d_im2col3x3_pad(ptr(x), B, H, W, Cc, k_pad, ptr(hi), ptr(lo), current_stream()), "mv3d_im2col3x3_pad")
+    return PadAct(hi, lo, B, H, W, 9 * Cc)
+
+
 def unpad_nhwc(a: PadAct) -> torch.Tensor:
     out = torch.empty((a.B, a.H, a.W, a.C), dtype=torch.float32, device=a.hi.device)
     check(lib().mv3d_unpad_nhwc(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.C, a.c_pad, ptr(out), current_stream()),
@@ -112,7 +122,19 @@ def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Op
 GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch with CUDA events on its stream
 
 
-def _run_gemm(**kw):
+def gemm_kernel_name(taps: int, k_per_tap: int, n: int, passes: int, split_k: int = 1) -> str:
+    """Which template instantiation mv3d_conv_gemm dispatches to (mirrors dispatch_bn / launch_gemm in
+    csrc/conv_gemm_tcgen05.cu) -- used to attribute per-launch timings to kernels in bench.py."""
+    if passes == 1 and n > 128:
+        bn = 256
+    else:
+        bn = 128 if n > 64 else (64 if n > 32 else 32)
+    if taps == 9 and k_per_tap % 64 == 0 and split_k <= 1:
+        return "conv3x3_reuse_kernel<%d,%d>" % (bn, passes)
+    return "conv_gemm_kernel<%d,%d,%d>" % (bn, 64 if k_per_tap % 64 == 0 else (32 if k_per_tap % 32 == 0 else 16), passes)
+
+
+def _run_gemm(_flops=0.0, **kw):
     d = GemmDesc()
     for k, v in kw.items():
         setattr(d, k, v)
@@ -122,7 +144,7 @@ def _run_gemm(**kw):
     check(lib().mv3d_conv_gemm(C.byref(d), current_stream()), "mv3d_conv_gemm")
     if GEMM_EVENTS is not None:
         e1.record(torch.cuda.current_stream())
-        GEMM_EVENTS.append((e0, e1))
+        GEMM_EVENTS.append((e0, e1, gemm_kernel_name(d.taps, d.Cin, d.N, d.passes, d.split_k), float(_flops)))
 
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
@@ -143,7 +165,8 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
                 lo.zero_()
         out = PadAct(hi, lo, a.B, a.H, a.W, w.cout)
     dense = torch.empty((a.B, a.H, a.W, w.cout), dtype=torch.float32, device=dev) if out_f32_dense else None
-    _run_gemm(M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=3 if precise else 1,
+    _run_gemm(_flops=2.0 * a.B * a.H * a.W * w.taps * min(a.C, w.cin) * w.cout,
+              M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=3 if precise else 1,
               d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo),
               d_bias=ptr(w.bias) if use_bias else None,
               relu=int(relu), d_out_hi=ptr(out.hi) if out else None, d_out_lo=ptr(out.lo) if out else None,
@@ -168,7 +191,8 @@ def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, re
         lo = torch.zeros_like(hi) if precise else None
     if split_k > 1 and mask_hi is None:
         acc = torch.zeros((M, w.cout), dtype=torch.float32, device=dev)
-        _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
+        _run_gemm(_flops=2.0 * M * w.cin * w.cout,
+                  M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
                   d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=None, relu=0, d_out_hi=None,
                   d_out_lo=None, ld_out=0, d_out_f32=ptr(acc), ld_f32=w.cout, f32_dense=0, split_k=split_k)
         if out_f32:
@@ -178,7 +202,8 @@ def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, re
         return hi, lo, f32
     if out_f32:
         f32 = torch.empty((M, w.cout), dtype=torch.float32, device=dev)
-    _run_gemm(M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
+    _run_gemm(_flops=2.0 * M * w.cin * w.cout,
+              M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
               d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=ptr(w.bias) if use_bias else None,
               relu=int(relu), d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad, d_out_f32=ptr(f32), ld_f32=w.cout,
               f32_dense=0, split_k=1, d_mask_hi=ptr(mask_hi), ld_mask=mask_hi.stride(0) if mask_hi is not None else 0,
@@ -228,7 +253,8 @@ def _run_wgrad(**kw):
     check(lib().mv3d_conv_wgrad(C.byref(d), current_stream()), "mv3d_conv_wgrad")
     if GEMM_EVENTS is not None:
         e1.record(torch.cuda.current_stream())
-        GEMM_EVENTS.append((e0, e1))
+        GEMM_EVENTS.append((e0, e1, "wgrad_kernel<%d,%d>" % (128 if d.Cx % 128 == 0 else (64 if d.Cx % 64 == 0 else 16), d.passes),
+                            2.0 * d.P * d.taps * d.cin * d.cout))
 
 
 def conv_wgrad(x: PadAct, g: PadAct, dw: torch.Tensor, precise: bool = True, accumulate: bool = True,

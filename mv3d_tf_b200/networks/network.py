@@ -201,11 +201,23 @@ class Network(object):
 
         def run(vals, node):
             v = vals[node.inputs[0]]
-            if v.pad is None:
-                v.pad = K.pad_nhwc(v.dense, precise=self.precise)
             want_pad = any(c in ('conv', 'max_pool') for c in node.consumers) or self.training
             want_dense = (not want_pad) or any(c not in ('conv', 'max_pool') for c in node.consumers) \
                 or node.attrs.get('fetched', False)
+            if (k_h, k_w) == (3, 3) and 9 * c_i <= 32 and v.dense is not None and v.pad is None and not self.training:
+                # tiny-channel first layer (RGB / front view): im2col once, then ONE K=32 GEMM instead of nine taps of
+                # 13/16 zero padding.  (Training keeps the nine-tap form: its backward-filter expects the PAD input.)
+                col = v.extra if isinstance(v.extra, K.PadAct) else K.im2col3x3(v.dense, precise=self.precise)
+                v.extra = col
+                pw = self._packed.get(name + '/im2col')
+                if pw is None:
+                    p = self.params[name]
+                    pw = self._packed[name + '/im2col'] = K.pack_weights(p['weights'].reshape(1, 1, 9 * c_i, c_o),
+                                                                         p['biases'], cin_pad=32)
+                out, dense = K.conv(col, pw, relu=relu, precise=self.precise, out_pad=want_pad, out_f32_dense=want_dense)
+                return Val(pad=out, dense=dense)
+            if v.pad is None:
+                v.pad = K.pad_nhwc(v.dense, precise=self.precise)
             out, dense = K.conv(v.pad, self._weight(name), relu=relu, precise=self.precise, out_pad=want_pad,
                                 out_f32_dense=want_dense)
             return Val(pad=out, dense=dense)

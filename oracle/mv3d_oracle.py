@@ -545,6 +545,57 @@ def synth_gt(n_gt=6, seed=1234, geom: BevGeometry = REF_GEOMETRY):
 
 
 # ----------------------------------------------------------------------------------------
+# f1. test_net post-processing (lib/fast_rcnn/test_mv.py:241-264, 420-444, 492-501)
+# ----------------------------------------------------------------------------------------
+def corners_to_bv(corners, geom: BevGeometry = REF_GEOMETRY):
+    """transform.py:342-366 (per class block of 24)."""
+    n_cls = corners.shape[1] // 24
+    bv = np.zeros((corners.shape[0], 4 * n_cls))
+    for i in range(n_cls):
+        c = corners[:, i * 24:(i + 1) * 24]
+        xmin, xmax = np.min(c[:, :8], axis=1).reshape(-1, 1), np.max(c[:, :8], axis=1).reshape(-1, 1)
+        ymin, ymax = np.min(c[:, 8:16], axis=1).reshape(-1, 1), np.max(c[:, 8:16], axis=1).reshape(-1, 1)
+        p = np.hstack([xmax, ymax, xmin, ymin])
+        p[:, 0], p[:, 1] = lidar_to_bv_coord(p[:, 0], p[:, 1], geom)
+        p[:, 2], p[:, 3] = lidar_to_bv_coord(p[:, 2], p[:, 3], geom)
+        bv[:, i * 4:(i + 1) * 4] = p
+    return bv
+
+
+def bbox_transform_inv_cnr(boxes, deltas):
+    """bbox_transform.py:157-176."""
+    if boxes.shape[0] == 0:
+        return np.zeros((0, deltas.shape[1]), dtype=deltas.dtype)
+    boxes = boxes.astype(deltas.dtype, copy=False)
+    diag = np.linalg.norm(boxes[:, 0::8] - boxes[:, 6::8], axis=1)
+    deltas = np.multiply(deltas, diag.reshape((-1, 1)))
+    pred = np.zeros(deltas.shape, dtype=deltas.dtype)
+    for i in range(deltas.shape[1] // 24):
+        pred[:, i * 24:i * 24 + 24] = deltas[:, i * 24:i * 24 + 24] + boxes
+    return pred
+
+
+def collect_detections(scores, boxes_bv, boxes_cnr, num_classes, thresh=0.05, nms_thresh=0.1, max_per_image=300):
+    """test_mv.py:420-444 + 492-501 for one frame."""
+    dets, dets_cnr = {}, {}
+    for j in range(1, num_classes):
+        inds = np.where(scores[:, j] > thresh)[0]
+        cs = scores[inds, j]
+        d = np.hstack((boxes_bv[inds, j * 4:(j + 1) * 4], cs[:, np.newaxis])).astype(np.float32, copy=False)
+        dc = np.hstack((boxes_cnr[inds, j * 24:(j + 1) * 24], cs[:, np.newaxis])).astype(np.float32, copy=False)
+        keep = nms(d, nms_thresh)
+        dets[j], dets_cnr[j] = d[keep, :], dc[keep, :]
+    if max_per_image > 0 and num_classes > 1:
+        sc = np.hstack([dets[j][:, -1] for j in range(1, num_classes)])
+        if len(sc) > max_per_image:
+            t = np.sort(sc)[-max_per_image]
+            for j in range(1, num_classes):
+                k = np.where(dets[j][:, -1] >= t)[0]
+                dets[j], dets_cnr[j] = dets[j][k, :], dets_cnr[j][k, :]
+    return dets, dets_cnr
+
+
+# ----------------------------------------------------------------------------------------
 # Front view (FV).  NOT in the reference: `proposal_transform(target='fv')` returns None (network.py:313-315) and there
 # is no FV raster / trunk / ROI anywhere in its tree.  BASELINE.json's north star asks for the paper's third view, so
 # the functions below ARE the specification (SURVEY 8f "Front view"), written down once here and implemented in

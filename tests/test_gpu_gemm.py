@@ -93,3 +93,28 @@ def test_softmax_pairs():
     y = k.softmax_pairs(x, 4)
     ref = torch.softmax(x.view(-1, 4, 2).double(), dim=-1).view(x.shape)
     assert _relerr(y, ref) < 1e-6
+
+
+@pytest.mark.parametrize("B,H,W,Cout,passes", [(1, 9, 11, 64, 3), (2, 37, 50, 64, 3), (1, 64, 96, 64, 1)])
+def test_first_layer_im2col_conv(B, H, W, Cout, passes):
+    """conv1_1 on a 3-channel input through the im2col + single K=32 GEMM path == the nine-tap path == torch."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    x = torch.randn(B, H, W, 3, device="cuda", generator=g) * 50
+    w = torch.randn(3, 3, 3, Cout, device="cuda", generator=g) * 0.2
+    b = torch.randn(Cout, device="cuda", generator=g)
+    precise = passes == 3
+    col = k.im2col3x3(x, precise=precise)
+    pw = k.pack_weights(w.reshape(1, 1, 27, Cout), b, cin_pad=32)
+    out, dense = k.conv(col, pw, relu=True, precise=precise, out_pad=True, out_f32_dense=True)
+    out9, dense9 = k.conv(k.pad_nhwc(x, precise=precise), k.pack_weights(w, b), relu=True, precise=precise,
+                          out_pad=True, out_f32_dense=True)
+    torch.cuda.synchronize()
+    xr, wr = (x.double(), w.double()) if precise else (x.bfloat16().double(), w.bfloat16().double())
+    ref = torch.relu(torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), b.double(), padding=1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert _relerr(dense, ref) < (3e-5 if precise else 1e-5)
+    assert _relerr(dense, dense9) < 3e-5
+    assert _relerr(k.unpad_nhwc(out), ref) < (3e-5 if precise else 1e-2)
+    assert float(out.hi[:, :, 0, :].abs().max()) == 0 and float(out.hi[:, H, :, :].abs().max()) == 0

@@ -166,9 +166,17 @@ def test_box_detect_matches_oracle_postprocessing(small_net, oracle):
                                                   net.calib: oracle.KITTI_CALIB})[0]["p3d"][:n, 1:7].cpu().numpy()
     c = oracle.lidar_3d_to_corners(rois3d)
     assert np.array_equal(cnr, np.hstack((c, c)))            # test_mv.py:253-255: un-regressed, duplicated per class
-    bvb = oracle.lidar_3d_to_bv(rois3d)                       # same corners -> same BEV box
-    assert np.array_equal(boxes_bv[:, :4].astype(np.float32), bvb) or np.abs(boxes_bv[:, :4] - bvb).max() <= 1
-    assert np.isfinite(cnr_r).all()
+    assert np.array_equal(boxes_bv, oracle.corners_to_bv(cnr))                    # transform.py:342-366
+    deltas = net.run([net.get_output("bbox_pred")], {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info,
+                                                       net.calib: oracle.KITTI_CALIB})[0][:n].cpu().numpy()
+    assert np.allclose(cnr_r, oracle.bbox_transform_inv_cnr(c, deltas), rtol=1e-5, atol=1e-5)
+    # the tail of test_net: per-class threshold + NMS (utils/nms.pyx rule) + per-image cap, vs the oracle
+    from mv3d_tf_b200.fast_rcnn.test_mv import collect_detections
+    for thr, cap in ((0.05, 300), (0.3, 20), (0.0, 5)):
+        got, got_c = collect_detections(scores, boxes_bv, cnr, 2, thresh=thr, nms_thresh=0.1, max_per_image=cap)
+        want, want_c = oracle.collect_detections(scores, boxes_bv, cnr, 2, thresh=thr, nms_thresh=0.1, max_per_image=cap)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got_c[1], want_c[1])
+        assert got[1].shape[0] <= cap or cap <= 0
 
 
 def test_frame_pipeline_two_in_flight_equals_sequential(oracle):

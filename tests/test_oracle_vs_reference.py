@@ -76,3 +76,16 @@ def test_target_layers_full_shape(oracle, ref, seed):
     got = oracle.proposal_target_layer_3d(rois_bv, rois_3d, gt_bv, gt_3d, gt_cnr, oracle.KITTI_CALIB, 2)
     for w, g in zip(want, got):
         assert w.dtype == g.dtype and np.array_equal(w, g)
+
+
+def test_box_detect_postprocessing_helpers(oracle, ref):
+    """corners_to_bv / bbox_transform_inv_cnr restatements (the tail of box_detect, test_mv.py:241-264) vs the reference."""
+    rng = np.random.default_rng(2)
+    p3d = np.column_stack((rng.uniform(2, 58, 200), rng.uniform(-28, 28, 200), rng.uniform(-2, 0, 200),
+                           rng.uniform(1, 5, 200), rng.uniform(1, 3, 200), rng.uniform(1, 2, 200))).astype(np.float32)
+    cnr = ref.transform.lidar_3d_to_corners(p3d)
+    assert np.array_equal(cnr, oracle.lidar_3d_to_corners(p3d))
+    both = np.hstack((cnr, cnr))
+    assert np.array_equal(ref.transform.corners_to_bv(both), oracle.corners_to_bv(both))
+    deltas = rng.normal(0, 0.1, (200, 48)).astype(np.float32)
+    assert np.array_equal(ref.bbox_transform.bbox_transform_inv_cnr(cnr, deltas), oracle.bbox_transform_inv_cnr(cnr, deltas))
