@@ -286,7 +286,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="precise", choices=["precise", "fast"])
+    ap.add_argument("--mode", default="precise", choices=["precise", "mixed", "fast"],
+                    help="precise: bf16 hi/lo 3-pass everywhere; mixed: fp16 + e5m2-pair operands (2 pass-equivalents) "
+                         "in the 3x3 convs, 3-pass elsewhere; fast: single bf16 pass (not a parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer: configs[1] frames/s (the headline); train: configs[2] train-step ms only")
@@ -349,8 +351,8 @@ def main():
 
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False  # reproduce the DEVICE=cpu rule (cpu_nms `>=`), the parity target
-    net = get_network("MV3D_test", bv_channels=36, precise=(args.mode == "precise"), geometry=CFG_GEOMETRY,
-                      fv=(args.views == 3))
+    net = get_network("MV3D_test", bv_channels=36, precise=(args.mode != "fast"), mixed=(args.mode == "mixed"),
+                      geometry=CFG_GEOMETRY, fv=(args.views == 3))
     net.init_weights(seed=7, mode="he")
     raster = BevRasterizer(**BEV)
     im_info = np.array([[701, 801, 1]], np.float32)
@@ -361,7 +363,7 @@ def main():
     dev_frames = [(torch.from_numpy(p).cuda(), torch.from_numpy(i).cuda()) for p, i in frames]
     pin_frames = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(i).pin_memory()) for p, i in frames]
 
-    precise = args.mode == "precise"
+    precise = args.mode != "fast"
 
     from mv3d_tf_b200.fast_rcnn.test_mv import FramePipeline, FrameRunner
 
@@ -465,7 +467,8 @@ def main():
             traffic = sum(r["dram_MB"] for r in rows) * 1e6 / len(rows)
     except Exception:
         pass
-    mult = 3 if args.mode == "precise" else 1
+    mult = {"precise": 3, "mixed": 2, "fast": 1}[args.mode] if "<" not in dom_name else \
+        {"3": 3, "2": 2, "1": 1}.get(dom_name.rstrip(">").split(",")[-1], 1)
     roofline = {"bound": "tensor", "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
                 "traffic": traffic,
                 "kernel": "%s: %d launches/frame, %.3f ms/frame, %.1f%% of the GEMM time; algorithmic FLOPs counted 1x "
@@ -482,7 +485,10 @@ def main():
     line = {"metric": "MV3D inference frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)" if args.mode == "precise" else "bf16",
+            "dtype": {"precise": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)",
+                      "mixed": "f16+2xe5m2 in the 3x3 convs (fp16 pass + one e5m2 pass carrying both correction terms = 2 "
+                               "pass-equivalents, fp32 accumulate), bf16x3 in 1x1/fc layers",
+                      "fast": "bf16"}[args.mode],
             "data": "synthetic", "config": dict(CONFIG, mode=args.mode, views=args.views, frames_in_flight=depth),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}

@@ -158,6 +158,9 @@ int mv3d_roi_pool_multiview(const mv3d_roi_view* views, int n_views, int num_roi
  *   hi*hi + lo*hi + hi*lo in fp32 (|err| ~ 2^-16, the parity mode); passes=1 uses hi only.
  *   D[m, n] = sum_{t<taps, c<Cin} A[m + shift_t, c] * W[n, t*Cin + c]  (+ bias[n], ReLU)
  * ------------------------------------------------------------------------------------------- */
+#define MV3D_FMT_BF16X2 0 /* x = hi + lo, two bf16 planes */
+#define MV3D_FMT_F16E5 1  /* x ~= h + l/4096: fp16 plane h; byte plane, per 64-channel chunk: 64 x e5m2(h), 64 x e5m2(l)
+                             (weights: fp16 plane = fp16(4096 w); byte plane = 64 x e5m2(residual), 64 x e5m2(w)) */
 typedef struct {
     int M;    /* rows of A and D: B*Hp*Wp pixels of the PAD layout, or plain rows for fc (taps=1) */
     int N;    /* output channels */
@@ -179,8 +182,27 @@ typedef struct {
      * indexing) or plain rows when Hp == 0 -- a second gradient path summed in before masking.  NULL = unused. */
     const void* d_mask_hi; int ld_mask; float mask_scale;
     const float* d_addend_f32; int ld_addend;
+    /* operand rendering of d_out_hi / d_out_lo: MV3D_FMT_BF16X2 (bf16 hi/lo planes, the default 0) or MV3D_FMT_F16E5
+     * (fp16 plane + e5m2 byte plane, below).  passes=2 declares that A and W are MV3D_FMT_F16E5 operands
+     * (3x3 convs with Cin % 64 == 0 only): one fp16 pass + one e5m2 pass at twice the rate carrying both first-order
+     * correction terms -- 2/3 of the tensor-pipe time of passes=3, error ~2^-14.5 per product (3-pass: 2^-17). */
+    int out_fmt;
 } mv3d_gemm_desc;
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
+/* A/B switch for the CTA-pair (tcgen05 cta_group::2, 256 x N tiles) form of the tap-reuse 3x3 conv kernel: on (default,
+ * also MV3D_PAIR=1) or off (single-CTA 128 x N tiles).  Same results either way; returns the previous setting. */
+int mv3d_gemm_set_pair_mode(int on);
+
+/* MV3D_FMT_F16E5 renderings of the layout helpers (fmt = MV3D_FMT_BF16X2 forwards to the plain functions; same
+ * arguments otherwise).  d_hi is the 16-bit plane, d_lo the byte plane of equal pitch; c_pad / cin_pad % 64 == 0. */
+int mv3d_pack_weights_fmt(const float* d_w, int taps, int cin, int cout, int cin_pad, void* d_hi, void* d_lo, int fmt,
+                          void* stream);
+int mv3d_pad_nhwc_fmt(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi, void* d_lo, int fmt,
+                      void* stream);
+int mv3d_unpad_nhwc_fmt(const void* d_hi, const void* d_lo, int B, int H, int W, int C, int c_pad, float* d_out, int fmt,
+                        void* stream);
+int mv3d_maxpool2x2_pad_fmt(const void* d_in_hi, const void* d_in_lo, int B, int H, int W, int c_pad, void* d_out_hi,
+                            void* d_out_lo, int fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward-filter GEMM (training):  dW[t, c, n] (+)= sum_p X[p + shift_t, c] * G[p, n].

@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
                 ("d_out_hi", c_void_p), ("d_out_lo", c_void_p), ("ld_out", c_int),
                 ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int),
                 ("d_mask_hi", c_void_p), ("ld_mask", c_int), ("mask_scale", c_float),
-                ("d_addend_f32", c_void_p), ("ld_addend", c_int)]
+                ("d_addend_f32", c_void_p), ("ld_addend", c_int), ("out_fmt", c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -77,6 +77,12 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     "mv3d_roi_pool_multiview": (c_int, [C.POINTER(RoiView), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mv3d_conv_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "mv3d_gemm_set_pair_mode": (c_int, [c_int]),
+    "mv3d_pack_weights_fmt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "mv3d_pad_nhwc_fmt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "mv3d_unpad_nhwc_fmt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mv3d_maxpool2x2_pad_fmt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                        c_void_p]),
     "mv3d_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "mv3d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_pad_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -140,7 +146,8 @@ def lib() -> C.CDLL:
 KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
                     "mv3d_roi_pool_forward": 1, "mv3d_roi_pool_backward": 1, "mv3d_roi_pool_multiview": 1,
                     "mv3d_conv_gemm": 1, "mv3d_conv_wgrad": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_im2col3x3_pad": 1, "mv3d_unpad_nhwc": 1,
-                    "mv3d_maxpool2x2_pad": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1,
+                    "mv3d_maxpool2x2_pad": 1, "mv3d_pack_weights_fmt": 1, "mv3d_pad_nhwc_fmt": 1, "mv3d_unpad_nhwc_fmt": 1,
+                    "mv3d_maxpool2x2_pad_fmt": 1, "mv3d_softmax_pairs": 1, "mv3d_bias_act": 1,
                     "mv3d_maxpool2x2_bwd_pad": 1, "mv3d_bias_grad": 1, "mv3d_pack_weights_dgrad": 1,
                     "mv3d_pad_nhwc_masked": 1, "mv3d_dropout": 1, "mv3d_rpn_loss": 1, "mv3d_rcnn_loss": 1,
                     "mv3d_adam": 1, "mv3d_fv_raster": 2, "mv3d_rois_to_fv": 1, "mv3d_anchor_targets": 2, "mv3d_roi_overlaps": 1, "mv3d_proposal_targets": 1}

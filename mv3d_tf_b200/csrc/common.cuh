@@ -1,6 +1,8 @@
 // Shared helpers for the mv3d_b200 kernels (status codes, launch checks, bf16 hi/lo split).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +30,45 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// "f16e5" operand format (MV3D_FMT_F16E5): x ~= h + l / 4096 with h = fp16(x); next to the fp16 plane a byte plane
+// holds, per 64-channel chunk, 64 x e5m2(h) followed by 64 x e5m2((x - h) * 4096)  (weights: residual first, then
+// e5m2(w); their fp16 plane is fp16(4096 w)).  One 128-byte row of the byte plane is then the K-concatenation
+// [A_h8 | A_l8] . [W_l8 ; W_h8] = 4096 (A_h W_l + A_l W_h): the two first-order correction terms of the split
+// product as ONE fp8 MMA pass at twice the fp16 rate, accumulated on top of 4096 A_h W_h.  The GEMM epilogue
+// multiplies by 2^-12.  Relative error per product ~2^-14.5 (bf16 hi/lo 3-pass: 2^-17; plain fp16: 2^-12).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr float kF16E5Scale = 4096.f;
+
+__device__ __forceinline__ uint8_t to_e5m2(float x) {
+    return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __forceinline__ float from_e5m2(uint8_t v) {  // e5m2 is the top byte of an fp16
+    return __half2float(__ushort_as_half((unsigned short)(v << 8)));
+}
+// byte offset of channel c's e5m2(h) inside a byte-plane row; the residual sits 64 bytes further (activations)
+__device__ __forceinline__ int f16e5_off(int c) { return ((c >> 6) << 7) + (c & 63); }
+
+__device__ __forceinline__ void split_f16e5(float x, unsigned short& h, uint8_t& h8, uint8_t& l8) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    const __half hh = __float2half_rn(x);
+    const float hf = __half2float(hh);
+    h = __half_as_ushort(hh);
+    h8 = to_e5m2(hf);
+    l8 = to_e5m2((x - hf) * kF16E5Scale);
+}
+__device__ __forceinline__ float join_f16e5(unsigned short h, uint8_t l8) {
+    return __half2float(__ushort_as_half(h)) + from_e5m2(l8) * (1.f / kF16E5Scale);
+}
+// weights: fp16 plane = fp16(4096 w), byte plane = [e5m2(4096 w - fp16 plane) | e5m2(w)]
+__device__ __forceinline__ void split_f16e5_weight(float w, unsigned short& h, uint8_t& l8, uint8_t& h8) {
+    const float ws = fminf(fmaxf(w * kF16E5Scale, -65504.f), 65504.f);
+    const __half hh = __float2half_rn(ws);
+    h = __half_as_ushort(hh);
+    l8 = to_e5m2(ws - __half2float(hh));
+    h8 = to_e5m2(w);
 }
 
 }  // namespace mv3d

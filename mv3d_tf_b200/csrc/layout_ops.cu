@@ -215,6 +215,139 @@ __global__ void bias_act_kernel(const float* __restrict__ acc, int M, int N, int
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// MV3D_FMT_F16E5 renderings of the same layout kernels (format: common.cuh).  `hi` is the fp16 plane, `lo` the byte
+// plane; both have the pitch of the bf16 planes (c_pad 16-bit units per row), c_pad % 64 == 0.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_f16e5_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_pad,
+                                          unsigned short* __restrict__ hi, uint8_t* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int kdim = taps * cin_pad;
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int k = k0 + j, n = n0 + threadIdx.x;
+        float x = 0.f;
+        if (k < kdim && n < cout) {
+            const int t = k / cin_pad, c = k - t * cin_pad;
+            if (c < cin) x = w[((long long)t * cin + c) * cout + n];
+        }
+        tile[j][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int n = n0 + j, k = k0 + threadIdx.x;
+        if (n < cout && k < kdim) {
+            unsigned short h;
+            uint8_t l8, h8;
+            split_f16e5_weight(tile[threadIdx.x][j], h, l8, h8);
+            hi[(long long)n * kdim + k] = h;
+            uint8_t* row = lo + (long long)n * kdim * 2;
+            row[f16e5_off(k)] = l8;        // residual first ...
+            row[f16e5_off(k) + 64] = h8;   // ... then e5m2(w): pairs with the activation row [e5m2(h) | residual]
+        }
+    }
+}
+
+__global__ void pad_nhwc_f16e5_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
+                                      unsigned short* __restrict__ hi, uint8_t* __restrict__ lo) {
+    const int Hp = H + 1, Wp = W + 1, cv = c_pad / 8;
+    const long long total = (long long)B * Hp * Wp * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
+        const long long row = r;
+        const int wp = (int)(r % Wp);
+        r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        const bool inside = wp > 0 && hp < H;
+        const float* src = in + (((long long)b * H + hp) * W + (wp - 1)) * C;
+        unsigned short vh[8];
+        uint8_t a8[8], b8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            split_f16e5((inside && c < C) ? src[c] : 0.f, vh[e], a8[e], b8[e]);
+        }
+        *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<uint4*>(vh);
+        uint8_t* ob = lo + row * c_pad * 2 + f16e5_off(c8 * 8);
+        *reinterpret_cast<uint2*>(ob) = *reinterpret_cast<uint2*>(a8);
+        *reinterpret_cast<uint2*>(ob + 64) = *reinterpret_cast<uint2*>(b8);
+    }
+}
+
+__global__ void unpad_nhwc_f16e5_kernel(const unsigned short* __restrict__ hi, const uint8_t* __restrict__ lo, int B,
+                                        int H, int W, int C, int c_pad, float* __restrict__ out) {
+    const int Hp = H + 1, Wp = W + 1;
+    const long long total = (long long)B * H * W * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int w = (int)(r % W);
+        r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        const long long row = ((long long)b * Hp + h) * Wp + (w + 1);
+        out[i] = join_f16e5(hi[row * c_pad + c], lo[row * c_pad * 2 + f16e5_off(c) + 64]);
+    }
+}
+
+// 2x2/2 VALID max-pool: the winner by decoded value, its (fp16, e5m2, e5m2) triple copied unchanged.
+__global__ void maxpool2x2_pad_f16e5_kernel(const unsigned short* __restrict__ ih, const uint8_t* __restrict__ il,
+                                            int B, int H, int W, int c_pad, unsigned short* __restrict__ oh,
+                                            uint8_t* __restrict__ ol) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int Hp = H + 1, Wp = W + 1, Hop = Ho + 1, Wop = Wo + 1;
+    const int cv = c_pad / 8;
+    const long long total = (long long)B * Hop * Wop * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
+        const long long orow = r;
+        const int wop = (int)(r % Wop);
+        r /= Wop;
+        const int hop = (int)(r % Hop);
+        const int b = (int)(r / Hop);
+        const int boff = f16e5_off(c8 * 8);
+        uint4 rh = make_uint4(0, 0, 0, 0);
+        uint2 ra = make_uint2(0, 0), rb = make_uint2(0, 0);
+        if (wop > 0 && hop < Ho) {
+            const int h0 = hop * 2, w0 = (wop - 1) * 2;
+            float best[8];
+            unsigned short bh[8];
+            uint8_t ba[8], bb[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { best[e] = -3.4e38f; bh[e] = 0; ba[e] = 0; bb[e] = 0; }
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const long long row = ((long long)b * Hp + h0 + dy) * Wp + (w0 + dx + 1);
+                    const uint4 vh = *reinterpret_cast<const uint4*>(ih + row * c_pad + c8 * 8);
+                    const uint2 va = *reinterpret_cast<const uint2*>(il + row * c_pad * 2 + boff);
+                    const uint2 vb = *reinterpret_cast<const uint2*>(il + row * c_pad * 2 + boff + 64);
+                    const unsigned short* ph = reinterpret_cast<const unsigned short*>(&vh);
+                    const uint8_t* pa = reinterpret_cast<const uint8_t*>(&va);
+                    const uint8_t* pb = reinterpret_cast<const uint8_t*>(&vb);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = join_f16e5(ph[e], pb[e]);
+                        if (x > best[e]) { best[e] = x; bh[e] = ph[e]; ba[e] = pa[e]; bb[e] = pb[e]; }
+                    }
+                }
+            rh = *reinterpret_cast<uint4*>(bh);
+            ra = *reinterpret_cast<uint2*>(ba);
+            rb = *reinterpret_cast<uint2*>(bb);
+        }
+        *reinterpret_cast<uint4*>(oh + orow * c_pad + c8 * 8) = rh;
+        *reinterpret_cast<uint2*>(ol + orow * c_pad * 2 + boff) = ra;
+        *reinterpret_cast<uint2*>(ol + orow * c_pad * 2 + boff + 64) = rb;
+    }
+}
+
 static inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 16;
@@ -278,6 +411,53 @@ extern "C" __attribute__((visibility("default"))) int mv3d_maxpool2x2_pad(const 
     maxpool2x2_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)d_in_hi, (const __nv_bfloat16*)d_in_lo, B, H, W, c_pad, (__nv_bfloat16*)d_out_hi,
         (__nv_bfloat16*)d_out_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+// ---- MV3D_FMT_F16E5 variants (fmt = MV3D_FMT_BF16X2 forwards to the functions above) ----
+extern "C" __attribute__((visibility("default"))) int mv3d_pack_weights_fmt(const float* d_w, int taps, int cin, int cout, int cin_pad, void* d_hi,
+                                                                           void* d_lo, int fmt, void* stream) {
+    if (fmt == MV3D_FMT_BF16X2) return mv3d_pack_weights(d_w, taps, cin, cout, cin_pad, d_hi, d_lo, stream);
+    MV3D_REQUIRE(fmt == MV3D_FMT_F16E5 && d_w && d_hi && d_lo && taps > 0 && cin > 0 && cout > 0 && cin_pad >= cin && cin_pad % 64 == 0);
+    MV3D_REQUIRE((long long)taps * cin_pad <= 65535LL * 32);
+    dim3 grid(ceil_div(cout, 32), ceil_div(taps * cin_pad, 32));
+    pack_weights_f16e5_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(d_w, taps, cin, cout, cin_pad,
+                                                                              (unsigned short*)d_hi, (uint8_t*)d_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_pad_nhwc_fmt(const float* d_in, int B, int H, int W, int C, int c_pad, void* d_hi,
+                                                                       void* d_lo, int fmt, void* stream) {
+    if (fmt == MV3D_FMT_BF16X2) return mv3d_pad_nhwc(d_in, B, H, W, C, c_pad, d_hi, d_lo, stream);
+    MV3D_REQUIRE(fmt == MV3D_FMT_F16E5 && d_in && d_hi && d_lo && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C && c_pad % 64 == 0);
+    const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
+    pad_nhwc_f16e5_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_in, B, H, W, C, c_pad,
+                                                                                   (unsigned short*)d_hi, (uint8_t*)d_lo);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_unpad_nhwc_fmt(const void* d_hi, const void* d_lo, int B, int H, int W, int C, int c_pad,
+                                                                         float* d_out, int fmt, void* stream) {
+    if (fmt == MV3D_FMT_BF16X2) return mv3d_unpad_nhwc(d_hi, d_lo, B, H, W, C, c_pad, d_out, stream);
+    MV3D_REQUIRE(fmt == MV3D_FMT_F16E5 && d_hi && d_lo && d_out && B > 0 && H > 0 && W > 0 && C > 0 && c_pad >= C && c_pad % 64 == 0);
+    const long long total = (long long)B * H * W * C;
+    unpad_nhwc_f16e5_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)d_hi, (const uint8_t*)d_lo, B, H, W, C, c_pad, d_out);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_maxpool2x2_pad_fmt(const void* d_in_hi, const void* d_in_lo, int B, int H, int W, int c_pad,
+                                                                             void* d_out_hi, void* d_out_lo, int fmt, void* stream) {
+    if (fmt == MV3D_FMT_BF16X2) return mv3d_maxpool2x2_pad(d_in_hi, d_in_lo, B, H, W, c_pad, d_out_hi, d_out_lo, stream);
+    MV3D_REQUIRE(fmt == MV3D_FMT_F16E5 && d_in_hi && d_in_lo && d_out_hi && d_out_lo && B > 0 && H > 1 && W > 1 && c_pad % 64 == 0);
+    const long long total = (long long)B * (H / 2 + 1) * (W / 2 + 1) * (c_pad / 8);
+    maxpool2x2_pad_f16e5_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)d_in_hi, (const uint8_t*)d_in_lo, B, H, W, c_pad, (unsigned short*)d_out_hi,
+        (uint8_t*)d_out_lo);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -6,6 +6,7 @@ libmv3d_b200.so.  Nothing here falls back to torch math or to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -28,9 +29,14 @@ def pad_channels(c: int) -> int:
     return 16 if c <= 16 else round_up(c, 64)
 
 
+FMT_BF16X2, FMT_F16E5 = 0, 1   # MV3D_FMT_* of include/mv3d_b200.h
+F16E5_MAX_WEIGHT = 15.9        # fp16(4096 w) must stay finite
+
+
 @dataclass
 class PadAct:
-    """Activation in the PAD layout: bf16 hi (+ optional lo) of shape (B, H+1, W+1, c_pad)."""
+    """Activation in the PAD layout, shape (B, H+1, W+1, c_pad): bf16 hi (+ optional lo) planes (fmt FMT_BF16X2), or an
+    fp16 plane + an e5m2 byte plane of the same pitch (fmt FMT_F16E5; both held in bf16-typed tensors as raw bits)."""
 
     hi: torch.Tensor
     lo: Optional[torch.Tensor]
@@ -38,6 +44,7 @@ class PadAct:
     H: int
     W: int
     C: int
+    fmt: int = FMT_BF16X2
 
     @property
     def c_pad(self) -> int:
@@ -54,14 +61,14 @@ def _new_pad(B, H, W, c_pad, precise, device):
     return hi, lo
 
 
-def pad_nhwc(x: torch.Tensor, precise: bool = True) -> PadAct:
+def pad_nhwc(x: torch.Tensor, precise: bool = True, fmt: int = FMT_BF16X2) -> PadAct:
     """(B,H,W,C) float32 -> PAD."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     B, H, W, Cc = x.shape
-    cp = pad_channels(Cc)
-    hi, lo = _new_pad(B, H, W, cp, precise, x.device)
-    check(lib().mv3d_pad_nhwc(ptr(x), B, H, W, Cc, cp, ptr(hi), ptr(lo), current_stream()), "mv3d_pad_nhwc")
-    return PadAct(hi, lo, B, H, W, Cc)
+    cp = pad_channels(Cc) if fmt == FMT_BF16X2 else round_up(Cc, 64)
+    hi, lo = _new_pad(B, H, W, cp, precise or fmt == FMT_F16E5, x.device)
+    check(lib().mv3d_pad_nhwc_fmt(ptr(x), B, H, W, Cc, cp, ptr(hi), ptr(lo), fmt, current_stream()), "mv3d_pad_nhwc_fmt")
+    return PadAct(hi, lo, B, H, W, Cc, fmt)
 
 
 def im2col3x3(x: torch.Tensor, precise: bool = True, k_pad: int = 32) -> PadAct:
@@ -76,8 +83,8 @@ def im2col3x3(x: torch.Tensor, precise: bool = True, k_pad: int = 32) -> PadAct:
 
 def unpad_nhwc(a: PadAct) -> torch.Tensor:
     out = torch.empty((a.B, a.H, a.W, a.C), dtype=torch.float32, device=a.hi.device)
-    check(lib().mv3d_unpad_nhwc(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.C, a.c_pad, ptr(out), current_stream()),
-          "mv3d_unpad_nhwc")
+    check(lib().mv3d_unpad_nhwc_fmt(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.C, a.c_pad, ptr(out), a.fmt, current_stream()),
+          "mv3d_unpad_nhwc_fmt")
     return out
 
 
@@ -85,9 +92,9 @@ def maxpool2x2(a: PadAct) -> PadAct:
     """Network.max_pool(2,2,2,2,'VALID') on the PAD layout."""
     Ho, Wo = a.H // 2, a.W // 2
     hi, lo = _new_pad(a.B, Ho, Wo, a.c_pad, a.lo is not None, a.hi.device)
-    check(lib().mv3d_maxpool2x2_pad(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.c_pad, ptr(hi), ptr(lo), current_stream()),
-          "mv3d_maxpool2x2_pad")
-    return PadAct(hi, lo, a.B, Ho, Wo, a.C)
+    check(lib().mv3d_maxpool2x2_pad_fmt(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.c_pad, ptr(hi), ptr(lo), a.fmt,
+                                        current_stream()), "mv3d_maxpool2x2_pad_fmt")
+    return PadAct(hi, lo, a.B, Ho, Wo, a.C, a.fmt)
 
 
 @dataclass
@@ -101,9 +108,11 @@ class PackedWeight:
     cin: int
     cin_pad: int
     cout: int
+    fmt: int = FMT_BF16X2
 
 
-def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None) -> PackedWeight:
+def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Optional[int] = None,
+                 fmt: int = FMT_BF16X2) -> PackedWeight:
     """HWIO (kh,kw,Cin,Cout) or (Cin,Cout) float32 -> PackedWeight (network.py:119 / :388 layouts)."""
     assert w_hwio.is_cuda and w_hwio.dtype == torch.float32
     w = w_hwio.contiguous()
@@ -111,12 +120,26 @@ def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Op
         w = w.view(1, 1, *w.shape)
     kh, kw, cin, cout = w.shape
     taps = kh * kw
-    cp = cin_pad or pad_channels(cin)
+    cp = cin_pad or (pad_channels(cin) if fmt == FMT_BF16X2 else round_up(cin, 64))
+    if fmt == FMT_F16E5 and not float(w.abs().max()) < F16E5_MAX_WEIGHT:  # once per weight version (range guard only)
+        raise ValueError("f16e5 weights must satisfy |w| < %g (fp16 plane holds 4096 w)" % F16E5_MAX_WEIGHT)
     hi = torch.empty((cout, taps * cp), dtype=BF16, device=w.device)
     lo = torch.empty_like(hi)
-    check(lib().mv3d_pack_weights(ptr(w), taps, cin, cout, cp, ptr(hi), ptr(lo), current_stream()), "mv3d_pack_weights")
+    check(lib().mv3d_pack_weights_fmt(ptr(w), taps, cin, cout, cp, ptr(hi), ptr(lo), fmt, current_stream()),
+          "mv3d_pack_weights_fmt")
     b = None if bias is None else bias.to(torch.float32).contiguous()
-    return PackedWeight(hi, lo, b, taps, cin, cp, cout)
+    return PackedWeight(hi, lo, b, taps, cin, cp, cout, fmt)
+
+
+PAIR_MODE = os.environ.get("MV3D_PAIR", "1") != "0"  # mirrors pair_mode() in csrc/conv_gemm_tcgen05.cu
+
+
+def set_pair_mode(on: bool) -> bool:
+    """CTA-pair (cta_group::2) 3x3 conv kernel on/off; returns the previous setting."""
+    global PAIR_MODE
+    prev = bool(lib().mv3d_gemm_set_pair_mode(1 if on else 0))
+    PAIR_MODE = bool(on)
+    return prev
 
 
 GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch with CUDA events on its stream
@@ -125,11 +148,17 @@ GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch wit
 def gemm_kernel_name(taps: int, k_per_tap: int, n: int, passes: int, split_k: int = 1) -> str:
     """Which template instantiation mv3d_conv_gemm dispatches to (mirrors dispatch_bn / launch_gemm in
     csrc/conv_gemm_tcgen05.cu) -- used to attribute per-launch timings to kernels in bench.py."""
+    if passes == 2:
+        if PAIR_MODE and (n % 256 == 0 or n in (64, 128)):
+            return "conv3x3_pair_kernel<%d,2>" % min(n, 256)
+        return "conv3x3_reuse_kernel<%d,2>" % (128 if n > 64 else 64)
     if passes == 1 and n > 128:
         bn = 256
     else:
         bn = 128 if n > 64 else (64 if n > 32 else 32)
     if taps == 9 and k_per_tap % 64 == 0 and split_k <= 1:
+        if PAIR_MODE and (n % 256 == 0 or n in (64, 128)):
+            return "conv3x3_pair_kernel<%d,%d>" % (min(n, 256), passes)
         return "conv3x3_reuse_kernel<%d,%d>" % (bn, passes)
     return "conv_gemm_kernel<%d,%d,%d>" % (bn, 64 if k_per_tap % 64 == 0 else (32 if k_per_tap % 32 == 0 else 16), passes)
 
@@ -149,24 +178,28 @@ def _run_gemm(_flops=0.0, **kw):
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
          out_f32_dense: bool = False, mask: Optional["PadAct"] = None, mask_scale: float = 1.0,
-         addend: Optional[torch.Tensor] = None, use_bias: bool = True):
+         addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2):
     """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None).
     mask / addend: the backward-data epilogue (out = (acc + addend) gated by mask > 0), see mv3d_gemm_desc."""
     assert w.cin_pad == a.c_pad, (w.cin_pad, a.c_pad)
     assert (not precise) or a.lo is not None
+    assert a.fmt == w.fmt, "activation / weight operand formats differ"
+    assert a.fmt == FMT_BF16X2 or (w.taps == 9 and a.c_pad % 64 == 0 and a.lo is not None)
+    passes = 2 if a.fmt == FMT_F16E5 else (3 if precise else 1)
     dev = a.hi.device
     n_pad = pad_channels(w.cout)
     out = None
     if out_pad:
-        hi, lo = _new_pad(a.B, a.H, a.W, n_pad, precise, dev)
+        assert out_fmt == FMT_BF16X2 or w.cout % 64 == 0
+        hi, lo = _new_pad(a.B, a.H, a.W, n_pad, precise or out_fmt == FMT_F16E5, dev)
         if n_pad != w.cout:
             hi.zero_()
             if lo is not None:
                 lo.zero_()
-        out = PadAct(hi, lo, a.B, a.H, a.W, w.cout)
+        out = PadAct(hi, lo, a.B, a.H, a.W, w.cout, out_fmt)
     dense = torch.empty((a.B, a.H, a.W, w.cout), dtype=torch.float32, device=dev) if out_f32_dense else None
     _run_gemm(_flops=2.0 * a.B * a.H * a.W * w.taps * min(a.C, w.cin) * w.cout,
-              M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=3 if precise else 1,
+              M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=passes, out_fmt=out_fmt,
               d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo),
               d_bias=ptr(w.bias) if use_bias else None,
               relu=int(relu), d_out_hi=ptr(out.hi) if out else None, d_out_lo=ptr(out.lo) if out else None,

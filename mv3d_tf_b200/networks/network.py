@@ -35,6 +35,7 @@ class Node:
     channels: int = 0            # feature channels (maps) or vector width (fc)
     pooled: Optional[tuple] = None  # (PH, PW) after roi_pool
     consumers: List[str] = field(default_factory=list)
+    consumer_nodes: List["Node"] = field(default_factory=list)
     attrs: Dict[str, Any] = field(default_factory=dict)
 
     def __hash__(self):
@@ -69,11 +70,15 @@ def layer(op):
 
 class Network(object):
     def __init__(self, inputs, trainable=True, precise=True, geometry: BevGeometry = REF_GEOMETRY,
-                 img_size=(375, 1242), device='cuda', fv_geometry=None):
+                 img_size=(375, 1242), device='cuda', fv_geometry=None, mixed=False):
         self.inputs = []
         self.layers = dict(inputs)
         self.trainable = trainable
         self.precise = precise          # True: 3-pass bf16 hi/lo GEMMs (parity mode); False: single pass
+        # mixed (inference, with precise): activations between 3x3 convs travel as fp16 + e5m2 pairs (FMT_F16E5) and those
+        # convs run one fp16 pass + one e5m2 correction pass (2/3 of the 3-pass tensor time, ~1e-4 at conv5_3 instead
+        # of ~2e-5; the contract is 1e-3).  1x1 convs, fc layers and training keep the bf16 hi/lo 3-pass form.
+        self.mixed = bool(mixed) and bool(precise)
         self.geometry = geometry
         self.img_size = img_size
         self.fv_geometry = fv_geometry   # None: two-view network exactly as the reference (network.py:313-315)
@@ -130,6 +135,7 @@ class Network(object):
         for i in ins:
             if isinstance(i, Node):
                 i.consumers.append(kind)
+                i.consumer_nodes.append(n)
         self._program.append(n)
         return n
 
@@ -179,15 +185,34 @@ class Network(object):
                 tgt[subkey] = t
         self._packed.clear()
 
-    def _weight(self, name, transform=None) -> K.PackedWeight:
-        pw = self._packed.get(name)
+    def _weight(self, name, transform=None, fmt=K.FMT_BF16X2) -> K.PackedWeight:
+        key = name if fmt == K.FMT_BF16X2 else name + '/f16e5'
+        pw = self._packed.get(key)
         if pw is None:
             p = self.params[name]
             w = p['weights']
             if transform is not None and not self.native_fc_layout:
                 w = transform(w)
-            pw = self._packed[name] = K.pack_weights(w, p['biases'])
+            pw = self._packed[key] = K.pack_weights(w, p['biases'], fmt=fmt)
         return pw
+
+    def _pad_out_fmt(self, node) -> int:
+        """Operand format of a conv node's PAD output: FMT_F16E5 when every reader of that PAD tensor is a 3x3 conv
+        (directly or through 2x2 pools), else bf16 hi/lo."""
+        if not self.mixed or self.training or node.channels % 64 != 0:
+            return K.FMT_BF16X2
+        fmt = node.attrs.get('pad_out_fmt')
+        if fmt is None:
+            def accepts(c):
+                if c.kind == 'conv':
+                    return c.attrs.get('k') == (3, 3)
+                if c.kind == 'max_pool':
+                    return all(accepts(cc) for cc in c.consumer_nodes if cc.kind in ('conv', 'max_pool'))
+                return True  # reads the dense rendering, not the PAD tensor
+            readers = [c for c in node.consumer_nodes if c.kind in ('conv', 'max_pool')]
+            fmt = K.FMT_F16E5 if readers and all(accepts(c) for c in readers) else K.FMT_BF16X2
+            node.attrs['pad_out_fmt'] = fmt
+        return fmt
 
     # ------------------------------------------------------------------ layers (reference signatures)
     @layer
@@ -214,14 +239,17 @@ class Network(object):
                     p = self.params[name]
                     pw = self._packed[name + '/im2col'] = K.pack_weights(p['weights'].reshape(1, 1, 9 * c_i, c_o),
                                                                          p['biases'], cin_pad=32)
-                out, dense = K.conv(col, pw, relu=relu, precise=self.precise, out_pad=want_pad, out_f32_dense=want_dense)
+                out, dense = K.conv(col, pw, relu=relu, precise=self.precise, out_pad=want_pad, out_f32_dense=want_dense,
+                                    out_fmt=self._pad_out_fmt(node))
                 return Val(pad=out, dense=dense)
             if v.pad is None:
                 v.pad = K.pad_nhwc(v.dense, precise=self.precise)
-            out, dense = K.conv(v.pad, self._weight(name), relu=relu, precise=self.precise, out_pad=want_pad,
-                                out_f32_dense=want_dense)
+            out, dense = K.conv(v.pad, self._weight(name, fmt=v.pad.fmt), relu=relu, precise=self.precise,
+                                out_pad=want_pad, out_f32_dense=want_dense, out_fmt=self._pad_out_fmt(node))
             return Val(pad=out, dense=dense)
-        return self._node(name, 'conv', [input], run, channels=c_o)
+        n = self._node(name, 'conv', [input], run, channels=c_o)
+        n.attrs['k'] = (k_h, k_w)
+        return n
 
     @layer
     def max_pool(self, input, k_h, k_w, s_h, s_w, name, padding=DEFAULT_PADDING):

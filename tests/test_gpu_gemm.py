@@ -118,3 +118,103 @@ def test_first_layer_im2col_conv(B, H, W, Cout, passes):
     assert _relerr(dense, dense9) < 3e-5
     assert _relerr(k.unpad_nhwc(out), ref) < (3e-5 if precise else 1e-2)
     assert float(out.hi[:, :, 0, :].abs().max()) == 0 and float(out.hi[:, H, :, :].abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [
+    (1, 12, 13, 64, 64, 3), (1, 23, 50, 128, 256, 3), (1, 23, 50, 128, 256, 1), (1, 30, 33, 256, 512, 3),
+    (2, 75, 75, 64, 128, 3), (1, 200, 300, 64, 64, 3), (1, 87, 100, 512, 512, 3),
+])
+def test_conv3x3_pair_kernel_equals_single_cta(B, H, W, Cin, Cout, passes):
+    """The CTA-pair (cta_group::2, 256 x N tiles) kernel against the single-CTA tap-reuse kernel and torch: the two
+    kernels issue the same K order into fp32 TMEM accumulators, so their outputs are expected to be identical."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H * 131 + W + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(3, 3, Cin, Cout, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    precise = passes == 3
+    a = k.pad_nhwc(x, precise=precise)
+    pw = k.pack_weights(w, b)
+    prev = k.set_pair_mode(True)
+    try:
+        assert k.gemm_kernel_name(9, a.hi.shape[-1], Cout, passes).startswith("conv3x3_pair_kernel")
+        out_p, dense_p = k.conv(a, pw, relu=True, precise=precise, out_pad=True, out_f32_dense=True)
+        k.set_pair_mode(False)
+        out_s, dense_s = k.conv(a, pw, relu=True, precise=precise, out_pad=True, out_f32_dense=True)
+        torch.cuda.synchronize()
+    finally:
+        k.set_pair_mode(prev)
+    xr, wr = (x.double(), w.double()) if precise else (x.bfloat16().double(), w.bfloat16().double())
+    ref = torch.relu(torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), b.double(), padding=1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert _relerr(dense_p, ref) < (3e-5 if precise else 1e-5)
+    assert torch.equal(dense_p, dense_s)
+    assert torch.equal(out_p.hi, out_s.hi)
+    if precise:
+        assert torch.equal(out_p.lo, out_s.lo)
+
+
+def _e5m2(x):
+    return x.float().to(torch.float8_e5m2).double()
+
+
+def _f16e5_conv_emulation(x, w, b):
+    """fp64 evaluation of exactly the operands the f16e5 mode feeds the tensor cores (include/mv3d_b200.h):
+    fp16(x) (x) fp16(4096 w) + [e5m2(x_h) (x) e5m2(residual_w) + e5m2(residual_x * 4096) (x) e5m2(w)], times 2^-12."""
+    S = 4096.0
+    xh = x.clamp(-65504, 65504).half().double()
+    xh8, xl8 = _e5m2(xh), _e5m2((x.double() - xh) * S)
+    wh = (w * S).half().double()
+    wl8, wh8 = _e5m2(w.double() * S - wh), _e5m2(w)
+    cv = lambda a, k: torch.nn.functional.conv2d(a.permute(0, 3, 1, 2), k.permute(3, 2, 0, 1), None, padding=1)
+    y = (cv(xh, wh) + cv(xh8, wl8) + cv(xl8, wh8)) / S + b.double().view(1, -1, 1, 1)
+    return torch.relu(y).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("pair", [True, False])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (1, 12, 13, 64, 64), (1, 23, 50, 128, 256), (1, 30, 33, 256, 512), (2, 75, 75, 64, 128), (1, 87, 100, 512, 512),
+    (1, 37, 41, 36, 64),
+])
+def test_conv3x3_f16e5(B, H, W, Cin, Cout, pair):
+    """passes=2: fp16 main pass + one e5m2 pass carrying both first-order correction terms.  Checked (a) against an fp64
+    evaluation of the very same quantised operands (layout / pairing / scaling exact up to fp32 accumulation) and
+    (b) against the true fp64 convolution: <= 1.5e-4 of max|ref| per layer (measured ~3e-5; bf16 3-pass ~1e-5,
+    plain fp16 ~4e-4), then pooled and chained into a second f16e5 conv."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H * 17 + W + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).abs() * 3
+    x = x * (torch.rand(B, H, W, Cin, device="cuda", generator=g) < 0.6)
+    w = torch.randn(3, 3, Cin, Cout, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    prev = k.set_pair_mode(pair)
+    try:
+        a = k.pad_nhwc(x, fmt=k.FMT_F16E5)
+        # the format itself: x ~= h + l/4096 to ~2^-14.5
+        assert _relerr(k.unpad_nhwc(a), x) < 6e-5
+        pw = k.pack_weights(w, b, fmt=k.FMT_F16E5)
+        out, dense = k.conv(a, pw, relu=True, out_pad=True, out_f32_dense=True, out_fmt=k.FMT_F16E5)
+        torch.cuda.synchronize()
+        emu = _f16e5_conv_emulation(x, w, b)
+        ref = torch.relu(torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1),
+                                                    b.double(), padding=1)).permute(0, 2, 3, 1)
+        assert _relerr(dense, emu) < 3e-5
+        assert _relerr(dense, ref) < 1.5e-4
+        assert _relerr(k.unpad_nhwc(out), dense) < 6e-5
+        assert float(out.hi.view(torch.int16)[:, :, 0, :].abs().max()) == 0
+        assert float(out.hi.view(torch.int16)[:, H, :, :].abs().max()) == 0
+        assert float(out.lo.view(torch.int16)[:, :, 0, :].abs().max()) == 0
+        pooled = k.maxpool2x2(out)
+        pr = torch.nn.functional.max_pool2d(k.unpad_nhwc(out).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        assert torch.equal(k.unpad_nhwc(pooled), pr.contiguous())
+        w2 = torch.randn(3, 3, Cout, 64, device="cuda", generator=g) * (2.0 / (9 * Cout)) ** 0.5
+        pw2 = k.pack_weights(w2, None, fmt=k.FMT_F16E5)
+        o2, d2 = k.conv(pooled, pw2, relu=False, out_pad=True, out_f32_dense=True, out_fmt=k.FMT_BF16X2)
+        r2 = torch.nn.functional.conv2d(pr.double().permute(0, 3, 1, 2), w2.double().permute(3, 2, 0, 1), None,
+                                        padding=1).permute(0, 2, 3, 1)
+        assert _relerr(d2, r2) < 1.5e-4
+        assert _relerr(k.unpad_nhwc(o2), d2) < 1e-5   # bf16 hi/lo rendering of the output for bf16x3 consumers
+    finally:
+        k.set_pair_mode(prev)
