@@ -12,7 +12,7 @@
 //
 // Tile: 128 (pixels) x BN (channels) per CTA, K step KC (64 -> SWIZZLE_128B, 16 -> SWIZZLE_32B).
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
-//             warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+//             warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter on alternate column chunks).
 // PASSES=3: x = hi + lo (bf16 pair); D += A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  (fp32 accumulate).
 // PASSES=2 (tap-reuse kernels only): "f16e5" operands (common.cuh): D += A_h*W_h (fp16) + [A_h8|A_l8]*[W_l8;W_h8] (e5m2,
 //           kind::f8f6f4 at twice the rate) -- the same two correction terms for 2/3 of the tensor-pipe time.
@@ -28,7 +28,7 @@ namespace mv3d {
 using namespace ptx;
 
 constexpr int kBM = 128;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 64 + 32 * 8;  // TMA warp, MMA warp, 8 epilogue warps
 
 struct GemmParams {
     int M, N, Cin, taps, Hp, Wp, H, W;
@@ -52,6 +52,8 @@ struct GemmParams {
     int ld_addend;
     int out_fmt;      // MV3D_FMT_BF16X2 / MV3D_FMT_F16E5 rendering of out_hi / out_lo
     float acc_scale;  // 2^-12 when the operands were f16e5 (PASSES == 2), else 1
+    int dbg_flags;    // MV3D_GEMM_DBG (measurement only, results are garbage): 1 = the pair kernel's producer stops issuing
+                      // TMA loads after the first lap of each ring (pure MMA rate on stale shared memory)
 };
 
 template <int BN, int KC, int PASSES>
@@ -71,35 +73,68 @@ struct GemmCfg {
     static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
 
-// Epilogue of one 128 x BN tile, executed by the 4 epilogue warps (TMEM lane quarter q = warp % 4):
-// TMEM -> registers -> bias / ReLU -> bf16 hi/lo split -> PAD layout and/or fp32.  Halo pixels are written as
-// zeros; the accumulator is handed back to the MMA warp as soon as its last chunk is in registers.
+// Epilogue of one 128 x BN tile, executed by kEpiWarps = 8 epilogue warps: TMEM lane quarter q = warp % 4 (the
+// hardware restriction), and the two warps of a quarter take alternate 32-column chunks (half = 0 / 1).
+// TMEM -> registers -> scale / bias / ReLU -> operand rendering (bf16 hi/lo or f16e5) -> PAD layout and/or fp32.  Halo
+// pixels are written as zeros; each warp hands the accumulator back as soon as its last chunk is in registers.
+// (One warp per quarter and ~40 scalar instructions per element left conv4/conv5 -- a single tile per CTA pair -- with
+// a 20 us serial tail and made the Cout = 64 layers epilogue-bound: ncu showed the MMAs at their floor and the tensor
+// pipe idle the rest of the time.  Hence 8 warps, packed cvt instructions and vector bias loads.)
+constexpr int kEpiWarps = 8;
+
+__device__ __forceinline__ uint32_t cvt_pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_pack_e5m2x2(float lo, float hi) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 template <int BN, int ACC_COLS, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tmem_base, int acc, int m0, int n0, int q,
-                                              int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl) {
+                                              int half, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl) {
+    constexpr int kChunks = (BN + 31) / 32;
     const int row = q * 32 + lane;
     const long long p = (long long)m0 + row;
     const bool in_range = p < prm.M;
     bool halo = false;
     long long dense_row = p;
-    if (prm.Hp > 0) {
-        const int wp = (int)(p % prm.Wp);
-        const long long t = p / prm.Wp;
-        const int hp = (int)(t % prm.Hp);
-        const long long b = t / prm.Hp;
+    if (prm.Hp > 0) {   // M < 2^31: 32-bit index arithmetic
+        const unsigned pu = (unsigned)p;
+        const unsigned t = pu / (unsigned)prm.Wp;
+        const int wp = (int)(pu - t * (unsigned)prm.Wp);
+        const unsigned b = t / (unsigned)prm.Hp;
+        const int hp = (int)(t - b * (unsigned)prm.Hp);
         halo = (wp == 0) || (hp == prm.Hp - 1);
-        dense_row = (b * prm.H + hp) * prm.W + (wp - 1);
+        dense_row = ((long long)b * prm.H + hp) * prm.W + (wp - 1);
     }
     mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
     tc_fence_after();
     const uint32_t taddr_row = tmem_base + acc * ACC_COLS + (uint32_t(q * 32) << 16);
+    const int n_mine = (kChunks - half + 1) / 2;   // this warp's chunks: half, half + 2, ...
+    if (n_mine == 0) {   // (BN = 32: one chunk) still one arrival per tile, in step with the accumulator phases
+        if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+            else mbar_arrive(&tmem_empty[acc]);
+        }
+        return;
+    }
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int k = 0; k < n_mine; ++k) {
+        const int c = (half + 2 * k) * 32;
         uint32_t v[32];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
         tmem_ld_32x32(taddr_row + c, v);
         tmem_ld_wait();
-        if (c + 32 >= BN) {  // last chunk is in registers: hand the accumulator back to the MMA warp
+        if (k == n_mine - 1) {  // this warp's last chunk is in registers: hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -118,15 +153,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
                 if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
             continue;
         }
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) * prm.acc_scale;
-            if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
-            if (prm.relu) x = fmaxf(x, 0.f);
-            f[j] = halo ? 0.f : x;
-        }
         const bool full = (col0 + 32 <= prm.N);
+        float f[32];
+        if (halo) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        } else {
+            const float sc = prm.acc_scale;
+            if (prm.bias != nullptr && full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + col0 + j));
+                    f[j] = __uint_as_float(v[j]) * sc + b4.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) * sc + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) * sc + b4.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) * sc + b4.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]) * sc;
+                    if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
+                    f[j] = x;
+                }
+            }
+            if (prm.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+        }
         if (prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
             const float* ad = prm.addend + dense_row * prm.ld_addend + col0;
 #pragma unroll
@@ -155,20 +210,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
         }
         if (prm.out_hi != nullptr && prm.out_fmt == MV3D_FMT_F16E5) {
             // fp16 plane + byte plane [e5m2(h) x64 | e5m2(residual * 4096) x64] per 64-channel chunk (host checks
-            // N % 64 == 0, ld_out % 64 == 0, so every 32-column chunk is full and 16-byte aligned)
+            // N % 64 == 0, ld_out % 64 == 0, so every 32-column chunk is full and 16-byte aligned).  Same arithmetic as
+            // split_f16e5 (common.cuh), two elements per cvt instruction.
             unsigned short* oh = reinterpret_cast<unsigned short*>(prm.out_hi) + p * prm.ld_out + col0;
             uint8_t* ob = reinterpret_cast<uint8_t*>(prm.out_lo) + p * prm.ld_out * 2 + f16e5_off(col0);
             uint32_t ph[16], p8[8], q8[8];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                unsigned short h[4];
-                uint8_t a8[4], b8[4];
+                uint32_t a8[2], b8[2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split_f16e5(f[j + e], h[e], a8[e], b8[e]);
-                ph[j / 2] = uint32_t(h[0]) | (uint32_t(h[1]) << 16);
-                ph[j / 2 + 1] = uint32_t(h[2]) | (uint32_t(h[3]) << 16);
-                p8[j / 4] = uint32_t(a8[0]) | (uint32_t(a8[1]) << 8) | (uint32_t(a8[2]) << 16) | (uint32_t(a8[3]) << 24);
-                q8[j / 4] = uint32_t(b8[0]) | (uint32_t(b8[1]) << 8) | (uint32_t(b8[2]) << 16) | (uint32_t(b8[3]) << 24);
+                for (int e = 0; e < 2; ++e) {
+                    const float x0 = fminf(fmaxf(f[j + 2 * e], -65504.f), 65504.f);
+                    const float x1 = fminf(fmaxf(f[j + 2 * e + 1], -65504.f), 65504.f);
+                    const uint32_t h2 = cvt_pack_f16x2(x0, x1);
+                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+                    ph[j / 2 + e] = h2;
+                    a8[e] = cvt_pack_e5m2x2(hf.x, hf.y);
+                    b8[e] = cvt_pack_e5m2x2((x0 - hf.x) * kF16E5Scale, (x1 - hf.y) * kF16E5Scale);
+                }
+                p8[j / 4] = a8[0] | (a8[1] << 16);
+                q8[j / 4] = b8[0] | (b8[1] << 16);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -186,12 +247,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
                 for (int j = 0; j < 32; j += 8) {
                     uint32_t ph4[4], pl4[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(f[j + 2 * e], h0, l0);
-                        split_bf16(f[j + 2 * e + 1], h1, l1);
-                        ph4[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-                        pl4[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+                    for (int e = 0; e < 4; ++e) {   // = split_bf16 on two elements
+                        const float x0 = f[j + 2 * e], x1 = f[j + 2 * e + 1];
+                        const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
+                        ph4[e] = h2;
+                        pl4[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
                     }
                     *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
                     if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
@@ -254,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[a], kEpiWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -342,13 +402,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
         int tl = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = ((w / tiles_n) % tiles_m) * kBM;
-            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
         }
     }
     tc_fence_before();
@@ -421,7 +481,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         }
         for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < Cfg::kNW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -517,7 +577,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = ((w / tiles_n) % tiles_m) * kBM;
-            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
         }
     }
     tc_fence_before();
@@ -592,7 +652,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
         for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < Cfg::kNW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kEpiWarps); }
         fence_barrier_init();
     }
     // tcgen05.alloc.cta_group::2 is a two-party protocol that ptxas expands into messages through the RESERVED shared
@@ -625,15 +685,24 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     mbar_wait(&a_empty[ea], ((ia / Cfg::kNA) & 1) ^ 1);
                     uint8_t* ab = a_ring + ea * Cfg::kAEntry;
                     const uint32_t afull = mapa_u32(smem_u32(&a_full[ea]), 0);
+                    const bool skip_a = (prm.dbg_flags & 1) && ia >= Cfg::kNA;
+                    if (skip_a) {
+                        if (rank == 0) mbar_arrive(&a_full[ea]);
+                    } else {
                     if (rank == 0) mbar_arrive_expect_tx(&a_full[ea], 2 * Cfg::kABoxBytes * Cfg::kOperands);
                     const int arow = m0 + (kh - 1) * prm.Wp - 1;
                     tma_load_2d_pair(ab, &map_a_hi, afull, c0, arow);
                     if (PASSES >= 2) tma_load_2d_pair(ab + Cfg::kAPlane, &map_a_lo, afull, c0, arow);
+                    }
                     for (int kw = 0; kw < 3; ++kw, ++iw) {
                         const int ew = iw % Cfg::kNW;
                         mbar_wait(&w_empty[ew], ((iw / Cfg::kNW) & 1) ^ 1);
                         uint8_t* wb = w_ring + ew * Cfg::kWEntry;
                         const uint32_t wfull = mapa_u32(smem_u32(&w_full[ew]), 0);
+                        if ((prm.dbg_flags & 1) && iw >= Cfg::kNW) {
+                            if (rank == 0) mbar_arrive(&w_full[ew]);
+                            continue;
+                        }
                         if (rank == 0) mbar_arrive_expect_tx(&w_full[ew], 2 * Cfg::kWEntry);
                         const int kcol = (kh * 3 + kw) * prm.Cin + c0;
                         tma_load_2d_pair(wb, &map_w_hi, wfull, kcol, n0);
@@ -698,7 +767,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         for (int w = pair_id; w < n_work; w += n_pairs, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = (w / tiles_n) * (2 * kBM) + (int)rank * kBM;
-            epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
         }
     }
     tc_fence_before();
@@ -761,6 +830,9 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MV3D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg_flags = dbg;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;

@@ -23,7 +23,7 @@ def main():
     mode = sys.argv[2] if len(sys.argv) > 2 else "precise"
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False
-    net = get_network("MV3D_test", bv_channels=36, precise=(mode == "precise"), geometry=CFG_GEOMETRY)
+    net = get_network("MV3D_test", bv_channels=36, precise=(mode != "fast"), mixed=(mode == "mixed"), geometry=CFG_GEOMETRY)
     net.init_weights(seed=7, mode="he")
     raster = BevRasterizer(**bench.BEV)
     pts, img = bench.synth_frame(0)
@@ -43,7 +43,7 @@ def main():
     for i in range(reps):
         if i == 3:
             kernels._run_gemm = traced
-        bv = raster.to_pad(pts, precise=(mode == "precise"))
+        bv = raster.to_pad(pts, precise=(mode != "fast"))
         net.run(fetch, {net.lidar_bv_data: bv, net.image_data: img, net.im_info: im_info, net.calib: orc.KITTI_CALIB})
     torch.cuda.synchronize()
     kernels._run_gemm = orig
