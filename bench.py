@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """MV3D per-frame detection hot path: frames/s on synthetic KITTI-shaped frames (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode precise|fast]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode mixed|precise|fast]
 
 One step = one frame through the whole path: LiDAR (120 k points) -> BEV raster 701x801x36 -> BEV + RGB
 VGG16 trunks (tcgen05 implicit GEMM) -> RPN head -> device proposal layer (decode/sort/NMS) -> fused 2-view
@@ -217,7 +217,7 @@ def run_train_bench(args, rank, world, local_rank):
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False
     B = args.train_batch
-    precise = args.mode == "precise"
+    precise = args.mode != "fast"   # training keeps the bf16 hi/lo 3-pass GEMMs in both parity modes
     net = get_network("MV3D_train", bv_channels=36, precise=precise, geometry=CFG_GEOMETRY)
     net.init_weights(seed=7, mode="he")
     sw = SolverWrapper(network=net, keep_prob=0.5, process_group=dist.group.WORLD if world > 1 else None)
@@ -275,7 +275,7 @@ def run_train_bench(args, rank, world, local_rank):
             "n_gpus": world, "gpu_launches_per_step": launches, "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
             "loss": [float(x) for x in loss.tolist()], "optimizer": "Adam lr=1e-5 (TF-1.0 defaults), keep_prob 0.5",
             "grad_allreduce": "NCCL all-reduce of the flat fp32 gradient buffer (%.0f MB)" % (sw.grad.numel() * 4 / 1e6)
-            if world > 1 else "off (single GPU)", "mode": args.mode,
+            if world > 1 else "off (single GPU)", "mode": "precise" if args.mode != "fast" else "fast",
             "workload": "configs[2]: MV3D train step fwd+bwd+Adam, %d frames/GPU: 120k-pt LiDAR -> BEV 701x801x36, RGB "
                         "375x1242, 6 GT cars/frame, RPN 12000/2000 proposals, 128 sampled rois/frame" % B}
 
@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="precise", choices=["precise", "mixed", "fast"],
+    ap.add_argument("--mode", default="mixed", choices=["precise", "mixed", "fast"],
                     help="precise: bf16 hi/lo 3-pass everywhere; mixed: fp16 + e5m2-pair operands (2 pass-equivalents) "
                          "in the 3x3 convs, 3-pass elsewhere; fast: single bf16 pass (not a parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -343,7 +343,7 @@ def main():
             print(json.dumps({"metric": "MV3D train-step ms", "value": tr["ms"], "unit": "ms", "n_gpus": world,
                               "steps": tr["steps"], "warmup": max(args.warmup, 3), "ms_per_step": tr["ms"],
                               "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3",
-                              "data": "synthetic", "config": {"workload": tr["workload"], "mode": args.mode},
+                              "data": "synthetic", "config": {"workload": tr["workload"], "mode": "precise" if args.mode != "fast" else "fast"},
                               "gpu_launches": tr["gpu_launches_per_step"] * tr["steps"], "train_step": tr}))
         if world > 1:
             dist.destroy_process_group()
