@@ -780,6 +780,169 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// fc layers over a few hundred ROIs (fc6: 300 x 25088 -> 2048): SWAPPED CTA-pair GEMM.  The layer is bound by weight
+// bytes (fc6: 205 MB of bf16 hi/lo per branch).  With the ROIs on the M side (three 128-row tiles) every weight tile
+// is pulled through L2 three times and each CTA moves as many activation bytes as weight bytes (1.2 GB L2->SM per
+// fc6, the L2 ceiling).  Here the WEIGHTS are the M operand of a 256-row pair tile and ALL ROIs are the N operand
+// (two MMA column chunks of C <= 256, the ROI rows split between the two CTAs), so each weight byte is fetched
+// exactly once and the (small, L2-resident) activation matrix once per 256 output features: 0.44 GB per fc6.
+//   D^T[f, r] = sum_k W[f, k] * A[r, k]        (both operands K-major, as they are stored)
+// K is split over work items; partial sums go to the fp32 accumulator out[r, f] with red.global.add -- lanes are
+// consecutive features, so the adds of one column are coalesced.  Same 3-pass bf16 hi/lo arithmetic.
+// ------------------------------------------------------------------------------------------------
+struct FcSwapParams {
+    int F, R, K;            // output features (rows of W), ROIs (rows of A), reduction length (multiple of 64)
+    int C;                  // columns per MMA chunk: 2 chunks cover R_pad = 2C ROIs; C % 16 == 0, C <= 256
+    int k_steps_total, k_steps_per_split, n_split, n_work;
+    int stages, stage_bytes;
+    float* out;             // (R, ld) fp32, zeroed by the caller
+    int ld;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+fc_swapped_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                       const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const FcSwapParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kWPlane = kBM * 128;                   // 128 weight rows x 64 channels
+    const int half_rows = prm.C / 2;                     // ROI rows this CTA stages per chunk
+    const int a_chunk = half_rows * 128;                 // bytes of one chunk tile
+    const int a_plane = 2 * a_chunk;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + prm.stages * prm.stage_bytes);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tmem_full = empty_bar + 8;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_w_hi);
+        prefetch_tensormap(&map_w_lo);
+        prefetch_tensormap(&map_a_hi);
+        prefetch_tensormap(&map_a_lo);
+        for (int i = 0; i < prm.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 2 * kEpiWarps);
+        fence_barrier_init();
+    }
+    cluster_sync_all();                                  // see conv3x3_pair_kernel: both CTAs running before the alloc
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) tmem_relinquish_pair();
+    const uint32_t tmem_base = *tmem_slot;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int w = pair_id; w < prm.n_work; w += n_pairs) {
+                const int mt = w / prm.n_split, sp = w - mt * prm.n_split;
+                const int f0 = mt * (2 * kBM) + (int)rank * kBM;
+                const int k_begin = sp * prm.k_steps_per_split;
+                const int k_end = min(k_begin + prm.k_steps_per_split, prm.k_steps_total);
+                for (int ks = k_begin; ks < k_end; ++ks, ++it) {
+                    const int s = it % prm.stages;
+                    mbar_wait(&empty_bar[s], ((it / prm.stages) & 1) ^ 1);
+                    uint8_t* st = smem + s * prm.stage_bytes;
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * prm.stage_bytes);
+                    const int c0 = ks * 64;
+                    tma_load_2d_pair(st, &map_w_hi, fb, c0, f0);
+                    tma_load_2d_pair(st + kWPlane, &map_w_lo, fb, c0, f0);
+                    uint8_t* ab = st + 2 * kWPlane;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r0 = h * prm.C + (int)rank * half_rows;
+                        tma_load_2d_pair(ab + h * a_chunk, &map_a_hi, fb, c0, r0);
+                        tma_load_2d_pair(ab + a_plane + h * a_chunk, &map_a_lo, fb, c0, r0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBM, prm.C);
+            int it = 0, tl = 0;
+            for (int w = pair_id; w < prm.n_work; w += n_pairs, ++tl) {
+                const int sp = w % prm.n_split;
+                const int k_begin = sp * prm.k_steps_per_split;
+                const int k_end = min(k_begin + prm.k_steps_per_split, prm.k_steps_total);
+                mbar_wait(tmem_empty, (tl & 1) ^ 1);
+                tc_fence_after();
+                for (int ks = k_begin; ks < k_end; ++ks, ++it) {
+                    const int s = it % prm.stages;
+                    mbar_wait(&full_bar[s], (it / prm.stages) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t w_hi = smem_u32(smem + s * prm.stage_bytes);
+                        const uint32_t w_lo = w_hi + kWPlane;
+                        const uint32_t a_hi = w_lo + kWPlane;
+                        const uint32_t a_lo = a_hi + a_plane;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t d_tmem = tmem_base + h * prm.C;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t dw = make_kmajor_desc(w_hi + k * 32, 128);
+                                const uint64_t dwl = make_kmajor_desc(w_lo + k * 32, 128);
+                                const uint64_t da = make_kmajor_desc(a_hi + h * a_chunk + k * 32, 128);
+                                const uint64_t dal = make_kmajor_desc(a_lo + h * a_chunk + k * 32, 128);
+                                mma_bf16_ss_pair(d_tmem, dw, da, idesc, (ks > k_begin || k > 0) ? 1u : 0u);
+                                mma_bf16_ss_pair(d_tmem, dwl, da, idesc, 1u);
+                                mma_bf16_ss_pair(d_tmem, dw, dal, idesc, 1u);
+                            }
+                        }
+                        mma_commit_pair(&empty_bar[s], 3);
+                        if (ks == k_end - 1) mma_commit_pair(tmem_full, 3);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int n_chunks = (2 * prm.C) / 32;
+        int tl = 0;
+        for (int w = pair_id; w < prm.n_work; w += n_pairs, ++tl) {
+            const int mt = w / prm.n_split;
+            const int f = mt * (2 * kBM) + (int)rank * kBM + q * 32 + lane;   // this thread's output feature
+            mbar_wait(tmem_full, tl & 1);
+            tc_fence_after();
+            const uint32_t taddr_row = tmem_base + (uint32_t(q * 32) << 16);
+            for (int ci = half; ci < n_chunks; ci += 2) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr_row + ci * 32, v);
+                tmem_ld_wait();
+                if (ci + 2 >= n_chunks) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty), 0));
+                }
+                if (f < prm.F) {
+                    float* o = prm.out + (long long)(ci * 32) * prm.ld + f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ci * 32 + j < prm.R) red_add_f32(o + (long long)j * prm.ld, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+    cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int tap_reuse_mode() {  // MV3D_TAP_REUSE=0 selects the plain nine-box kernel (A/B comparisons); default on
@@ -863,6 +1026,49 @@ static int try_launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream, bool* t
     if (d->N == 128) return launch_pair<128, PASSES>(d, stream);
     if (d->N == 64) return launch_pair<64, PASSES>(d, stream);
     *taken = false;
+    return MV3D_OK;
+}
+
+// fc over <= 512 ROIs with a split-K fp32 accumulator: the swapped CTA-pair kernel (weights stream through once).
+static bool fc_swap_applicable(const mv3d_gemm_desc* d) {
+    return d->taps == 1 && d->Hp == 0 && d->passes == 3 && d->split_k > 1 && d->d_out_f32 && d->Cin % 64 == 0 &&
+           d->N % 256 == 0 && d->M >= 64 && d->M <= 512 && pair_mode() != 0;
+}
+
+static int launch_fc_swapped(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    FcSwapParams p;
+    p.F = d->N; p.R = d->M; p.K = d->Cin;
+    p.C = ceil_div(d->M, 32) * 16;
+    p.k_steps_total = d->Cin / 64;
+    const int m_tiles = d->N / (2 * kBM);
+    const int pairs_avail = num_sms() / 2;
+    int split = pairs_avail / m_tiles;                    // one wave of work items
+    if (split < 1) split = 1;
+    if (split > p.k_steps_total) split = p.k_steps_total;
+    p.k_steps_per_split = ceil_div(p.k_steps_total, split);
+    p.n_split = ceil_div(p.k_steps_total, p.k_steps_per_split);
+    p.n_work = m_tiles * p.n_split;
+    p.stage_bytes = 2 * kBM * 128 + 2 * (2 * (p.C / 2) * 128);
+    p.stages = (220 * 1024) / p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return MV3D_ERR_ARG;
+    p.out = d->d_out_f32; p.ld = d->ld_f32;
+    CUtensorMap mw_hi, mw_lo, ma_hi, ma_lo;
+    int rc;
+    if ((rc = make_map_2d(&mw_hi, d->d_w_hi, d->N, d->Cin, kBM, 64)) != MV3D_OK) return rc;
+    if ((rc = make_map_2d(&mw_lo, d->d_w_lo, d->N, d->Cin, kBM, 64)) != MV3D_OK) return rc;
+    if ((rc = make_map_2d(&ma_hi, d->d_a_hi, d->M, d->Cin, p.C / 2, 64)) != MV3D_OK) return rc;
+    if ((rc = make_map_2d(&ma_lo, d->d_a_lo, d->M, d->Cin, p.C / 2, 64)) != MV3D_OK) return rc;
+    const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fc_swapped_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    const int pairs = p.n_work < pairs_avail ? p.n_work : pairs_avail;
+    fc_swapped_pair_kernel<<<2 * pairs, kGemmThreads, smem_bytes, stream>>>(mw_hi, mw_lo, ma_hi, ma_lo, p);
+    MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }
 
@@ -1013,6 +1219,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(!d->f32_dense || d->Hp > 0);
     MV3D_REQUIRE(d->split_k <= 1 || (!d->d_mask_hi && !d->d_addend_f32));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (fc_swap_applicable(d)) return launch_fc_swapped(d, s);
     if (d->passes == 2) {
         if (pair_mode() != 0) {
             bool taken = false;

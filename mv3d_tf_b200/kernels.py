@@ -145,9 +145,12 @@ def set_pair_mode(on: bool) -> bool:
 GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch with CUDA events on its stream
 
 
-def gemm_kernel_name(taps: int, k_per_tap: int, n: int, passes: int, split_k: int = 1) -> str:
+def gemm_kernel_name(taps: int, k_per_tap: int, n: int, passes: int, split_k: int = 1, m: int = 0, hp: int = 0) -> str:
     """Which template instantiation mv3d_conv_gemm dispatches to (mirrors dispatch_bn / launch_gemm in
     csrc/conv_gemm_tcgen05.cu) -- used to attribute per-launch timings to kernels in bench.py."""
+    if (taps == 1 and hp == 0 and passes == 3 and split_k > 1 and k_per_tap % 64 == 0 and n % 256 == 0
+            and 64 <= m <= 512 and PAIR_MODE):
+        return "fc_swapped_pair_kernel"
     if passes == 2:
         if PAIR_MODE and (n % 256 == 0 or n in (64, 128)):
             return "conv3x3_pair_kernel<%d,2>" % min(n, 256)
@@ -173,7 +176,7 @@ def _run_gemm(_flops=0.0, **kw):
     check(lib().mv3d_conv_gemm(C.byref(d), current_stream()), "mv3d_conv_gemm")
     if GEMM_EVENTS is not None:
         e1.record(torch.cuda.current_stream())
-        GEMM_EVENTS.append((e0, e1, gemm_kernel_name(d.taps, d.Cin, d.N, d.passes, d.split_k), float(_flops)))
+        GEMM_EVENTS.append((e0, e1, gemm_kernel_name(d.taps, d.Cin, d.N, d.passes, d.split_k, d.M, d.Hp), float(_flops)))
 
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,

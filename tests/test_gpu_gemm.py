@@ -20,6 +20,8 @@ def _relerr(a, b):
 @pytest.mark.parametrize("M,N,K,passes,split_k", [
     (128, 32, 64, 1, 1), (128, 64, 64, 3, 1), (300, 128, 256, 3, 1), (1000, 512, 1152, 3, 1), (1000, 512, 1152, 1, 1),
     (257, 50, 4096, 3, 1), (300, 2048, 3136, 3, 4), (77, 24, 48, 3, 1), (640, 256, 16, 1, 1), (130, 8, 512, 3, 1),
+    # split-K fc over <= 512 rows with N % 256 == 0: the swapped CTA-pair kernel (weights on the M side)
+    (128, 256, 512, 3, 2), (512, 512, 1024, 3, 3), (65, 256, 192, 3, 2), (300, 2048, 25088, 3, 3), (256, 2048, 2048, 3, 3),
 ])
 def test_fc_gemm(M, N, K, passes, split_k):
     from mv3d_tf_b200 import kernels as k
@@ -30,6 +32,8 @@ def test_fc_gemm(M, N, K, passes, split_k):
     b = torch.randn(N, device="cuda", generator=g)
     pw = k.pack_weights(w, b, cin_pad=K)
     a_hi, a_lo = _split(a)
+    if passes == 3 and split_k > 1 and N % 256 == 0 and 64 <= M <= 512 and K % 64 == 0:
+        assert k.gemm_kernel_name(1, K, N, 3, split_k, M, 0) == "fc_swapped_pair_kernel"
     hi, lo, f32 = k.linear(a_hi, a_lo, pw, relu=True, precise=(passes == 3), out_bf16=True, out_f32=True, split_k=split_k)
     torch.cuda.synchronize()
     if passes == 3:
