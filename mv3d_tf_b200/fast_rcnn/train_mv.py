@@ -128,7 +128,9 @@ class SolverWrapper(object):
         if self.output_dir is None:
             return None
         os.makedirs(self.output_dir, exist_ok=True)
-        filename = os.path.join(self.output_dir, 'MV3D_iter_{:d}.npy'.format(iter + 1))
+        from .config import cfg
+        infix = ('_' + cfg.TRAIN.SNAPSHOT_INFIX if cfg.TRAIN.get('SNAPSHOT_INFIX', '') != '' else '')
+        filename = os.path.join(self.output_dir, cfg.TRAIN.SNAPSHOT_PREFIX + infix + '_iter_{:d}'.format(iter + 1) + '.npy')
         np.save(filename, self.export_params(), allow_pickle=True)
         print('Wrote snapshot to: {:s}'.format(filename))
         return filename
@@ -288,6 +290,8 @@ class SolverWrapper(object):
         """train_mv.py:87-219: loop over blobs, one Adam step each, periodic loss print + snapshot."""
         from .config import cfg
         data = self.roidb if data is None else data
+        if isinstance(data, list) and data and isinstance(data[0], dict) and 'lidar_bv_path' in data[0]:
+            data = get_data_layer(data, self.imdb.num_classes if self.imdb is not None else 2)   # train_mv.py:154
         it = iter(data)
         last = None
         for i in range(max_iters):
@@ -308,8 +312,44 @@ class SolverWrapper(object):
             self.snapshot(None, max_iters - 1)
 
 
+def get_training_roidb(imdb):
+    """train_mv.py:315-332: (optionally flipped) roidb enriched by prepare_roidb."""
+    from .config import cfg
+    from ..roi_data_layer import roidb as rdl_roidb
+    if cfg.TRAIN.USE_FLIPPED:
+        raise NotImplementedError('USE_FLIPPED: the MV3D minibatch never flips its blobs (minibatch_mv3d.py:32-40); '
+                                  'the reference default is False (config.py:84)')
+    print('Preparing training data...')
+    rdl_roidb.prepare_roidb(imdb)
+    print('done')
+    return imdb.roidb
+
+
+def get_data_layer(roidb, num_classes):
+    """train_mv.py:335-346."""
+    from ..roi_data_layer.layer import RoIDataLayer
+    return RoIDataLayer(roidb, num_classes)
+
+
+def filter_roidb(roidb):
+    """train_mv.py:348-371: drop entries with neither a foreground nor a background RoI."""
+    from .config import cfg
+
+    def is_valid(entry):
+        overlaps = entry['max_overlaps']
+        fg_inds = np.where(overlaps >= cfg.TRAIN.FG_THRESH)[0]
+        bg_inds = np.where((overlaps < cfg.TRAIN.BG_THRESH_HI) & (overlaps >= cfg.TRAIN.BG_THRESH_LO))[0]
+        return len(fg_inds) > 0 or len(bg_inds) > 0
+    num = len(roidb)
+    filtered_roidb = [entry for entry in roidb if is_valid(entry)]
+    print('Filtered {} roidb entries: {} -> {}'.format(num - len(filtered_roidb), num, len(filtered_roidb)))
+    return filtered_roidb
+
+
 def train_net(network, imdb, roidb, output_dir, pretrained_model=None, max_iters=10000):
     """train_mv.py:373-381."""
+    if isinstance(roidb, list) and roidb and isinstance(roidb[0], dict) and 'max_overlaps' in roidb[0]:
+        roidb = filter_roidb(roidb)
     sw = SolverWrapper(None, None, network, imdb, roidb, output_dir, pretrained_model=pretrained_model)
     print('Solving...')
     sw.train_model(None, max_iters)

@@ -218,3 +218,76 @@ def load() -> _Ref:
 if __name__ == "__main__":
     r = load()
     print("reference shim ok:", sorted(vars(r)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KITTI feed: the reference's dataset / data-layer modules, same mechanical treatment
+# ---------------------------------------------------------------------------------------------------------------
+_FEED_FILES = [
+    ("datasets/imdb.py", "datasets/imdb.py"),
+    ("datasets/kitti_mv3d.py", "datasets/kitti_mv3d.py"),
+    ("roi_data_layer/roidb.py", "roi_data_layer/roidb.py"),
+    ("roi_data_layer/minibatch_mv3d.py", "roi_data_layer/minibatch_mv3d.py"),
+    ("roi_data_layer/layer.py", "roi_data_layer/layer.py"),
+    ("utils/boxes_grid.py", "utils/boxes_grid.py"),
+    ("utils/blob.py", "utils/blob.py"),
+]
+_FEED_RULES = [
+    (r"^(\s*)print (?!\()([^#]*?)\s+#(.*)$", r"\1print(\2)  #\3"),   # print statement with a trailing comment
+] + _PY_RULES + [
+    (r"^import cPickle$", "import pickle as cPickle"),
+    (r"^from read_lidar import", "from utils.read_lidar import"),
+    (r"if roidb\[i\]\['boxes_corners'\] == \[\]:", "if isinstance(roidb[i]['boxes_corners'], list) and roidb[i]['boxes_corners'] == []:"),
+    (r"if dets == \[\]:", "if isinstance(dets, list) and dets == []:"),
+]
+
+
+def build_feed(force: bool = False) -> str:
+    root = build(force)
+    stamp = os.path.join(root, ".feed_built")
+    if os.path.exists(stamp) and not force:
+        return root
+    for pkg in ("datasets", "roi_data_layer"):
+        os.makedirs(os.path.join(root, pkg), exist_ok=True)
+    open(os.path.join(root, "roi_data_layer", "__init__.py"), "w").close()
+    # datasets/__init__.py of the reference imports every dataset (pascal, coco, matlab ...); the stub keeps the two
+    # names kitti_mv3d.py uses: the imdb class and ROOT_DIR (overridable for tests)
+    with open(os.path.join(root, "datasets", "__init__.py"), "w") as f:
+        f.write("import os\nfrom .imdb import imdb\nROOT_DIR = os.environ.get('MV3D_SHIM_ROOT_DIR', '/tmp/mv3d_ref_shim_root')\n")
+    # cv2 is not installed: imread through PIL, in cv2's B,G,R channel order
+    with open(os.path.join(root, "cv2.py"), "w") as f:
+        f.write("import numpy as np\nfrom PIL import Image\n"
+                "def imread(p):\n    return np.ascontiguousarray(np.asarray(Image.open(p).convert('RGB'))[:, :, ::-1])\n")
+    for src, dst in _FEED_FILES:
+        text = _patch(open(os.path.join(REF_ROOT, "lib", src)).read(), _FEED_RULES)
+        open(os.path.join(root, dst), "w").write(text)
+        compile(text, os.path.join(root, dst), "exec")
+    open(stamp, "w").write("ok\n")
+    return root
+
+
+def load_feed() -> _Ref:
+    """kitti_mv3d / prepare_roidb / get_minibatch / RoIDataLayer of the reference, importable under py3."""
+    root = build_feed()
+    pk = _PKGS + ("datasets", "roi_data_layer", "cv2")
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in pk}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, root)
+    try:
+        ns = _Ref()
+        ns.config = importlib.import_module("fast_rcnn.config")
+        ns.cfg = ns.config.cfg
+        ns.datasets = importlib.import_module("datasets")
+        ns.kitti_mv3d = importlib.import_module("datasets.kitti_mv3d")
+        ns.roidb = importlib.import_module("roi_data_layer.roidb")
+        ns.minibatch = importlib.import_module("roi_data_layer.minibatch_mv3d")
+        ns.layer = importlib.import_module("roi_data_layer.layer")
+        ns.transform = importlib.import_module("utils.transform")
+        ns.yml = os.path.join(REF_ROOT, "experiments", "cfgs", "faster_rcnn_end2end.yml")
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k.split(".")[0] in pk]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return ns
