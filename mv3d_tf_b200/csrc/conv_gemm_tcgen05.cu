@@ -52,8 +52,9 @@ struct GemmParams {
     int ld_addend;
     int out_fmt;      // MV3D_FMT_BF16X2 / MV3D_FMT_F16E5 rendering of out_hi / out_lo
     float acc_scale;  // 2^-12 when the operands were f16e5 (PASSES == 2), else 1
-    int dbg_flags;    // MV3D_GEMM_DBG (measurement only, results are garbage): 1 = the pair kernel's producer stops issuing
-                      // TMA loads after the first lap of each ring (pure MMA rate on stale shared memory)
+    int dbg_flags;    // MV3D_GEMM_DBG (measurement only, results are garbage; pair kernel): 1 = the producer stops issuing TMA
+                      // loads after the first lap of each ring (pure MMA rate on stale shared memory), 4 = the epilogue
+                      // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
 };
 
 template <int BN, int KC, int PASSES>
@@ -143,6 +144,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
             }
         }
         if (!in_range) continue;
+        if (prm.dbg_flags & 4) continue;   // MV3D_GEMM_DBG=4 (timing experiment): drain the accumulator, skip the math / stores
         const int col0 = n0 + c;
         if (col0 >= prm.N) continue;
         if (prm.split_k > 1) {
@@ -725,32 +727,25 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 for (int g = 0; g < n_groups; ++g, ++ia) {
                     const int ea = ia % Cfg::kNA;
                     mbar_wait(&a_full[ea], (ia / Cfg::kNA) & 1);
-                    const uint32_t a_hi = smem_u32(a_ring + ea * Cfg::kAEntry);
-                    const uint32_t a_lo = a_hi + Cfg::kAPlane;
+                    // descriptor low words: base of this A entry, advanced by whole rows (kw) and along K (k) with adds
+                    const uint32_t da_base = kmajor_desc_lo(smem_u32(a_ring + ea * Cfg::kAEntry));
                     for (int kw = 0; kw < 3; ++kw, ++iw) {
                         const int ew = iw % Cfg::kNW;
                         mbar_wait(&w_full[ew], (iw / Cfg::kNW) & 1);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t w_hi = smem_u32(w_ring + ew * Cfg::kWEntry);
-                            const uint32_t w_lo = w_hi + Cfg::kWPlane;
+                            const uint32_t da_kw = da_base + kw * (128 >> 4);
+                            const uint32_t db_base = kmajor_desc_lo(smem_u32(w_ring + ew * Cfg::kWEntry));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint32_t aoff = kw * 128 + k * 32;
-                                const uint64_t da = make_kmajor_desc(a_hi + aoff, 128);
-                                const uint64_t db = make_kmajor_desc(w_hi + k * 32, 128);
-                                mma_bf16_ss_pair(d_tmem, da, db, idesc, (g > 0 || kw > 0 || k > 0) ? 1u : 0u);
+                                const uint32_t da = da_kw + k * (32 >> 4), db = db_base + k * (32 >> 4);
+                                mma_f16_pair_lo(d_tmem, da, db, idesc, (g > 0 || kw > 0 || k > 0) ? 1u : 0u);
                                 if (PASSES == 3) {
-                                    const uint64_t dal = make_kmajor_desc(a_lo + aoff, 128);
-                                    const uint64_t dbl = make_kmajor_desc(w_lo + k * 32, 128);
-                                    mma_bf16_ss_pair(d_tmem, dal, db, idesc, 1u);
-                                    mma_bf16_ss_pair(d_tmem, da, dbl, idesc, 1u);
+                                    mma_f16_pair_lo(d_tmem, da + (Cfg::kAPlane >> 4), db, idesc, 1u);
+                                    mma_f16_pair_lo(d_tmem, da, db + (Cfg::kWPlane >> 4), idesc, 1u);
                                 }
-                                if (PASSES == 2) {
-                                    const uint64_t dal = make_kmajor_desc(a_lo + aoff, 128);
-                                    const uint64_t dbl = make_kmajor_desc(w_lo + k * 32, 128);
-                                    mma_f8_ss_pair(d_tmem, dal, dbl, idesc8, 1u);
-                                }
+                                if (PASSES == 2)
+                                    mma_f8_pair_lo(d_tmem, da + (Cfg::kAPlane >> 4), db + (Cfg::kWPlane >> 4), idesc8, 1u);
                             }
                             mma_commit_pair(&w_empty[ew], 3);
                             if (kw == 2) mma_commit_pair(&a_empty[ea], 3);
@@ -993,6 +988,7 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
+    p.dbg_flags = 0;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MV3D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg_flags = dbg;
@@ -1102,6 +1098,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
+    p.dbg_flags = 0;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1152,6 +1149,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
+    p.dbg_flags = 0;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation

@@ -175,6 +175,31 @@ __device__ __forceinline__ void mma_f8_ss_pair(uint32_t d_tmem, uint64_t a_desc,
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Pair MMAs with the shared-memory descriptors passed as their LOW words (start address >> 4 | LBO field); the high
+// word of a SWIZZLE_128B K-major descriptor is a constant.  Advancing a descriptor along K or by whole rows is then one
+// 32-bit add in the issuing thread -- the issue loop is the bottleneck of the narrow (Cout <= 128) layers.
+constexpr uint32_t kDescHiSw128 = 0x40004040u;  // SBO = 1024 B, version 1, layout SWIZZLE_128B (make_kmajor_desc(.., 128) >> 32)
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma_f16_pair_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f8_pair_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+        : "memory");
+}
 // Arrive on the mbarrier at this offset in every CTA of `cta_mask` once the issued pair MMAs have completed.
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
     asm volatile(
