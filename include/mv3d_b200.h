@@ -59,6 +59,11 @@ int mv3d_bev_raster_pad(const float* d_points, int n_points, int point_stride, v
                         int c_pad, int H, int W, int C, int nslices, const double* h_slice_lo,
                         const double* h_slice_hi, float res, float fwd0, float fwd1, float side0, float side1,
                         float height0, int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream);
+/* mv3d_bev_raster_pad with the PAD planes rendered in `fmt` (MV3D_FMT_BF16X2, or MV3D_FMT_F16E5 with c_pad % 64 == 0). */
+int mv3d_bev_raster_pad_fmt(const float* d_points, int n_points, int point_stride, void* d_pad_hi, void* d_pad_lo,
+                            int c_pad, int H, int W, int C, int nslices, const double* h_lo, const double* h_hi,
+                            float res, float fwd0, float fwd1, float side0, float side1, float height0, int xoff,
+                            int yoff, void* d_workspace, size_t workspace_bytes, int fmt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (iii) NMS.

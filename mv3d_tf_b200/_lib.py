@@ -61,6 +61,9 @@ SIGNATURES = {
     "mv3d_bev_raster_pad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float, c_int,
                                     c_int, c_void_p, c_size_t, c_void_p]),
+    "mv3d_bev_raster_pad_fmt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float, c_int,
+                                        c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "_nms": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int]),
     "mv3d_nms_workspace_bytes": (c_size_t, [c_int]),
     "mv3d_nms": (c_int, [c_void_p, c_int, c_int, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -143,7 +146,7 @@ def lib() -> C.CDLL:
 
 
 # kernels launched by one successful call of each entry point (memsets not counted) -- bench.py's gpu_launches
-KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
+KERNELS_PER_CALL = {"mv3d_bev_raster": 4, "mv3d_bev_raster_pad": 4, "mv3d_bev_raster_pad_fmt": 4, "mv3d_nms": 2, "mv3d_proposal_layer_3d": 7, "mv3d_proposal_decode": 1,
                     "mv3d_roi_pool_forward": 1, "mv3d_roi_pool_backward": 1, "mv3d_roi_pool_multiview": 1,
                     "mv3d_conv_gemm": 1, "mv3d_conv_wgrad": 1, "mv3d_pack_weights": 1, "mv3d_pad_nhwc": 1, "mv3d_im2col3x3_pad": 1, "mv3d_unpad_nhwc": 1,
                     "mv3d_maxpool2x2_pad": 1, "mv3d_pack_weights_fmt": 1, "mv3d_pad_nhwc_fmt": 1, "mv3d_unpad_nhwc_fmt": 1,

@@ -21,6 +21,7 @@ struct RasterGeom {
     int H, W, C, nslices;
     int pad;          // 0: float32 (H,W,C) output; 1: PAD bf16 output (H+1, W+1, c_pad), pixel (r,c) at [r][c+1]
     int Hout, Wout, c_pad;
+    int pad_fmt;      // rendering of the PAD output: MV3D_FMT_BF16X2 (hi/lo planes) or MV3D_FMT_F16E5 (fp16 + e5m2 byte plane)
     int tiles_x, tiles_y;  // 16x16 tiles over the OUTPUT grid
     float res, fwd0, fwd1, side0, side1, h0;
     int xoff, yoff;
@@ -122,6 +123,25 @@ __global__ void raster_scatter_kernel(const float* __restrict__ pts, int n, int 
     }
 }
 
+// One value of the PAD output in the trunk's operand format.
+__device__ __forceinline__ void store_pad(const RasterGeom& g, __nv_bfloat16* pad_hi, __nv_bfloat16* pad_lo, size_t pix,
+                                          int ch, float v) {
+    if (g.pad_fmt == MV3D_FMT_F16E5) {
+        unsigned short h;
+        uint8_t h8, l8;
+        split_f16e5(v, h, h8, l8);
+        reinterpret_cast<unsigned short*>(pad_hi)[pix * g.c_pad + ch] = h;
+        uint8_t* row = reinterpret_cast<uint8_t*>(pad_lo) + pix * g.c_pad * 2;
+        row[f16e5_off(ch)] = h8;
+        row[f16e5_off(ch) + 64] = l8;
+    } else {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        pad_hi[pix * g.c_pad + ch] = h;
+        if (pad_lo) pad_lo[pix * g.c_pad + ch] = l;
+    }
+}
+
 // One CTA per tile.  smem: winner table [256 cells][nslices] (point index + 1, 0 = empty) + top winner [256].
 __global__ void __launch_bounds__(kRasterThreads)
 raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, const int* __restrict__ offset,
@@ -180,10 +200,7 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
             if (!(z >= g.lo[sl] && z < g.hi[sl]) || tab[cell * ns + sl] != idx + 1 || sl == g.C - 1) continue;
             const float v = __fsub_rn(zf, g.h0);                                                  // :106,110
             if (g.pad) {
-                __nv_bfloat16 h, l;
-                split_bf16(v, h, l);
-                pad_hi[pix * g.c_pad + sl] = h;
-                if (pad_lo) pad_lo[pix * g.c_pad + sl] = l;
+                store_pad(g, pad_hi, pad_lo, pix, sl, v);
             } else {
                 top[pix * g.C + sl] = v;
             }
@@ -191,10 +208,7 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
         if (top_winner[cell] == idx + 1) {                                                       // :113
             const float v = p[3];
             if (g.pad) {
-                __nv_bfloat16 h, l;
-                split_bf16(v, h, l);
-                pad_hi[pix * g.c_pad + g.C - 1] = h;
-                if (pad_lo) pad_lo[pix * g.c_pad + g.C - 1] = l;
+                store_pad(g, pad_hi, pad_lo, pix, g.C - 1, v);
             } else {
                 top[pix * g.C + g.C - 1] = v;
             }
@@ -219,8 +233,10 @@ using namespace mv3d;
 static int raster_impl(const float* d_points, int n_points, int point_stride, float* d_top, void* d_pad_hi,
                        void* d_pad_lo, int c_pad, int H, int W, int C, int nslices, const double* h_lo,
                        const double* h_hi, float res, float fwd0, float fwd1, float side0, float side1, float height0,
-                       int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream) {
+                       int xoff, int yoff, void* d_workspace, size_t workspace_bytes, void* stream,
+                       int pad_fmt = MV3D_FMT_BF16X2) {
     const int pad = d_pad_hi ? 1 : 0;
+    MV3D_REQUIRE(pad_fmt == MV3D_FMT_BF16X2 || (pad_fmt == MV3D_FMT_F16E5 && d_pad_hi && d_pad_lo && c_pad % 64 == 0));
     MV3D_REQUIRE((d_top || d_pad_hi) && H > 0 && W > 0 && C > 0 && n_points >= 0 && point_stride >= 4);
     MV3D_REQUIRE(n_points == 0 || d_points);
     MV3D_REQUIRE(nslices >= 0 && nslices <= kMaxSlices && nslices <= C && (nslices == 0 || (h_lo && h_hi)));
@@ -228,7 +244,7 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
     MV3D_REQUIRE(!pad || (c_pad >= C && c_pad % 8 == 0));
     RasterGeom g;
     g.H = H; g.W = W; g.C = C; g.nslices = nslices;
-    g.pad = pad; g.Hout = H + pad; g.Wout = W + pad; g.c_pad = c_pad;
+    g.pad = pad; g.Hout = H + pad; g.Wout = W + pad; g.c_pad = c_pad; g.pad_fmt = pad_fmt;
     g.tiles_x = ceil_div(g.Wout, kTile); g.tiles_y = ceil_div(g.Hout, kTile);
     g.res = res; g.fwd0 = fwd0; g.fwd1 = fwd1; g.side0 = side0; g.side1 = side1; g.h0 = height0;
     g.xoff = xoff; g.yoff = yoff;
@@ -306,4 +322,15 @@ extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster_pad(
     MV3D_REQUIRE(d_pad_hi != nullptr);
     return raster_impl(d_points, n_points, point_stride, nullptr, d_pad_hi, d_pad_lo, c_pad, H, W, C, nslices, h_lo,
                        h_hi, res, fwd0, fwd1, side0, side1, height0, xoff, yoff, d_workspace, workspace_bytes, stream);
+}
+
+/* Same, with the PAD planes rendered in `fmt` (MV3D_FMT_BF16X2 = mv3d_bev_raster_pad; MV3D_FMT_F16E5: fp16 plane + e5m2
+ * byte plane, c_pad % 64 == 0), so that conv1_1 of the BEV trunk consumes the raster in the mixed-mode operand format. */
+extern "C" __attribute__((visibility("default"))) int mv3d_bev_raster_pad_fmt(
+    const float* d_points, int n_points, int point_stride, void* d_pad_hi, void* d_pad_lo, int c_pad, int H, int W,
+    int C, int nslices, const double* h_lo, const double* h_hi, float res, float fwd0, float fwd1, float side0,
+    float side1, float height0, int xoff, int yoff, void* d_workspace, size_t workspace_bytes, int fmt, void* stream) {
+    MV3D_REQUIRE(d_pad_hi != nullptr);
+    return raster_impl(d_points, n_points, point_stride, nullptr, d_pad_hi, d_pad_lo, c_pad, H, W, C, nslices, h_lo,
+                       h_hi, res, fwd0, fwd1, side0, side1, height0, xoff, yoff, d_workspace, workspace_bytes, stream, fmt);
 }

@@ -9,6 +9,8 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
+from .. import kernels as K
+
 from ..utils.read_lidar import BevRasterizer
 from ..utils.transform import projection_matrix
 from .config import cfg
@@ -50,7 +52,9 @@ class FrameRunner:
 
     # ------------------------------------------------------------------
     def _forward(self):
-        bv = self.raster.to_pad(self.pts, precise=self.net.precise)
+        # mixed mode: the raster is written in the f16e5 operand format when conv1_1 can consume it (>= 17 channels pad to 64)
+        fmt = K.FMT_F16E5 if (getattr(self.net, 'mixed', False) and self.raster.g["C"] > 16) else K.FMT_BF16X2
+        bv = self.raster.to_pad(self.pts, precise=self.net.precise, fmt=fmt)
         feed = {self.net.lidar_bv_data: bv, self.net.image_data: self.img, self.net.im_info: self.im_info,
                 self.net.calib: self.proj}
         if self.fv_raster is not None:

@@ -61,29 +61,30 @@ class BevRasterizer:
             self._ws_points = n
         return self._ws
 
-    def to_pad(self, clouds, precise: bool = True):
-        """Rasterise one cloud per frame straight into the conv trunk's input layout (kernels.PadAct, bf16 hi/lo,
-        zero halo) -- the float32 map is never materialised."""
-        from ..kernels import BF16, PadAct, pad_channels
+    def to_pad(self, clouds, precise: bool = True, fmt: int = 0):
+        """Rasterise one cloud per frame straight into the conv trunk's input layout (kernels.PadAct, zero halo) -- the
+        float32 map is never materialised.  fmt: kernels.FMT_BF16X2 (bf16 hi/lo) or kernels.FMT_F16E5 (the mixed-mode
+        operand format; channels padded to a multiple of 64)."""
+        from ..kernels import BF16, FMT_F16E5, PadAct, pad_channels, round_up
 
         if isinstance(clouds, torch.Tensor):
             clouds = [clouds]
         g = self.g
-        cp = pad_channels(g["C"])
+        cp = round_up(g["C"], 64) if fmt == FMT_F16E5 else pad_channels(g["C"])
         dev = clouds[0].device
         hi = torch.empty((len(clouds), g["H"] + 1, g["W"] + 1, cp), dtype=BF16, device=dev)
-        lo = torch.empty_like(hi) if precise else None
+        lo = torch.empty_like(hi) if (precise or fmt == FMT_F16E5) else None
         res, zres, side, fwd, hr = self.args
         for b, pts in enumerate(clouds):
             assert pts.is_cuda and pts.dtype == torch.float32 and pts.dim() == 2 and pts.shape[1] >= 4
             pts = pts.contiguous()
             ws = self._workspace(pts.shape[0], dev)
-            check(lib().mv3d_bev_raster_pad(ptr(pts), pts.shape[0], pts.shape[1], ptr(hi[b]),
-                                            ptr(lo[b]) if lo is not None else None, cp, g["H"], g["W"], g["C"],
-                                            g["nslices"], ptr(g["lo"]), ptr(g["hi"]), res, fwd[0], fwd[1], side[0],
-                                            side[1], hr[0], g["xoff"], g["yoff"], ptr(ws), ws.numel(),
-                                            current_stream()), "mv3d_bev_raster_pad")
-        return PadAct(hi, lo, len(clouds), g["H"], g["W"], g["C"])
+            check(lib().mv3d_bev_raster_pad_fmt(ptr(pts), pts.shape[0], pts.shape[1], ptr(hi[b]),
+                                                ptr(lo[b]) if lo is not None else None, cp, g["H"], g["W"], g["C"],
+                                                g["nslices"], ptr(g["lo"]), ptr(g["hi"]), res, fwd[0], fwd[1], side[0],
+                                                side[1], hr[0], g["xoff"], g["yoff"], ptr(ws), ws.numel(), fmt,
+                                                current_stream()), "mv3d_bev_raster_pad_fmt")
+        return PadAct(hi, lo, len(clouds), g["H"], g["W"], g["C"], fmt)
 
 
 def point_cloud_2_top(points, res=0.1, zres=0.3, side_range=(-10., 10.), fwd_range=(-10., 10.),

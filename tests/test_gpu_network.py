@@ -244,3 +244,42 @@ def test_frame_pipeline_two_in_flight_equals_sequential(oracle):
                 assert torch.equal(w[name], g[name]), name
             else:
                 assert torch.allclose(w[name], g[name], rtol=1e-4, atol=1e-5), name
+
+
+def test_mixed_trunk_from_f16e5_raster(oracle):
+    """Mixed mode end to end on the BEV branch: the rasteriser writes the f16e5 operand format directly (>= 17 channels),
+    conv1_1 already runs the 2-pass form, conv5_3 stays within the 1e-3 contract of the fp32 CPU oracle."""
+    from oracle import net_oracle
+    from mv3d_tf_b200 import kernels as K
+    from mv3d_tf_b200.networks.factory import get_network
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+
+    rk = dict(res=0.1, zres=0.1, side_range=(-8., 8.), fwd_range=(0., 16.), height_range=(-2.0, 0.4))
+    pts = oracle.synth_points(40000, seed=11)
+    pts[:, 0] *= 0.2
+    pts[:, 1] *= 0.17
+    top = oracle.point_cloud_2_top(pts, **rk)
+    C = top.shape[-1]
+    assert C > 16
+    raster = BevRasterizer(**rk)
+    dev_pts = torch.from_numpy(pts).cuda()
+    pad = raster.to_pad(dev_pts, fmt=K.FMT_F16E5)
+    assert pad.fmt == K.FMT_F16E5 and pad.c_pad == 64
+    # the raster in operand format == the float32 raster pushed through the same rendering
+    want = K.unpad_nhwc(K.pad_nhwc(torch.from_numpy(top[None]).cuda(), fmt=K.FMT_F16E5))
+    assert torch.equal(K.unpad_nhwc(pad), want)
+    assert float((want.cpu() - torch.from_numpy(top[None])).abs().max()) < 1e-4
+    net = get_network("MV3D_test", bv_channels=C, precise=True, mixed=True)
+    net.init_weights(seed=7, mode="he")
+    rng = np.random.default_rng(1)
+    img = rng.normal(0, 40, (1, 64, 256, 3)).astype(np.float32)
+    feed = {net.lidar_bv_data: pad, net.image_data: img, net.im_info: np.array([[161, 161, 1]], np.float32),
+            net.calib: oracle.KITTI_CALIB}
+    c12, c53 = net.run([net.get_output("conv1_2"), net.get_output("conv5_3")], feed)
+    torch.cuda.synchronize()
+    params = {k: {kk: vv.cpu().numpy() for kk, vv in v.items()} for k, v in net.params.items()}
+    keep = {}
+    ref = net_oracle.trunk(top[None], params, "", keep=keep)
+    e12, e53 = _rel(c12, keep["conv1_2"]), _rel(c53, ref)
+    print("mixed trunk from f16e5 raster: conv1_2 %.2e conv5_3 %.2e" % (e12, e53))
+    assert e12 < 2e-4 and e53 < 1e-3
