@@ -51,6 +51,48 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, int taps,
     }
 }
 
+// 64(K) x 64(cout) tiles, 256 threads: reads run along cout (256 B per k row), every thread then emits EIGHT consecutive
+// packed-K elements of one output row as one 16-byte store per plane (8 lanes cover 128 contiguous bytes of a row).
+// The packers run once per weight version -- once per training step for all 143 M parameters.
+__global__ void __launch_bounds__(256)
+pack_weights_tiled64_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cin_pad,
+                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    __shared__ float tile[64][65];
+    const int kdim = taps * cin_pad;
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int j = ty; j < 64; j += 4) {
+        const int k = k0 + j, n = n0 + tx;
+        float x = 0.f;
+        if (k < kdim && n < cout) {
+            const int t = k / cin_pad, c = k - t * cin_pad;
+            if (c < cin) x = __ldg(w + ((long long)t * cin + c) * cout + n);
+        }
+        tile[j][tx] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int item = threadIdx.x + it * 256;
+        const int kg = item & 7, nn = item >> 3;
+        const int n = n0 + nn, k = k0 + kg * 8;
+        if (n >= cout || k >= kdim) continue;       // kdim % 8 == 0 (cin_pad is a multiple of 16)
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(tile[kg * 8 + 2 * e][nn], h0, l0);
+            split_bf16(tile[kg * 8 + 2 * e + 1][nn], h1, l1);
+            ph[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+            pl[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+        }
+        const long long o = (long long)n * kdim + k;
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+
 // (B,H,W,C) fp32 -> PAD (B,H+1,W+1,c_pad) bf16 hi/lo.  One thread per 8 output channels (16-byte stores).
 __global__ void pad_nhwc_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -362,7 +404,12 @@ extern "C" __attribute__((visibility("default"))) int mv3d_pack_weights(const fl
                                  void* stream) {
     MV3D_REQUIRE(d_w && d_hi && taps > 0 && cin > 0 && cout > 0 && cin_pad >= cin);
     const long long total = (long long)cout * taps * cin_pad;
-    if (cout >= 32 && (long long)taps * cin_pad <= 65535LL * 32) {
+    if (cout >= 64 && cin_pad % 8 == 0 && (long long)taps * cin_pad <= 65535LL * 64 &&
+        (reinterpret_cast<uintptr_t>(d_hi) & 15) == 0 && (!d_lo || (reinterpret_cast<uintptr_t>(d_lo) & 15) == 0)) {
+        dim3 grid(ceil_div(cout, 64), ceil_div(taps * cin_pad, 64));
+        pack_weights_tiled64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    } else if (cout >= 32 && (long long)taps * cin_pad <= 65535LL * 32) {
         dim3 grid(ceil_div(cout, 32), ceil_div(taps * cin_pad, 32));
         pack_weights_tiled_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
             d_w, taps, cin, cout, cin_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);

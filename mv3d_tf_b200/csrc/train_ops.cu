@@ -167,6 +167,42 @@ __global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, int taps,
     }
 }
 
+// Same packing, eight consecutive output channels per thread (two float4 loads, one 16-byte store per plane); used when
+// cout % 4 == 0 so that the loads are aligned.
+__global__ void pack_weights_dgrad_vec_kernel(const float* __restrict__ w, int taps, int cin, int cout, int cout_pad,
+                                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int nv = cout_pad / 8;
+    const long long total = (long long)cin * taps * nv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int n8 = (int)(i % nv) * 8;
+        const long long r = i / nv;
+        const int tp = (int)(r % taps);
+        const int c = (int)(r / taps);
+        const float* src = w + ((long long)(taps - 1 - tp) * cin + c) * cout + n8;
+        float x[8];
+        if (n8 + 8 <= cout) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = (n8 + e < cout) ? src[e] : 0.f;
+        }
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x[2 * e], h0, l0);
+            split_bf16(x[2 * e + 1], h1, l1);
+            ph[e] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+            pl[e] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+        }
+        *reinterpret_cast<uint4*>(hi + i * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (lo) *reinterpret_cast<uint4*>(lo + i * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+
 // dense fp32 (B,H,W,C) gradient -> PAD bf16 hi/lo gated by (mask_hi > 0) (mask = forward activation, PAD, same C pad).
 __global__ void pad_nhwc_masked_kernel(const float* __restrict__ in, int B, int H, int W, int C, int c_pad,
                                        const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ hi,
@@ -433,8 +469,13 @@ MV3D_API int mv3d_pack_weights_dgrad(const float* d_w, int taps, int cin, int co
                                      void* d_lo, void* stream) {
     MV3D_REQUIRE(d_w && d_hi && taps > 0 && cin > 0 && cout > 0 && cout_pad >= cout);
     const long long total = (long long)cin * taps * cout_pad;
-    pack_weights_dgrad_kernel<<<grid_for_t(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        d_w, taps, cin, cout, cout_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    if (cout % 4 == 0 && cout_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(d_hi) & 15) == 0 && (!d_lo || (reinterpret_cast<uintptr_t>(d_lo) & 15) == 0))
+        pack_weights_dgrad_vec_kernel<<<grid_for_t(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            d_w, taps, cin, cout, cout_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
+    else
+        pack_weights_dgrad_kernel<<<grid_for_t(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            d_w, taps, cin, cout, cout_pad, (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -237,3 +237,31 @@ def test_adam_matches_tf_formula():
     assert float((theta.double() - ref).abs().max()) < 1e-6
     # (1 - beta2) is formed in float32 like TF's fp32 variables do: 1 - 0.999f carries a 4.7e-5 relative error
     assert _relerr(m, rm) < 1e-5 and _relerr(v, rv) < 1e-4
+
+
+@pytest.mark.parametrize("kh,cin,cout,off", [(3, 64, 64, 0), (3, 36, 128, 0), (1, 4096, 50, 0), (1, 512, 24, 0), (3, 128, 256, 2),
+                                              (1, 200, 2048, 0), (3, 9, 64, 1), (1, 4096, 2, 0)])
+def test_weight_packers_exact(kh, cin, cout, off):
+    """pack_weights (forward, K-major transposed) and pack_weights_dgrad (flipped taps) against the index formulas of
+    include/mv3d_b200.h, bit for bit -- every kernel variant (64x64 tiles, 32x32 tiles, scalar; vector / scalar dgrad),
+    including a weight view that is not 16-byte aligned (`off` floats into a flat buffer, as in the trainer)."""
+    from mv3d_tf_b200 import kernels as k
+
+    gen = torch.Generator(device="cuda").manual_seed(kh * 1000 + cin + cout)
+    flat = torch.randn(off + kh * kh * cin * cout, device="cuda", generator=gen)
+    w = flat[off:].view(kh, kh, cin, cout)
+    taps = kh * kh
+    pw = k.pack_weights(w, None)
+    cp = pw.cin_pad
+    ref = torch.zeros(cout, taps, cp, device="cuda")
+    ref[:, :, :cin] = w.reshape(taps, cin, cout).permute(2, 0, 1)
+    ref = ref.reshape(cout, taps * cp)
+    hi = ref.bfloat16()
+    assert torch.equal(pw.hi, hi) and torch.equal(pw.lo, (ref - hi.float()).bfloat16())
+    pd = k.pack_weights_dgrad(w)
+    cop = pd.cin_pad                     # (PackedWeight of the dgrad operand: its K extent is the padded cout)
+    refd = torch.zeros(cin, taps, cop, device="cuda")
+    refd[:, :, :cout] = w.reshape(taps, cin, cout).flip(0).permute(1, 0, 2)
+    refd = refd.reshape(cin, taps * cop)
+    hid = refd.bfloat16()
+    assert torch.equal(pd.hi, hid) and torch.equal(pd.lo, (refd - hid.float()).bfloat16())
