@@ -233,23 +233,37 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
                 p8[j / 4] = a8[0] | (a8[1] << 16);
                 q8[j / 4] = b8[0] | (b8[1] << 16);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(oh)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                reinterpret_cast<uint4*>(ob)[j] = make_uint4(p8[4 * j], p8[4 * j + 1], p8[4 * j + 2], p8[4 * j + 3]);
-                reinterpret_cast<uint4*>(ob + 64)[j] = make_uint4(q8[4 * j], q8[4 * j + 1], q8[4 * j + 2], q8[4 * j + 3]);
-            }
+            // each thread owns one pixel row: 256-bit stores = whole 32-byte sectors (rows are >= 128 B apart, so a
+            // 16-byte store per lane would touch 32 half sectors per instruction -- the LSU transaction count, not the
+            // arithmetic, was what the epilogue spent its time on)
+            st_global_v8(oh, ph);
+            st_global_v8(oh + 16, ph + 8);
+            st_global_v8(ob, p8);
+            st_global_v8(ob + 64, q8);
         } else if (prm.out_hi != nullptr) {
             __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
             __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
-            if (full && (prm.ld_out % 8 == 0)) {
+            if (full && !(prm.dbg_flags & 8) && (prm.ld_out % 16 == 0) && ((reinterpret_cast<uintptr_t>(prm.out_hi) | reinterpret_cast<uintptr_t>(prm.out_lo)) & 31) == 0) {
+                uint32_t ph[16], pl[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {   // = split_bf16 on two elements
+                    const float x0 = f[2 * e], x1 = f[2 * e + 1];
+                    const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
+                    ph[e] = h2;
+                    pl[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
+                }
+                st_global_v8(oh, ph);
+                st_global_v8(oh + 16, ph + 8);
+                if (ol) {
+                    st_global_v8(ol, pl);
+                    st_global_v8(ol + 16, pl + 8);
+                }
+            } else if (full && (prm.ld_out % 8 == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     uint32_t ph4[4], pl4[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {   // = split_bf16 on two elements
+                    for (int e = 0; e < 4; ++e) {
                         const float x0 = f[j + 2 * e], x1 = f[j + 2 * e + 1];
                         const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
                         ph4[e] = h2;
@@ -269,7 +283,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
         }
         if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
             float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
-            if (full && (prm.ld_f32 % 4 == 0)) {
+            if (full && !(prm.dbg_flags & 8) && (prm.ld_f32 % 8 == 0) && (reinterpret_cast<uintptr_t>(prm.out_f32) & 31) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) st_global_v8(o + j, reinterpret_cast<const uint32_t*>(f + j));
+            } else if (full && (prm.ld_f32 % 4 == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -949,6 +966,11 @@ static int tap_reuse_mode() {  // MV3D_TAP_REUSE=0 selects the plain nine-box ke
     return mode;
 }
 
+static int gemm_dbg_flags() {   // MV3D_GEMM_DBG, see GemmParams::dbg_flags (8 = 128-bit instead of 256-bit epilogue stores)
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MV3D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    return dbg;
+}
 static int g_pair_mode = -1;
 static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B comparisons); default on
     if (g_pair_mode < 0) {
@@ -988,10 +1010,7 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
-    p.dbg_flags = 0;
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("MV3D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
-    p.dbg_flags = dbg;
+    p.dbg_flags = gemm_dbg_flags();
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1098,7 +1117,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
-    p.dbg_flags = 0;
+    p.dbg_flags = gemm_dbg_flags();
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1149,7 +1168,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.mask_hi = static_cast<const __nv_bfloat16*>(d->d_mask_hi); p.ld_mask = d->ld_mask; p.mask_scale = d->mask_scale;
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
-    p.dbg_flags = 0;
+    p.dbg_flags = gemm_dbg_flags();
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
@@ -1206,7 +1225,8 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(d->passes == 1 || (d->d_a_lo && d->d_w_lo));
     MV3D_REQUIRE(d->out_fmt == MV3D_FMT_BF16X2 || d->out_fmt == MV3D_FMT_F16E5);
     // f16e5 output: whole 64-channel chunks, both planes
-    MV3D_REQUIRE(d->out_fmt != MV3D_FMT_F16E5 || !d->d_out_hi || (d->d_out_lo && d->N % 64 == 0 && d->ld_out % 64 == 0 && d->split_k <= 1));
+    MV3D_REQUIRE(d->out_fmt != MV3D_FMT_F16E5 || !d->d_out_hi || (d->d_out_lo && d->N % 64 == 0 && d->ld_out % 64 == 0 && d->split_k <= 1 &&
+                                                                   ((reinterpret_cast<uintptr_t>(d->d_out_hi) | reinterpret_cast<uintptr_t>(d->d_out_lo)) & 31) == 0));
     // f16e5 operands: the tap-reuse 3x3 kernels only
     MV3D_REQUIRE(d->passes != 2 || (d->taps == 9 && d->Cin % 64 == 0 && d->split_k <= 1));
     MV3D_REQUIRE(d->taps == 1 || (d->Hp > 1 && d->Wp > 1));
