@@ -173,3 +173,30 @@ def test_cfg_from_list_and_output_dir(tmp_path):
     finally:
         c.cfg.ROOT_DIR = old
         c.cfg.update(c._defaults())
+
+
+def test_feed_matches_committed_golden(tmp_path, golden_dir):
+    """Same comparison against tests/golden/kitti_feed.npz (the reference's outputs on the seed-3 tree, produced by
+    tests/golden/make_golden_feed.py) -- runs where the reference tree is not mounted."""
+    from mv3d_tf_b200.fast_rcnn import config as ours_cfg
+    from mv3d_tf_b200.fast_rcnn.train_mv import get_training_roidb
+    from mv3d_tf_b200.roi_data_layer.layer import RoIDataLayer
+    from mv3d_tf_b200.roi_data_layer.minibatch_mv3d import get_minibatch
+
+    g = np.load(os.path.join(golden_dir, 'kitti_feed.npz'))
+    sel = make_tree(str(tmp_path), n_frames=5, seed=3)
+    assert int(g['n']) == len(sel)
+    ours_cfg.cfg_from_end2end_yml()
+    roidb = get_training_roidb(_ours(str(tmp_path)))
+    for i, e in enumerate(roidb):
+        for key in [k for k in g.files if k.startswith('roidb%d_' % i)]:
+            name = key.split('_', 1)[1]
+            mine = e[name].toarray() if name == 'gt_overlaps' else np.asarray(e[name])
+            assert mine.dtype == g[key].dtype and np.array_equal(mine, g[key]), key
+        blobs = get_minibatch([e], 2)
+        for key in [k for k in g.files if k.startswith('blob%d_' % i)]:
+            name = key.split('_', 1)[1]
+            assert blobs[name].dtype == g[key].dtype and np.array_equal(blobs[name], g[key]), key
+    np.random.seed(3)
+    layer = RoIDataLayer(roidb, 2)
+    assert [layer.forward()['calib'][0, 3] for _ in range(9)] == g['layer_walk'].tolist()
