@@ -123,3 +123,46 @@ def test_product_package_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.\.?oracle|oracle/", txt, flags=re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_mixed_mode_format_plan_is_static_graph_analysis():
+    """Which conv outputs travel as f16e5 is decided from the graph alone (no device needed): every PAD tensor whose
+    readers are 3x3 convs (directly or through 2x2 pools) -- the trunks; bf16 hi/lo wherever a 1x1 conv reads it
+    (rpn_conv/3x3) or nobody reads the PAD rendering (conv5_3_2 feeds only the ROI pool); never while training."""
+    from mv3d_tf_b200 import kernels as K
+    from mv3d_tf_b200.networks.factory import get_network
+
+    net = get_network("MV3D_test", bv_channels=36, precise=True, mixed=True, fv=True)
+    fm = {n.name: net._pad_out_fmt(n) for n in net._program if n.kind == "conv"}
+    for s in ("", "_2", "_3"):
+        for name in ("conv1_1", "conv1_2", "conv2_2", "conv3_3", "conv4_3", "conv5_2"):
+            assert fm[name + s] == K.FMT_F16E5, name + s
+    assert fm["conv5_3"] == K.FMT_F16E5            # read by rpn_conv/3x3 (a 3x3 conv)
+    assert fm["conv5_3_2"] == fm["conv5_3_3"] == K.FMT_BF16X2
+    assert fm["rpn_conv/3x3"] == fm["rpn_cls_score"] == fm["rpn_bbox_pred"] == K.FMT_BF16X2
+    net.training = True
+    assert all(net._pad_out_fmt(n) == K.FMT_BF16X2 for n in net._program if n.kind == "conv")
+    plain = get_network("MV3D_test", bv_channels=36, precise=True)
+    assert all(plain._pad_out_fmt(n) == K.FMT_BF16X2 for n in plain._program if n.kind == "conv")
+    assert not get_network("MV3D_test", precise=False, mixed=True).mixed     # mixed is a parity mode: needs precise
+
+
+def test_gemm_dispatch_mirror():
+    """kernels.gemm_kernel_name mirrors the C dispatch (bench.py attributes GEMM time by it)."""
+    from mv3d_tf_b200 import kernels as K
+
+    old = K.PAIR_MODE
+    try:
+        K.PAIR_MODE = True
+        assert K.gemm_kernel_name(9, 512, 512, 2) == "conv3x3_pair_kernel<256,2>"
+        assert K.gemm_kernel_name(9, 64, 64, 3) == "conv3x3_pair_kernel<64,3>"
+        assert K.gemm_kernel_name(9, 64, 128, 2) == "conv3x3_pair_kernel<128,2>"
+        assert K.gemm_kernel_name(9, 64, 96, 3) == "conv3x3_reuse_kernel<128,3>"      # width does not tile a pair
+        assert K.gemm_kernel_name(1, 25088, 2048, 3, split_k=3, m=300) == "fc_swapped_pair_kernel"
+        assert K.gemm_kernel_name(1, 25088, 2048, 3, split_k=3, m=2000) == "conv_gemm_kernel<128,64,3>"
+        assert K.gemm_kernel_name(1, 32, 64, 3) == "conv_gemm_kernel<64,32,3>"
+        K.PAIR_MODE = False
+        assert K.gemm_kernel_name(9, 512, 512, 3) == "conv3x3_reuse_kernel<128,3>"
+        assert K.gemm_kernel_name(9, 512, 512, 2) == "conv3x3_reuse_kernel<128,2>"
+    finally:
+        K.PAIR_MODE = old
