@@ -166,3 +166,49 @@ def test_gemm_dispatch_mirror():
         assert K.gemm_kernel_name(9, 512, 512, 2) == "conv3x3_reuse_kernel<128,2>"
     finally:
         K.PAIR_MODE = old
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every ctypes argtypes list has the arity and the pointer / integer / float kinds of its prototype in
+    include/mv3d_b200.h (a mismatch would otherwise only surface as garbage arguments on the GPU box), and the two
+    descriptor structs have the header's field order."""
+    import ctypes as C
+    from mv3d_tf_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "mv3d_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(mv3d_[a-z0-9_]+|_nms)\s*\(([^;{}]*)\)\s*;", hdr))
+
+    def kind_of_decl(p):
+        p = p.strip()
+        if "*" in p:
+            return "ptr"
+        t = p.split()
+        base = " ".join(t[:-1]) if len(t) > 1 else t[0]
+        if "float" in base or "double" in base:
+            return "float"
+        return "int"
+
+    def kind_of_ctype(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        if t in (C.c_float, C.c_double):
+            return "float"
+        return "int"
+
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert name in protos, name
+        params = [p for p in (x.strip() for x in protos[name].replace("\n", " ").split(",")) if p and p != "void"]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        assert [kind_of_decl(p) for p in params] == [kind_of_ctype(t) for t in argtypes], name
+    for struct, cls in (("mv3d_gemm_desc", _lib.GemmDesc), ("mv3d_wgrad_desc", _lib.WgradDesc)):
+        end = re.search(r"\}\s*%s;" % struct, hdr).start()
+        body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        fields = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            for part in stmt.split(","):
+                fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+        assert fields == [f[0] for f in cls._fields_], struct
