@@ -1,67 +1,78 @@
-"""get_minibatch (lib/roi_data_layer/minibatch_mv3d.py:17-76): one roidb entry -> the blob dict the MV3D_train
-placeholders take.  Same keys, shapes and dtypes.  When the entry's `lidar_bv_path` is a raw Velodyne `.bin` (no offline
-raster on disk) the BEV blob is rasterised on the GPU and stays there (a torch CUDA tensor; Network.run takes either)."""
+"""Blob assembly for one training frame.  Interface of lib/roi_data_layer/minibatch_mv3d.py:17-76 (`get_minibatch(roidb,
+num_classes)` -> dict), written from the blob specification below rather than from the reference text:
+
+    image_data        (1, H, W, 3)  float32   BGR image minus cfg.PIXEL_MEANS
+    lidar_bv_data     (1, Hb, Wb, C) float32  BEV map: the offline `.npy` raster, or -- new here -- rasterised on the GPU
+                                              from the raw Velodyne `.bin` (then a CUDA tensor; Network.run takes either)
+    calib             (4, 12)                 P2 / P3 / R0 / Tr rows as kitti_mv3d.calib_at returns them
+    gt_boxes          (G, 4+1)  float32       image boxes | class      } rows = annotations whose class != 0,
+    gt_boxes_bv       (G, 4+1)  float32       BEV boxes | class        } in roidb order
+    gt_boxes_3d       (G, 6+1)  float32       x,y,z,l,w,h | class      }
+    gt_boxes_corners  (G, 24+1) float32       8 corners (x0..7,y0..7,z0..7) | class
+    im_info           (1, 3)    float32       [Hb, Wb, scale = 1]
+
+The reference draws (and discards) one `npr.randint` per call for its unused multi-scale option (:22-23); the draw is
+kept so that numpy's global random stream -- which the target layers sample from afterwards -- stays in step with it.
+Bit-identical blobs vs the reference run through the shim: tests/test_kitti_feed.py."""
 import numpy as np
 import numpy.random as npr
 
 from ..fast_rcnn.config import cfg
 
-_RASTER = {}
+# blob name -> (roidb field, columns before the class label)
+GT_BLOBS = {'gt_boxes': ('boxes', 4), 'gt_boxes_bv': ('boxes_bv', 4), 'gt_boxes_3d': ('boxes_3D', 6),
+            'gt_boxes_corners': ('boxes_corners', 24)}
+IMAGE_SCALE = 1            # the MV3D feed never rescales the image
+REF_RASTER = dict(res=0.1, zres=0.3, side_range=(-30., 30.), fwd_range=(0., 60.), height_range=(-2., 0.4))
+_rasterizers = {}
 
 
 def imread_bgr(path):
-    """cv2.imread(path) of minibatch_mv3d.py:32: HxWx3 uint8 in B,G,R order."""
+    """What cv2.imread returns for a colour image: (H, W, 3) uint8, channels in B,G,R order."""
     from PIL import Image
-    return np.ascontiguousarray(np.asarray(Image.open(path).convert('RGB'))[:, :, ::-1])
+    rgb = np.asarray(Image.open(path).convert('RGB'))
+    return np.ascontiguousarray(rgb[:, :, ::-1])
 
 
 def load_bev(path, raster_args=None):
+    """BEV map of one frame: `.npy` = the reference's offline raster; anything else is a Velodyne float32 (n,4) file that
+    is rasterised on the GPU (one cached BevRasterizer per grid configuration)."""
     if path.endswith('.npy'):
         return np.load(path)
     import torch
     from ..utils.read_lidar import BevRasterizer
-    args = dict(res=0.1, zres=0.3, side_range=(-30., 30.), fwd_range=(0., 60.), height_range=(-2., 0.4))
-    args.update(raster_args or {})
-    key = tuple(sorted(args.items()))
-    if key not in _RASTER:
-        _RASTER[key] = BevRasterizer(**args)
-    pts = np.fromfile(path, dtype=np.float32).reshape(-1, 4)
-    return _RASTER[key](torch.from_numpy(pts).cuda())
+    grid = dict(REF_RASTER, **(raster_args or {}))
+    key = tuple(sorted(grid.items()))
+    raster = _rasterizers.get(key)
+    if raster is None:
+        raster = _rasterizers[key] = BevRasterizer(**grid)
+    cloud = np.fromfile(path, dtype=np.float32).reshape(-1, 4)
+    return raster(torch.from_numpy(cloud).cuda())
+
+
+def _labelled_rows(entry, field, width, rows, classes, scale=None):
+    out = np.empty((rows.size, width + 1), dtype=np.float32)
+    vals = entry[field][rows, :]
+    out[:, :width] = vals if scale is None else vals * scale
+    out[:, width] = classes
+    return out
 
 
 def get_minibatch(roidb, num_classes, raster_args=None):
-    """Given a roidb (one entry: the reference is single-image), construct a minibatch sampled from it."""
-    num_images = len(roidb)
-    scales = cfg.TRAIN.get('SCALES', (600,))
-    npr.randint(0, high=len(scales), size=num_images)   # minibatch_mv3d.py:22-23: drawn and unused; keeps the RNG stream
-    assert cfg.TRAIN.BATCH_SIZE % num_images == 0, \
-        'num_images ({}) must divide BATCH_SIZE ({})'.format(num_images, cfg.TRAIN.BATCH_SIZE)
-    im_scales = [1]
-    im = imread_bgr(roidb[0]['image_path']).astype(np.float32, copy=False)
-    lidar_bv_blob = load_bev(roidb[0]['lidar_bv_path'], raster_args)
-    im -= cfg.PIXEL_MEANS          # float32 -= float64 (1,1,3): computed in float64, stored float32, as numpy does there
-    im_blob = im.reshape((1, im.shape[0], im.shape[1], im.shape[2]))
-    lidar_bv_blob = lidar_bv_blob.reshape((1, lidar_bv_blob.shape[0], lidar_bv_blob.shape[1], lidar_bv_blob.shape[2]))
-    blobs = {'image_data': im_blob, 'lidar_bv_data': lidar_bv_blob}
-    blobs['calib'] = roidb[0]['calib']
-    assert len(im_scales) == 1, "Single batch only"
-    assert len(roidb) == 1, "Single batch only"
-    gt_inds = np.where(roidb[0]['gt_classes'] != 0)[0]
-    gt_boxes = np.empty((len(gt_inds), 5), dtype=np.float32)
-    gt_boxes[:, 0:4] = roidb[0]['boxes'][gt_inds, :] * im_scales[0]
-    gt_boxes[:, 4] = roidb[0]['gt_classes'][gt_inds]
-    blobs['gt_boxes'] = gt_boxes
-    gt_boxes_bv = np.empty((len(gt_inds), 5), dtype=np.float32)
-    gt_boxes_bv[:, 0:4] = roidb[0]['boxes_bv'][gt_inds, :]
-    gt_boxes_bv[:, 4] = roidb[0]['gt_classes'][gt_inds]
-    blobs['gt_boxes_bv'] = gt_boxes_bv
-    gt_boxes_3d = np.empty((len(gt_inds), 7), dtype=np.float32)
-    gt_boxes_3d[:, 0:6] = roidb[0]['boxes_3D'][gt_inds, :]
-    gt_boxes_3d[:, 6] = roidb[0]['gt_classes'][gt_inds]
-    blobs['gt_boxes_3d'] = gt_boxes_3d
-    gt_boxes_corners = np.empty((len(gt_inds), 25), dtype=np.float32)
-    gt_boxes_corners[:, 0:24] = roidb[0]['boxes_corners'][gt_inds, :]
-    gt_boxes_corners[:, 24] = roidb[0]['gt_classes'][gt_inds]
-    blobs['gt_boxes_corners'] = gt_boxes_corners
-    blobs['im_info'] = np.array([[lidar_bv_blob.shape[1], lidar_bv_blob.shape[2], im_scales[0]]], dtype=np.float32)
+    n = len(roidb)
+    npr.randint(0, high=len(cfg.TRAIN.get('SCALES', (600,))), size=n)     # see the module docstring
+    if cfg.TRAIN.BATCH_SIZE % n != 0:
+        raise AssertionError('num_images ({}) must divide BATCH_SIZE ({})'.format(n, cfg.TRAIN.BATCH_SIZE))
+    if n != 1:
+        raise AssertionError('Single batch only')
+    entry = roidb[0]
+    image = imread_bgr(entry['image_path']).astype(np.float32, copy=False)
+    image -= cfg.PIXEL_MEANS       # float32 array, float64 means: numpy computes in float64 and stores float32
+    bev = load_bev(entry['lidar_bv_path'], raster_args)
+    blobs = {'image_data': image[None], 'lidar_bv_data': bev[None], 'calib': entry['calib']}
+    fg = np.flatnonzero(entry['gt_classes'] != 0)
+    classes = entry['gt_classes'][fg]
+    for name, (field, width) in GT_BLOBS.items():
+        blobs[name] = _labelled_rows(entry, field, width, fg, classes, IMAGE_SCALE if name == 'gt_boxes' else None)
+    blobs['im_info'] = np.array([[bev.shape[0], bev.shape[1], IMAGE_SCALE]], dtype=np.float32)
     return blobs
