@@ -115,7 +115,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg, views=3):
+def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg, views=2):
     """One frame of the reference's CPU path: the oracle port (numpy/C restatement + torch-CPU fp32 graph),
     with the per-box projection loop in the reference's own shape (transform.py:483-500)."""
     bv = orc.point_cloud_2_top(pts, **BEV)[None]
@@ -138,7 +138,7 @@ def cpu_frame(orc, net_oracle, params, pts, img, im_info, calib, cfg, views=3):
     return cls, bb
 
 
-def make_cpu_params(seed=7, views=3):
+def make_cpu_params(seed=7, views=2):
     """Same architecture, random init, built directly on the host (no GPU needed for the reference arm)."""
     import torch
 
@@ -164,7 +164,7 @@ def make_cpu_params(seed=7, views=3):
     return params
 
 
-def run_cpu_reference(steps, warmup, frames, views=3):
+def run_cpu_reference(steps, warmup, frames, views=2, params=None):
     import torch
 
     from oracle import build as ob
@@ -174,7 +174,7 @@ def run_cpu_reference(steps, warmup, frames, views=3):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = make_cpu_params(views=views)
+    params = make_cpu_params(views=views) if params is None else params
     cfg = {"TEST": dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5)}
     im_info = np.array([[701, 801, 1]], np.float32)
     t_w = time.perf_counter()
@@ -190,14 +190,16 @@ def run_cpu_reference(steps, warmup, frames, views=3):
     return steps / dt, dt / steps * 1e3, cores, steps
 
 
-CONFIG = {"workload": "configs[1]: full MV3D inference batch=1 per GPU: 120k-pt LiDAR -> BEV 701x801x36 + FV 64x512x3 "
-                      "rasters, BEV+FV+RGB(375x1242) VGG16 trunks, 3D-RPN + proposal layer (6000/300, NMS 0.7), fused "
-                      "3-view ROI pool, fc fusion head (the FV view has no reference counterpart, network.py:313-315: "
-                      "it follows this repo's written spec; --views 2 runs the reference's exact two-view network)",
-          "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective", "execution": "one CUDA graph per frame (FrameRunner: the trunks on separate captured "
-          "streams), independent batch-1 frames replayed round-robin on separate streams (FramePipeline)",
-          "l2_policy": "per-frame working set (144 MB/activation at conv1, 411 MB fc6 weights) exceeds the 126 MB L2; "
-                       "4 distinct frames rotate"}
+def make_config(views):
+    """The `config` object of the JSON line -- identical in both arms (ours / reference) for a given --views."""
+    net = ("the reference's own two-view network (BEV + RGB; lib/networks/network.py:313-315 has no front-view branch)"
+           if views == 2 else "BEV + FV (64x512x3, this repo's written spec: the reference has none) + RGB")
+    return {"workload": "configs[1]: full MV3D inference batch=1 per GPU, %s: 120k-pt LiDAR -> BEV 701x801x36 raster, "
+                        "VGG16 trunks (RGB 375x1242), 3D-RPN + proposal layer (6000/300, NMS 0.7), fused multi-view ROI "
+                        "pool, fc fusion head" % net,
+            "views": views, "frames_per_step_per_gpu": 1, "parallelism": "frames data-parallel, no collective",
+            "l2_policy": "per-frame working set (144 MB/activation at conv1, 411 MB fc6 weights) exceeds the 126 MB L2; "
+                         "4 distinct frames rotate"}
 
 
 def run_train_bench(args, rank, world, local_rank):
@@ -280,6 +282,25 @@ def run_train_bench(args, rank, world, local_rank):
                         "375x1242, 6 GT cars/frame, RPN 12000/2000 proposals, 128 sampled rois/frame" % B}
 
 
+def cpu_train_step_ms(frames, params, views_unused=2):
+    """The reference's train step on the host cores (oracle port: torch-CPU fp32 autograd + numpy/C target layers),
+    ONE frame timed; a configs[2] step is two such frames back to back (the reference is strictly batch 1)."""
+    import torch
+    from oracle import mv3d_oracle as orc
+    from oracle import net_oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    pts, img = frames[0]
+    bv = orc.point_cloud_2_top(pts, **BEV)[None]
+    gt = orc.synth_gt(6, seed=500, geom=orc.CFG_GEOMETRY)
+    np.random.seed(3)
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        net_oracle.train_forward_backward(bv, img, np.array([[701, 801, 1]], np.float32), orc.KITTI_CALIB, *gt, params,
+                                          geom=orc.CFG_GEOMETRY)
+    return (time.perf_counter() - t0) * 1e3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -297,32 +318,39 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the train_step leg of the default run")
     ap.add_argument("--no-precise-leg", action="store_true",
                     help="mixed mode only: skip the extra device-resident timing of the bf16x3-everywhere network")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0] / configs[4] extras")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--in-flight", type=int, default=2, help="independent batch-1 frames in flight per GPU (streams)")
-    ap.add_argument("--views", type=int, default=3, choices=[2, 3],
-                    help="3: BEV+FV+RGB (BASELINE configs[1]); 2: the reference's own BEV+RGB network")
+    ap.add_argument("--views", type=int, default=2, choices=[2, 3],
+                    help="2 (default): the reference's own BEV+RGB network (lib/networks/network.py:313-315 has no FV "
+                         "branch) -- the anchored comparison; 3: BEV+FV+RGB.  The other view count is reported beside it")
+    ap.add_argument("--no-other-views", action="store_true", help="skip the extra leg with the other view count")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    warmup = max(args.warmup, 3)
     n_frames = 4
     frames = [synth_frame(i + 16 * rank) for i in range(n_frames)]
+    other_views = 5 - args.views
 
     if args.impl == "reference":
         if rank != 0:
             return
-        fps, ms, cores, n_done = run_cpu_reference(args.steps, max(1, min(args.warmup, 1)), frames, args.views)
+        fps, ms, cores, n_done = run_cpu_reference(args.steps, warmup, frames, args.views)
         line = {"impl": "reference", "metric": "MV3D inference frames/sec", "value": fps, "unit": "frames/s",
-                "n_gpus": args.gpus, "steps": n_done, "warmup": max(1, min(args.warmup, 1)), "ms_per_step": ms,
+                "n_gpus": args.gpus, "steps": n_done, "warmup": warmup, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(CONFIG, mode="f32", views=args.views),
+                "config": make_config(args.views),
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d whole frames, 1 per step (of %d requested; bounded to ~150 s; numpy/C "
                                            "oracle port of the reference's host layers incl. its per-box projection "
-                                           "loop; conv/fc via torch-CPU fp32 because TensorFlow 1.0 is not installable)"
-                                           % (n_done, args.steps)},
+                                           "loop; conv/fc via torch-CPU fp32 because TensorFlow 1.0 is not installable); "
+                                           "one CPU process whatever --gpus says" % (n_done, args.steps)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if not args.no_other_views:
+            f2, m2, _, n2 = run_cpu_reference(2, 1, frames, other_views)
+            line["views%d" % other_views] = {"value": f2, "unit": "frames/s", "steps": n2, "config": make_config(other_views)}
         print(json.dumps(line))
         return
 
@@ -335,7 +363,7 @@ def main():
     from mv3d_tf_b200 import _lib, kernels
     from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
     from mv3d_tf_b200.networks.factory import get_network
-    from mv3d_tf_b200.utils.read_lidar import BevRasterizer
+    from mv3d_tf_b200.utils.read_lidar import BevRasterizer, FvRasterizer
     from mv3d_tf_b200.utils.transform import CFG_GEOMETRY
     from oracle import mv3d_oracle as orc  # KITTI_CALIB constants + synthetic generators only
 
@@ -353,85 +381,108 @@ def main():
 
     cfg_from_end2end_yml()
     cfg.USE_GPU_NMS = False  # reproduce the DEVICE=cpu rule (cpu_nms `>=`), the parity target
-    net = get_network("MV3D_test", bv_channels=36, precise=(args.mode != "fast"), mixed=(args.mode == "mixed"),
-                      geometry=CFG_GEOMETRY, fv=(args.views == 3))
-    net.init_weights(seed=7, mode="he")
-    raster = BevRasterizer(**BEV)
     im_info = np.array([[701, 801, 1]], np.float32)
     calib = orc.KITTI_CALIB
-    fetch = [net.get_output("cls_prob"), net.get_output("bbox_pred"), net.get_output("roi_data_bv")]
     stream = torch.cuda.current_stream()
-
     dev_frames = [(torch.from_numpy(p).cuda(), torch.from_numpy(i).cuda()) for p, i in frames]
     pin_frames = [(torch.from_numpy(p).pin_memory(), torch.from_numpy(i).pin_memory()) for p, i in frames]
-
-    precise = args.mode != "fast"
+    depth = max(1, args.in_flight)
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
 
     from mv3d_tf_b200.fast_rcnn.test_mv import FramePipeline, FrameRunner
-
-    # The product call: each frame is one captured CUDA graph (FrameRunner); `--in-flight` of them are replayed
-    # round-robin on separate streams (FramePipeline) so that one frame's serial tail overlaps the next frame's trunks.
-    def make_runner():
-        r = FrameRunner(net, BevRasterizer(**BEV), N_POINTS, IMG_HW, im_info, fetch=("cls_prob", "bbox_pred", "roi_data_bv"),
-                        use_graph=not args.no_graph)
-        r.load_device(dev_frames[0][0], dev_frames[0][1], calib)
-        return r
-    _lib.reset_launch_count()
-    runner = make_runner().capture()
-    launches_per_frame = _lib.launch_count() // (3 if not args.no_graph else 2)
-    depth = max(1, args.in_flight)
-    pipe = FramePipeline(make_runner, depth=depth)
-
-    def step_device(i):
-        pts, img = dev_frames[i % n_frames]
-        if pipe.head - pipe.tail >= depth:
-            pipe.tail += 1                      # device-resident leg: nothing to collect on the host
-        pipe.submit(pts, img, None, device_inputs=True)   # D2D into the graph's static inputs (4 distinct frames rotate)
-
-    def step_e2e(i):
-        pts_h, img_h = pin_frames[i % n_frames]
-        if pipe.head - pipe.tail >= depth:
-            pipe.collect()                      # the oldest frame's detections are on the host (pinned) here
-        pipe.submit(pts_h, img_h, calib)        # pinned host in -> H2D, graph, D2H -> pinned host out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for i in range(steps):
-            fn(i)
-        while pipe.tail < pipe.head and fn is step_e2e:
-            pipe.collect()                      # the last frames' detections reach the host inside the timed region
-        pipe.drain()                            # device-side join of the per-frame streams
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
+    class Leg:
+        """One network (views, mode) behind the product call: each frame is one captured CUDA graph (FrameRunner);
+        `--in-flight` of them are replayed round-robin on separate streams (FramePipeline) so that one frame's serial
+        tail overlaps the next frame's trunks."""
 
-    for i in range(warmup):
-        step_device(i)
+        def __init__(self, views, mode):
+            self.views, self.mode = views, mode
+            self.net = get_network("MV3D_test", bv_channels=36, precise=(mode != "fast"), mixed=(mode == "mixed"),
+                                   geometry=CFG_GEOMETRY, fv=(views == 3))
+            self.net.init_weights(seed=7, mode="he")
+            _lib.reset_launch_count()
+            self.runner = self.make_runner().capture()
+            self.launches_per_frame = _lib.launch_count() // (3 if not args.no_graph else 2)
+            self.pipe = FramePipeline(self.make_runner, depth=depth)
+
+        def make_runner(self):
+            r = FrameRunner(self.net, BevRasterizer(**BEV), N_POINTS, IMG_HW, im_info,
+                            fetch=("cls_prob", "bbox_pred", "roi_data_bv"), use_graph=not args.no_graph)
+            r.load_device(dev_frames[0][0], dev_frames[0][1], calib)
+            return r
+
+        def step_device(self, i):
+            pts, img = dev_frames[i % n_frames]
+            pipe = self.pipe
+            if pipe.head - pipe.tail >= depth:
+                pipe.tail += 1                      # device-resident leg: nothing to collect on the host
+            pipe.submit(pts, img, None, device_inputs=True)   # D2D into the graph's static inputs (4 distinct frames rotate)
+
+        def step_e2e(self, i):
+            pts_h, img_h = pin_frames[i % n_frames]
+            pipe = self.pipe
+            if pipe.head - pipe.tail >= depth:
+                pipe.collect()                      # the oldest frame's detections are on the host (pinned) here
+            pipe.submit(pts_h, img_h, calib)        # pinned host in -> H2D, graph, D2H -> pinned host out
+
+        def timed(self, fn, steps):
+            pipe = self.pipe
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for i in range(steps):
+                fn(i)
+            while pipe.tail < pipe.head and fn == self.step_e2e:
+                pipe.collect()                      # the last frames' detections reach the host inside the timed region
+            pipe.drain()                            # device-side join of the per-frame streams
+            e1.record(stream)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            t = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall * 1e3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0]), float(t[1])
+
+        def measure(self, steps, e2e=True):
+            for i in range(warmup):
+                self.step_device(i)
+            ms_dev, _ = self.timed(self.step_device, steps)
+            out = {"value": world * steps / (ms_dev * 1e-3), "ms_per_step": ms_dev / steps, "steps": steps}
+            if e2e:
+                for i in range(warmup):
+                    self.step_e2e(i)
+                _, ms_wall = self.timed(self.step_e2e, steps)
+                out["e2e"] = world * steps / (ms_wall * 1e-3)
+            return out
+
+        def parity_outputs(self):
+            """Frame 0 through the same network, eagerly, with the intermediate tensors fetched (for the parity leg)."""
+            from oracle import parity
+            fvr = FvRasterizer(self.net.fv_geometry) if self.views == 3 else None
+            return parity.gpu_frame_outputs(self.net, BevRasterizer(**BEV), dev_frames[0][0], frames[0][1], im_info, calib, fvr)
+
+        def close(self):
+            self.pipe.drain(host_sync=True)
+            del self.pipe, self.runner, self.net
+            torch.cuda.empty_cache()
+
+    leg = Leg(args.views, args.mode)
     with ClockSampler(local_rank) as clk:
-        ms_dev, _ = timed(step_device, args.steps)
-        launches = launches_per_frame * args.steps
-        for i in range(warmup):
-            step_e2e(i)
-        _, ms_e2e_wall = timed(step_e2e, args.steps)
-    value = world * args.steps / (ms_dev * 1e-3)
-    e2e = world * args.steps / (ms_e2e_wall * 1e-3)
+        res = leg.measure(args.steps)
+    value, e2e = res["value"], res["e2e"]
+    launches = leg.launches_per_frame * args.steps
     h2d = sum(int(t.numel() * t.element_size()) for t in pin_frames[0])
-    d2h = sum(int(t.numel() * t.element_size()) for t in runner.host)
+    d2h = sum(int(t.numel() * t.element_size()) for t in leg.runner.host)
 
     # ---- roofline of the dominant kernel (conv/fc tcgen05 GEMM): per-launch CUDA events on the launch stream
+    net, runner = leg.net, leg.runner
     kernels.GEMM_EVENTS = []
     net.use_side_stream = False   # serialise the two trunks so that every event pair brackets exactly one kernel
     for i in range(3):
@@ -455,6 +506,7 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_burst = float(peaks.get("bf16_tflops", 1645.0))
     all_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     # the dominant kernel = the template instantiation with the largest share of the GEMM time
     dom = max(per_kernel.items(), key=lambda kv: kv[1][1])
@@ -472,61 +524,136 @@ def main():
     mult = {"precise": 3, "mixed": 2, "fast": 1}[args.mode] if "<" not in dom_name else \
         {"3": 3, "2": 2, "1": 1}.get(dom_name.rstrip(">").split(",")[-1], 1)
     roofline = {"bound": "tensor", "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
-                "traffic": traffic,
+                "frac_of_burst_peak": dom_tf / peak_burst, "traffic": traffic,
                 "kernel": "%s: %d launches/frame, %.3f ms/frame, %.1f%% of the GEMM time; algorithmic FLOPs counted 1x "
                           "(the %s mode issues %dx the MMAs: %.0f TFLOP/s issued)"
                           % (dom_name, dom_n // 3, dom_ms / 3.0, 100.0 * dom_ms / (gemm_ms * 3.0), args.mode, mult, dom_tf * mult),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (the kernels are timed inside a long step); "
+                                "frac_of_burst_peak uses bf16_tflops") if peaks else "fallback 1.4 PFLOP/s",
                 "all_gemm_kernels": {"launches_per_frame": n_gemm, "ms_per_frame": gemm_ms, "algorithmic_gflop_per_frame": flops / 1e9,
                                      "achieved": all_tf, "frac": all_tf / peak_tf,
                                      "by_kernel": {k: {"launches": v[0] // 3, "ms": v[1] / 3.0,
                                                        "tflops_1x": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
                                                    for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}},
-                "gemm_share_of_step": gemm_ms / (ms_dev / args.steps) if ms_dev > 0 else None}
+                "gemm_share_of_step": gemm_ms / res["ms_per_step"] if res["ms_per_step"] > 0 else None}
 
     line = {"metric": "MV3D inference frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"precise": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)",
                       "mixed": "f16+2xe5m2 in the 3x3 convs (fp16 pass + one e5m2 pass carrying both correction terms = 2 "
                                "pass-equivalents, fp32 accumulate), bf16x3 in 1x1/fc layers",
                       "fast": "bf16"}[args.mode],
-            "data": "synthetic", "config": dict(CONFIG, mode=args.mode, views=args.views, frames_in_flight=depth),
+            "data": "synthetic", "config": make_config(args.views),
+            "impl_config": {"mode": args.mode, "frames_in_flight": depth,
+                            "execution": "one CUDA graph per frame (FrameRunner: the trunks on separate captured streams), "
+                                         "independent batch-1 frames replayed round-robin on separate streams (FramePipeline)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline}
 
+    # ---- parity, measured in THIS run: frame 0 of this network (and of the bf16x3 network below) against the CPU oracle
+    # on the same weights.  GPU side here; the oracle runs in the cpu_baseline leg at the end.
+    parity_gpu, cpu_params = {}, None
+    if want_cpu:
+        try:
+            parity_gpu[args.mode] = leg.parity_outputs()
+            cpu_params = {k: {kk: vv.cpu().numpy() for kk, vv in v.items()} for k, v in net.params.items()}
+        except Exception as e:
+            line["parity"] = {"error": repr(e)[:300]}
+    leg.close()
+    del net, runner
+
+    if not args.no_other_views:
+        # the other view count through the same pipeline, beside the headline (north_star names three views; the
+        # reference has two).  Same clocks caveat: shorter run.
+        try:
+            leg = Leg(other_views, args.mode)
+            n_alt = min(args.steps, 100)
+            r2 = leg.measure(n_alt)
+            line["views%d" % other_views] = {"value": r2["value"], "unit": "frames/s", "steps": n_alt,
+                                             "e2e": {"value": r2["e2e"], "unit": "frames/s"}, "ms_per_step": r2["ms_per_step"],
+                                             "config": make_config(other_views)}
+            leg.close()
+        except Exception as e:
+            line["views%d" % other_views] = {"error": repr(e)[:300]}
     if args.mode == "mixed" and not args.no_precise_leg:
         # The same frames through the bf16 hi/lo 3-pass network (every GEMM at ~2^-17 per product), reported beside the
         # headline so that the cost of the tighter arithmetic is on record in the same run.
         try:
-            pipe.drain()
-            del pipe, runner
-            torch.cuda.empty_cache()
-            net = get_network("MV3D_test", bv_channels=36, precise=True, mixed=False, geometry=CFG_GEOMETRY,
-                              fv=(args.views == 3))
-            net.init_weights(seed=7, mode="he")
-            pipe = FramePipeline(make_runner, depth=depth)
+            leg = Leg(args.views, "precise")
             n_alt = min(args.steps, 100)
-            for i in range(warmup):
-                step_device(i)
-            ms_alt, _ = timed(step_device, n_alt)
-            line["precise_mode"] = {"value": world * n_alt / (ms_alt * 1e-3), "unit": "frames/s", "steps": n_alt,
+            r3 = leg.measure(n_alt, e2e=False)
+            line["precise_mode"] = {"value": r3["value"], "unit": "frames/s", "steps": n_alt,
                                     "dtype": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate) in every GEMM",
-                                    "note": "device-resident inputs, same pipeline; conv5_3 vs the fp32 CPU oracle: "
-                                            "9e-5 (mixed: 1.1e-4; contract 1e-3)"}
+                                    "note": "device-resident inputs, same pipeline"}
+            if want_cpu:
+                parity_gpu["precise"] = leg.parity_outputs()
+            leg.close()
         except Exception as e:
             line["precise_mode"] = {"error": repr(e)[:300]}
     if not args.no_train:
-        del net
-        torch.cuda.empty_cache()
         try:
             line["train_step"] = run_train_bench(args, rank, world, local_rank)
         except Exception as e:  # the inference headline must survive a failure of the secondary leg
             line["train_step"] = {"error": repr(e)[:300]}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, ms, cores, _ = run_cpu_reference(2, 1, frames, args.views)
+    if not args.no_extras:
+        # configs[4] (raster sweep, every rank rasterises its own clouds: N GPUs = N x the frames) and configs[0]
+        # (BEV-only 3D-RPN forward: the CPU port beside the device layer) in the driver-run line
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import raster_sweep
+            rows, shape, peak_hbm = raster_sweep.sweep(iters=20, check=(world == 1), rank=rank, world=world)
+            line["raster_sweep"] = {"workload": "configs[4]: LiDAR -> BEV 701x801x36 float32 raster, CUDA-graph replay of 20 frames, "
+                                                "max over ranks; GB/s = (16 B/point + 4 B/output element) / time",
+                                    "n_gpus": world, "hbm_peak_gbs": peak_hbm, "checked_bit_exact_vs_oracle": world == 1,
+                                    "rows": rows}
+        except Exception as e:
+            line["raster_sweep"] = {"error": repr(e)[:300]}
+        if want_cpu:
+            try:
+                import rpn_config0
+                rows = rpn_config0.run(reps=1, gpu_iters=10)
+                line["config0_rpn"] = {"workload": "configs[0]: BEV-only 3D-RPN forward (proposal_layer_3d: anchors + "
+                                                   "bbox_transform + projection + filters + sort + NMS), CPU port on 1 host "
+                                                   "thread (numpy + C NMS, per-box projection loop kept) vs the device layer",
+                                       "rows": [dict(zip(("grid", "cfg", "pre_nms", "post_nms", "proposals", "cpu_ms", "b200_ms",
+                                                          "survivors_identical"), r)) for r in rows]}
+            except Exception as e:
+                line["config0_rpn"] = {"error": repr(e)[:300]}
+    if want_cpu:
+        # the reference's CPU path on this box's host cores -- WITH THE GPU NETWORK'S WEIGHTS, so that the same oracle
+        # frames also yield the parity numbers of this run
+        params = cpu_params if cpu_params is not None else make_cpu_params(views=args.views)
+        fps, ms, cores, _ = run_cpu_reference(2, 1, frames, args.views, params=params)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "2 whole frames after 1 warm-up (oracle port; conv/fc torch-CPU fp32)"}
+        if "train_step" in line and "ms" in line.get("train_step", {}):
+            try:
+                one = cpu_train_step_ms(frames, params)
+                line["train_step"]["cpu_baseline"] = {
+                    "value": 2.0 * one, "unit": "ms per 2-frame step", "cores": cores, "kind": "port",
+                    "sample": "ONE frame fwd+bwd timed (%.0f ms) x 2: the reference trains strictly batch 1, a configs[2] "
+                              "step is two sequential CPU steps (torch-CPU fp32 autograd + numpy/C target layers; Adam "
+                              "not included)" % one}
+            except Exception as e:
+                line["train_step"]["cpu_baseline"] = {"error": repr(e)[:200]}
+        if parity_gpu and cpu_params is not None:
+            try:
+                from oracle import parity
+                bv0 = orc.point_cloud_2_top(frames[0][0], **BEV)[None]
+                fv0 = orc.point_cloud_2_front(frames[0][0])[None] if args.views == 3 else None
+                ocfg = {"TEST": dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=5)}
+                par = {"metric": "max|gpu - oracle| / max|oracle| per tensor (``_abs``: absolute); frame 0, %d views, same "
+                                 "weights; ``_tf``: teacher-forced on the GPU's own conv5 maps and rois" % args.views,
+                       "tolerance": parity.FLOAT_TOL}
+                for mode, got in parity_gpu.items():
+                    errs, exact, prop = parity.oracle_frame_errors(got, cpu_params, bv0, frames[0][1], im_info, calib,
+                                                                   orc.CFG_GEOMETRY, cfg=ocfg, fv=fv0)
+                    par[mode] = {"errors": errs, "exact": exact, "proposals": prop,
+                                 "within_tolerance": bool(all(v < parity.FLOAT_TOL for v in errs.values()) and all(exact.values()))}
+                line["parity"] = par
+            except Exception as e:
+                line["parity"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

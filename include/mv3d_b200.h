@@ -197,6 +197,10 @@ int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
 /* A/B switch for the CTA-pair (tcgen05 cta_group::2, 256 x N tiles) form of the tap-reuse 3x3 conv kernel: on (default,
  * also MV3D_PAIR=1) or off (single-CTA 128 x N tiles).  Same results either way; returns the previous setting. */
 int mv3d_gemm_set_pair_mode(int on);
+/* Measurement only: a device buffer of 8 int64 that CTA pair 0 of every following 3x3 pair-kernel launch fills with
+ * clock64() at its phase boundaries (start, set-up done, first operands landed, last MMA issued, last accumulator
+ * complete, epilogue done, both CTAs done, exit); NULL switches it off.  tools/gemm_phases.py prints the breakdown. */
+int mv3d_gemm_set_stamps(void* d_stamps8);
 
 /* MV3D_FMT_F16E5 renderings of the layout helpers (fmt = MV3D_FMT_BF16X2 forwards to the plain functions; same
  * arguments otherwise).  d_hi is the 16-bit plane, d_lo the byte plane of equal pitch; c_pad / cin_pad % 64 == 0. */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "mv3d_roi_pool_multiview": (c_int, [C.POINTER(RoiView), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mv3d_conv_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "mv3d_gemm_set_pair_mode": (c_int, [c_int]),
+    "mv3d_gemm_set_stamps": (c_int, [c_void_p]),
     "mv3d_pack_weights_fmt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mv3d_pad_nhwc_fmt": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "mv3d_unpad_nhwc_fmt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

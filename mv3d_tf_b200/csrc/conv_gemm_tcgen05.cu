@@ -55,7 +55,12 @@ struct GemmParams {
     int dbg_flags;    // MV3D_GEMM_DBG (measurement only, results are garbage; pair kernel): 1 = the producer stops issuing TMA
                       // loads after the first lap of each ring (pure MMA rate on stale shared memory), 4 = the epilogue
                       // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
+    long long* stamps;  // measurement only (mv3d_gemm_set_stamps): clock64 of pair 0's phases, see conv3x3_pair_kernel
 };
+
+__device__ __forceinline__ void stamp(const GemmParams& prm, int slot) {
+    if (prm.stamps != nullptr && blockIdx.x == 0) prm.stamps[slot] = clock64();
+}
 
 template <int BN, int KC, int PASSES>
 struct GemmCfg {
@@ -661,6 +666,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) stamp(prm, 0);   // kernel start
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -690,6 +696,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int tiles_n = prm.tiles_n, n_work = prm.n_work;
     const int n_groups = prm.k_chunks * 3;
     const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (threadIdx.x == 0) stamp(prm, 1);   // set-up done (barriers, cluster syncs, TMEM)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -744,6 +751,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 for (int g = 0; g < n_groups; ++g, ++ia) {
                     const int ea = ia % Cfg::kNA;
                     mbar_wait(&a_full[ea], (ia / Cfg::kNA) & 1);
+                    if (ia == 0 && lane == 0) stamp(prm, 2);   // first activation box landed
                     // descriptor low words: base of this A entry, advanced by whole rows (kw) and along K (k) with adds
                     const uint32_t da_base = kmajor_desc_lo(smem_u32(a_ring + ea * Cfg::kAEntry));
                     for (int kw = 0; kw < 3; ++kw, ++iw) {
@@ -772,6 +780,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     }
                 }
             }
+            if (lane == 0) stamp(prm, 3);   // last MMA issued
         }
     } else {
         const int q = warp & 3;
@@ -779,16 +788,23 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         for (int w = pair_id; w < n_work; w += n_pairs, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = (w / tiles_n) * (2 * kBM) + (int)rank * kBM;
+            if (w + n_pairs >= n_work && warp == 2 && lane == 0 && prm.stamps != nullptr && blockIdx.x == 0) {
+                mbar_wait(&tmem_full[tl & 1], (tl >> 1) & 1);
+                stamp(prm, 4);   // last accumulator complete (MMAs retired)
+            }
             epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
         }
+        if (warp == 2 && lane == 0) stamp(prm, 5);   // this warp's epilogue done
     }
     tc_fence_before();
     cluster_sync_all();  // the leader's MMAs read the peer's shared memory / write its TMEM until the last commit
+    if (threadIdx.x == 0) stamp(prm, 6);   // all warps of both CTAs done
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     }
     cluster_sync_all();
+    if (threadIdx.x == 0) stamp(prm, 7);   // exit
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -971,6 +987,7 @@ static int gemm_dbg_flags() {   // MV3D_GEMM_DBG, see GemmParams::dbg_flags (8 =
     if (dbg < 0) { const char* e = getenv("MV3D_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     return dbg;
 }
+static long long* g_stamps = nullptr;   // mv3d_gemm_set_stamps
 static int g_pair_mode = -1;
 static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B comparisons); default on
     if (g_pair_mode < 0) {
@@ -1011,6 +1028,7 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
+    p.stamps = g_stamps;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1118,6 +1136,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
+    p.stamps = nullptr;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1169,6 +1188,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.addend = d->d_addend_f32; p.ld_addend = d->ld_addend;
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
+    p.stamps = nullptr;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
@@ -1213,6 +1233,14 @@ extern "C" __attribute__((visibility("default"))) int mv3d_gemm_set_pair_mode(in
     const int prev = mv3d::pair_mode();
     mv3d::g_pair_mode = on ? 1 : 0;
     return prev;
+}
+
+// Measurement only: device buffer of 8 int64 that pair 0 of every conv3x3_pair_kernel launch fills with clock64() at its
+// phase boundaries (0 start, 1 set-up done, 2 first operands landed, 3 last MMA issued, 4 last accumulator complete,
+// 5 epilogue done, 6 both CTAs done, 7 exit); nullptr switches it off.  tools/gemm_phases.py prints the breakdown.
+extern "C" __attribute__((visibility("default"))) int mv3d_gemm_set_stamps(void* d_stamps) {
+    mv3d::g_stamps = static_cast<long long*>(d_stamps);
+    return MV3D_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_gemm_desc* d, void* stream) {

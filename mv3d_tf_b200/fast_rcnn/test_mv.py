@@ -90,7 +90,8 @@ class FrameRunner:
         return self.outs
 
     def load_device(self, pts: torch.Tensor, img: torch.Tensor, calib=None):
-        """Device-resident inputs -> static buffers (D2D copies on the current stream)."""
+        """Inputs (device tensors, or pinned host tensors) -> static buffers, asynchronously on the current stream: the
+        caller's buffers must stay untouched until the frame's results were collected / the stream synchronised."""
         n = pts.shape[0]
         assert n <= self.max_points
         self.pts[:n].copy_(pts[:, :4], non_blocking=True)
@@ -158,10 +159,16 @@ class FramePipeline:
         r = self.runners[k]
         return dict(zip(r.fetch_names + ["num_rois"], r.host))
 
-    def drain(self):
-        """Make the current stream wait for everything in flight (device-side join, no host sync)."""
+    def drain(self, host_sync=False):
+        """Make the current stream wait for everything in flight (device-side join).  With `host_sync` (or whenever a
+        frame's results were not collected) the per-slot events are also waited for on the host, because the next
+        submit() rewrites that slot's pinned calib / output buffers while its async copies could still be running."""
         for st in self.streams:
             torch.cuda.current_stream().wait_stream(st)
+        if host_sync or self.tail < self.head:
+            for ev in self.done:
+                if ev is not None:
+                    ev.synchronize()
         self.tail = self.head
 
 

@@ -46,6 +46,9 @@ class SolverWrapper(object):
         self.exchange = FlatGradExchange(process_group) if process_group is not None else None
         self.step = 0
         net = self.net
+        if process_group is not None:   # data-parallel ranks must not draw identical dropout masks
+            import torch.distributed as dist
+            net.dropout_seed = (dist.get_rank(process_group) + 1) << 32
         net.training = True
         if not net.params:
             net.init_weights()
@@ -53,6 +56,7 @@ class SolverWrapper(object):
             net.load(pretrained_model, None, None, True)
         self._flatten_parameters()
         self._dpacked: Dict[str, K.PackedWeight] = {}
+        net._on_weights_changed.append(self._dpacked.clear)   # Network.load on a live solver (resume)
         self.loss = torch.zeros(4, dtype=torch.float32, device=net.device)  # rpn_cls, rpn_box, cls, box
         self.last_grad_events = None
 
@@ -286,10 +290,11 @@ class SolverWrapper(object):
             grads[src] = gsrc
 
     # ------------------------------------------------------------------ reference-shaped loop
-    def train_model(self, sess=None, max_iters=10000, data=None, display=10):
+    def train_model(self, sess=None, max_iters=10000, data=None, display=None):
         """train_mv.py:87-219: loop over blobs, one Adam step each, periodic loss print + snapshot."""
         from .config import cfg
         data = self.roidb if data is None else data
+        display = int(cfg.TRAIN.DISPLAY) if display is None else display    # train_mv.py:197
         if isinstance(data, list) and data and isinstance(data[0], dict) and 'lidar_bv_path' in data[0]:
             data = get_data_layer(data, self.imdb.num_classes if self.imdb is not None else 2)   # train_mv.py:154
         it = iter(data)

@@ -86,6 +86,7 @@ class Network(object):
         self.params: Dict[str, Dict[str, torch.Tensor]] = {}
         self.param_specs: Dict[str, dict] = {}
         self._packed: Dict[str, K.PackedWeight] = {}
+        self._on_weights_changed: List[Callable] = []   # e.g. the solver's backward-data operand cache
         self._program: List[Node] = []
         self._proposal_layers: Dict[tuple, ProposalLayer3D] = {}
         self._anchor_target_layers: Dict[tuple, AnchorTargetLayer] = {}
@@ -167,8 +168,12 @@ class Network(object):
 
     def load(self, data_path, session=None, saver=None, ignore_missing=False):
         """`.npy` dict {layer: {'weights': HWIO / (in,out), 'biases'}} (network.py:45-64).  session/saver are
-        accepted for signature compatibility and unused."""
+        accepted for signature compatibility and unused.
+        A parameter that already exists is overwritten IN PLACE: under a live SolverWrapper the parameters are views
+        into its flat buffer (Adam updates that buffer), and fc-after-roi_pool weights live there with their rows in the
+        kernel-native (H,W,C) order (`native_fc_layout`), so the file's (C,H,W) rows are permuted on the way in."""
         data_dict = np.load(data_path, allow_pickle=True, encoding='latin1').item()
+        chw = {n.name: n.attrs['flatten_chw'] for n in self._program if n.kind == 'fc' and 'flatten_chw' in n.attrs}
         for key in data_dict:
             if key not in self.param_specs:
                 if not ignore_missing:
@@ -177,13 +182,22 @@ class Network(object):
             tgt = self.params.setdefault(key, {})
             for subkey, arr in data_dict[key].items():
                 t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
-                want = self.param_specs[key]['shape'] if subkey == 'weights' else (self.param_specs[key]['shape'][-1],)
+                shape = self.param_specs[key]['shape']
+                want = shape if subkey == 'weights' else (shape[-1],)
                 if tuple(t.shape) != tuple(want):
                     if not ignore_missing:
                         raise ValueError('shape mismatch for %s/%s' % (key, subkey))
                     continue
-                tgt[subkey] = t
+                if subkey == 'weights' and self.native_fc_layout and key in chw:
+                    cc, ph, pw = chw[key]
+                    t = t.view(cc, ph * pw, shape[-1]).permute(1, 0, 2).reshape(shape)
+                if subkey in tgt and tgt[subkey].shape == t.shape:
+                    tgt[subkey].copy_(t)
+                else:
+                    tgt[subkey] = t.contiguous()
         self._packed.clear()
+        for hook in self._on_weights_changed:
+            hook()
 
     def _weight(self, name, transform=None, fmt=K.FMT_BF16X2) -> K.PackedWeight:
         key = name if fmt == K.FMT_BF16X2 else name + '/f16e5'

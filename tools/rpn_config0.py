@@ -16,8 +16,8 @@ ob.build()
 from oracle import mv3d_oracle as orc  # noqa: E402
 
 
-def main():
-    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+def run(reps=2, gpu_iters=20, grids=("REF", "CFG"), keys=("TEST", "TRAIN")):
+    """-> list of rows (grid, cfg key, pre, post, proposals, CPU ms, B200 ms, identical)."""
     import torch
     from mv3d_tf_b200.fast_rcnn.config import cfg, cfg_from_end2end_yml
     from mv3d_tf_b200.rpn_msr.proposal_layer_tf import ProposalLayer3D
@@ -29,8 +29,10 @@ def main():
     rows = []
     for (hf, wf), im_info, pg, og, tag in (((75, 75), (601, 601, 1), REF_GEOMETRY, orc.REF_GEOMETRY, "REF 601x601 (N=22500)"),
                                             ((87, 100), (701, 801, 1), CFG_GEOMETRY, orc.CFG_GEOMETRY, "CFG 701x801 (N=34800)")):
+        if tag[:3] not in grids:
+            continue
         prob, deltas = orc.synth_rpn_outputs(hf, wf, seed=77)
-        for key in ("TEST", "TRAIN"):
+        for key in keys:
             c = cfg[key]
             ocfg = {key: dict(RPN_PRE_NMS_TOP_N=c.RPN_PRE_NMS_TOP_N, RPN_POST_NMS_TOP_N=c.RPN_POST_NMS_TOP_N,
                               RPN_NMS_THRESH=c.RPN_NMS_THRESH, RPN_MIN_SIZE=c.RPN_MIN_SIZE)}
@@ -48,7 +50,7 @@ def main():
                 for _ in range(3):
                     out = layer(p, d, orc.KITTI_CALIB)
                 torch.cuda.synchronize()
-                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(gpu_iters)]
                 for a, b in ev:
                     a.record()
                     out = layer(p, d, orc.KITTI_CALIB)
@@ -59,6 +61,11 @@ def main():
                 same = "yes" if (n == bv.shape[0] and np.array_equal(out["bv"][:n].cpu().numpy(), bv)
                                  and np.array_equal(out["img"][:n].cpu().numpy(), img)) else "NO"
             rows.append((tag, key, c.RPN_PRE_NMS_TOP_N, c.RPN_POST_NMS_TOP_N, bv.shape[0], cpu_ms, gpu_ms, same))
+    return rows
+
+
+def main():
+    rows = run(int(sys.argv[1]) if len(sys.argv) > 1 else 2)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     path = os.path.join(ROOT, "gpurun_out", "config0_rpn.md")
     with open(path, "w") as f:
