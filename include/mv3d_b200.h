@@ -111,6 +111,8 @@ typedef struct {
     float batch_index;
     const float* d_proj; /* optional DEVICE copy of the 12 projection floats; when set it overrides h_proj (which may
                             then be NULL) so that a captured CUDA graph can be replayed with a per-frame calib */
+    int ld_prob, ld_deltas; /* floats between consecutive feature-map cells of d_prob / d_deltas; 0 = dense (2A / 6A).
+                               Lets both be column ranges of one fused (Hf*Wf, 8A) head output */
 } mv3d_proposal_params;
 
 size_t mv3d_proposal_workspace_bytes(const mv3d_proposal_params* p);
@@ -139,18 +141,42 @@ int mv3d_roi_pool_backward(const float* d_top_diff, float spatial_scale, int bat
                            const float* d_bottom_rois, float* d_bottom_diff, const int* d_argmax_data,
                            void* stream);
 
+/* where a view's rectangles come from in mv3d_roi_pool_fused */
+#define MV3D_ROI_GIVEN 0 /* d_rois (R,5), as the reference op receives them */
+#define MV3D_ROI_BEV 1   /* projected in the kernel from d_rois_3d: lidar_3d_to_bv + clip_boxes (transform.py:113-142) */
+#define MV3D_ROI_IMG 2   /* 8 corners -> image box (transform.py:290-315,483-500), int32-truncated */
+#define MV3D_ROI_FV 3    /* front-view box (this repo's specification; the reference has no FV branch) */
 typedef struct {
     const float* d_data;  /* (B,H,W,C) float32 NHWC */
-    const float* d_rois;  /* (R,5) */
+    const float* d_rois;  /* (R,5); may be NULL when source != MV3D_ROI_GIVEN */
     int height, width;
     float spatial_scale;
     float* d_top;         /* (R,PH,PW,C) float32, may be NULL */
     int* d_argmax;        /* (R,PH,PW,C) int32, may be NULL */
     void* d_top_hi;       /* optional bf16 (R, PH*PW*C) hi/lo pair feeding fc6, may be NULL */
     void* d_top_lo;
+    int source;           /* MV3D_ROI_* (mv3d_roi_pool_fused only; mv3d_roi_pool_multiview always reads d_rois) */
+    float* d_rois_out;    /* optional (R,5) [batch,x1,y1,x2,y2]: the rectangle the kernel pooled (fused form) */
 } mv3d_roi_view;
+/* projection constants of the fused form: BEV grid (transform.py:3-20) + clip bounds (im_info), the float32 3x4 image
+ * projection (P2.R0).Tr by value or as a device pointer (graph replay), the FV map geometry (radians) */
+typedef struct {
+    double xn, yn, x_min, y_min, res;
+    float im_h, im_w;
+    float h_proj[12];
+    const float* d_proj;  /* overrides h_proj when not NULL */
+    int fv_h, fv_w;
+    double fv_theta_min, fv_dtheta, fv_phi_max, fv_dphi;
+} mv3d_roi_projection;
 int mv3d_roi_pool_multiview(const mv3d_roi_view* views, int n_views, int num_rois, const int* d_num_valid,
                             int channels, int pooled_height, int pooled_width, void* stream);
+/* north-star (iv): ONE launch for all views that also PROJECTS each 3-D proposal (d_rois_3d (R,7) [batch,x,y,z,l,w,h])
+ * into the views whose `source` says so, stages every roi window in shared memory once and emits fc6's bf16 hi/lo
+ * operand with 16-byte stores.  Replaces the two RoiPool launches + proposal_transform of the reference
+ * (lib/networks/MV3D_test.py:87-113, network.py:292-315).  channels % 8 == 0. */
+int mv3d_roi_pool_fused(const mv3d_roi_view* views, int n_views, const float* d_rois_3d,
+                        const mv3d_roi_projection* proj, int num_rois, const int* d_num_valid, int channels,
+                        int pooled_height, int pooled_width, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (ii) conv / fc as one tcgen05 implicit GEMM.  Replaces Network.conv (+bias+ReLU) and Network.fc,
@@ -192,6 +218,11 @@ typedef struct {
      * (3x3 convs with Cin % 64 == 0 only): one fp16 pass + one e5m2 pass at twice the rate carrying both first-order
      * correction terms -- 2/3 of the tensor-pipe time of passes=3, error ~2^-14.5 per product (3-pass: 2^-17). */
     int out_fmt;
+    /* > 0: columns [0, softmax_cols) of the float32 output are adjacent (bg, fg) score pairs; the epilogue replaces
+     * each pair by its softmax (the reference's reshape -> softmax -> reshape over the last dim of 2,
+     * lib/networks/MV3D_test.py:76-81, network.py:399-405) -- used to fold rpn_cls_score | rpn_bbox_pred into ONE
+     * N = 32 GEMM whose output is (prob x 8 | deltas x 24).  Requires d_out_f32, relu = 0, split_k <= 1, even. */
+    int softmax_cols;
 } mv3d_gemm_desc;
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
 /* A/B switch for the CTA-pair (tcgen05 cta_group::2, 256 x N tiles) form of the tap-reuse 3x3 conv kernel: on (default,

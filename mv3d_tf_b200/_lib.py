@@ -20,13 +20,24 @@ class ProposalParams(C.Structure):
                 ("im_h", c_float), ("im_w", c_float), ("im_scale", c_float),
                 ("img_h", c_float), ("img_w", c_float), ("min_size", c_float),
                 ("pre_nms_top_n", c_int), ("post_nms_top_n", c_int),
-                ("nms_thresh", c_double), ("nms_rule_ge", c_int), ("batch_index", c_float), ("d_proj", c_void_p)]
+                ("nms_thresh", c_double), ("nms_rule_ge", c_int), ("batch_index", c_float), ("d_proj", c_void_p),
+                ("ld_prob", c_int), ("ld_deltas", c_int)]
 
 
 class RoiView(C.Structure):
     _fields_ = [("d_data", c_void_p), ("d_rois", c_void_p), ("height", c_int), ("width", c_int),
                 ("spatial_scale", c_float), ("d_top", c_void_p), ("d_argmax", c_void_p),
-                ("d_top_hi", c_void_p), ("d_top_lo", c_void_p)]
+                ("d_top_hi", c_void_p), ("d_top_lo", c_void_p), ("source", c_int), ("d_rois_out", c_void_p)]
+
+
+ROI_GIVEN, ROI_BEV, ROI_IMG, ROI_FV = 0, 1, 2, 3   # MV3D_ROI_* of include/mv3d_b200.h
+
+
+class RoiProjection(C.Structure):
+    _fields_ = [("xn", c_double), ("yn", c_double), ("x_min", c_double), ("y_min", c_double), ("res", c_double),
+                ("im_h", c_float), ("im_w", c_float), ("h_proj", c_float * 12), ("d_proj", c_void_p),
+                ("fv_h", c_int), ("fv_w", c_int), ("fv_theta_min", c_double), ("fv_dtheta", c_double),
+                ("fv_phi_max", c_double), ("fv_dphi", c_double)]
 
 
 class GemmDesc(C.Structure):
@@ -37,7 +48,7 @@ class GemmDesc(C.Structure):
                 ("d_out_hi", c_void_p), ("d_out_lo", c_void_p), ("ld_out", c_int),
                 ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int),
                 ("d_mask_hi", c_void_p), ("ld_mask", c_int), ("mask_scale", c_float),
-                ("d_addend_f32", c_void_p), ("ld_addend", c_int), ("out_fmt", c_int)]
+                ("d_addend_f32", c_void_p), ("ld_addend", c_int), ("out_fmt", c_int), ("softmax_cols", c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -79,6 +90,8 @@ SIGNATURES = {
     "mv3d_roi_pool_backward": (c_int, [c_void_p, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "mv3d_roi_pool_multiview": (c_int, [C.POINTER(RoiView), c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mv3d_roi_pool_fused": (c_int, [C.POINTER(RoiView), c_int, c_void_p, C.POINTER(RoiProjection), c_int, c_void_p,
+                                    c_int, c_int, c_int, c_void_p]),
     "mv3d_conv_gemm": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "mv3d_gemm_set_pair_mode": (c_int, [c_int]),
     "mv3d_gemm_set_stamps": (c_int, [c_void_p]),

@@ -55,6 +55,7 @@ struct GemmParams {
     int dbg_flags;    // MV3D_GEMM_DBG (measurement only, results are garbage; pair kernel): 1 = the producer stops issuing TMA
                       // loads after the first lap of each ring (pure MMA rate on stale shared memory), 4 = the epilogue
                       // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
+    int softmax_cols;   // mv3d_gemm_desc::softmax_cols
     long long* stamps;  // measurement only (mv3d_gemm_set_stamps): clock64 of pair 0's phases, see conv3x3_pair_kernel
 };
 
@@ -72,7 +73,7 @@ struct GemmCfg {
     static constexpr int kSmemBudget = 200 * 1024;
     static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 512 /*bias*/;
     static constexpr int kAccCols = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator
     static constexpr int kTmemCols = 2 * kAccCols;       // double-buffered: MMA of tile i+1 overlaps epilogue of tile i
     static_assert(kStages >= 2, "need at least a double buffer");
@@ -87,6 +88,15 @@ struct GemmCfg {
 // a 20 us serial tail and made the Cout = 64 layers epilogue-bound: ncu showed the MMAs at their floor and the tensor
 // pipe idle the rest of the time.  Hence 8 warps, packed cvt instructions and vector bias loads.)
 constexpr int kEpiWarps = 8;
+constexpr int kBiasSmem = 512;   // bias vectors up to this many floats are staged in shared memory once per CTA
+
+// All threads, before the set-up barrier: the epilogue then reads its bias from shared memory instead of paying an L2
+// round trip per chunk on its serial TMEM-load -> render -> store chain.
+__device__ __forceinline__ const float* stage_bias(const GemmParams& prm, float* bias_s) {
+    if (prm.bias == nullptr || prm.N > kBiasSmem) return nullptr;
+    for (int i = threadIdx.x; i < prm.N; i += blockDim.x) bias_s[i] = prm.bias[i];
+    return bias_s;
+}
 
 __device__ __forceinline__ uint32_t cvt_pack_f16x2(float lo, float hi) {
     uint32_t r;
@@ -106,7 +116,8 @@ __device__ __forceinline__ uint32_t cvt_pack_e5m2x2(float lo, float hi) {
 
 template <int BN, int ACC_COLS, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tmem_base, int acc, int m0, int n0, int q,
-                                              int half, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl) {
+                                              int half, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl,
+                                              const float* bias_s) {
     constexpr int kChunks = (BN + 31) / 32;
     const int row = q * 32 + lane;
     const long long p = (long long)m0 + row;
@@ -122,183 +133,210 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
         halo = (wp == 0) || (hp == prm.Hp - 1);
         dense_row = ((long long)b * prm.H + hp) * prm.W + (wp - 1);
     }
-    mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
-    tc_fence_after();
     const uint32_t taddr_row = tmem_base + acc * ACC_COLS + (uint32_t(q * 32) << 16);
     const int n_mine = (kChunks - half + 1) / 2;   // this warp's chunks: half, half + 2, ...
-    if (n_mine == 0) {   // (BN = 32: one chunk) still one arrival per tile, in step with the accumulator phases
+    // Hand the accumulator back to the MMA warp.  The tcgen05.ld results are in registers (wait::ld) and fenced, so a
+    // RELAXED arrive is enough: a release at cluster scope compiles to MEMBAR.ALL.GPU, which stalls on this warp's own
+    // global stores of the previous chunks / tile (~1 us per tile in the store-heavy early layers).
+    auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
         if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+            if (PAIR) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // the leader CTA's barrier
             else mbar_arrive(&tmem_empty[acc]);
         }
+    };
+    mbar_wait(&tmem_full[acc], (tl >> 1) & 1);
+    tc_fence_after();
+    if (n_mine == 0) {   // (BN = 32: one chunk) still one arrival per tile, in step with the accumulator phases
+        release();
         return;
     }
-#pragma unroll 1
-    for (int k = 0; k < n_mine; ++k) {
-        const int c = (half + 2 * k) * 32;
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent `continue`s
-        tmem_ld_32x32(taddr_row + c, v);
-        tmem_ld_wait();
-        if (k == n_mine - 1) {  // this warp's last chunk is in registers: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // the leader CTA's barrier
-                else mbar_arrive(&tmem_empty[acc]);
-            }
-        }
-        if (!in_range) continue;
-        if (prm.dbg_flags & 4) continue;   // MV3D_GEMM_DBG=4 (timing experiment): drain the accumulator, skip the math / stores
-        const int col0 = n0 + c;
-        if (col0 >= prm.N) continue;
-        if (prm.split_k > 1) {
-            if (halo) continue;
-            float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+    // One 32-column chunk: scale / bias / ReLU (/ addend / gate) -> operand rendering -> stores.
+    auto process = [&](const uint32_t (&v)[32], const int c) {
+    if (!in_range) return;
+    if (prm.dbg_flags & 4) return;   // MV3D_GEMM_DBG=4 (timing experiment): drain the accumulator, skip the math / stores
+    const int col0 = n0 + c;
+    if (col0 >= prm.N) return;
+    if (prm.split_k > 1) {
+        if (halo) return;
+        float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
-            continue;
-        }
-        const bool full = (col0 + 32 <= prm.N);
-        float f[32];
-        if (halo) {
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
+        return;
+    }
+    const bool full = (col0 + 32 <= prm.N);
+    float f[32];
+    if (halo) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;
-        } else {
-            const float sc = prm.acc_scale;
-            if (prm.bias != nullptr && full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(prm.bias + col0 + j));
-                    f[j] = __uint_as_float(v[j]) * sc + b4.x;
-                    f[j + 1] = __uint_as_float(v[j + 1]) * sc + b4.y;
-                    f[j + 2] = __uint_as_float(v[j + 2]) * sc + b4.z;
-                    f[j + 3] = __uint_as_float(v[j + 3]) * sc + b4.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) * sc;
-                    if (prm.bias != nullptr && col0 + j < prm.N) x += __ldg(prm.bias + col0 + j);
-                    f[j] = x;
-                }
-            }
-            if (prm.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-        }
-        if (prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
-            const float* ad = prm.addend + dense_row * prm.ld_addend + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (col0 + j < prm.N) f[j] += __ldg(ad + j);
-        }
-        if (prm.mask_hi != nullptr && !halo) {  // ReLU / dropout gate of the forward activation
-            const __nv_bfloat16* mk = prm.mask_hi + p * prm.ld_mask + col0;
-            if (full && (prm.ld_mask % 8 == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mk + j));
-                    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
-                        const uint32_t a = mw[e] & 0xFFFFu, b = mw[e] >> 16;
-                        f[j + 2 * e] = (a != 0 && a < 0x8000u) ? f[j + 2 * e] * prm.mask_scale : 0.f;
-                        f[j + 2 * e + 1] = (b != 0 && b < 0x8000u) ? f[j + 2 * e + 1] * prm.mask_scale : 0.f;
-                    }
-                }
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < prm.N) f[j] = (__bfloat162float(mk[j]) > 0.f) ? f[j] * prm.mask_scale : 0.f;
-            }
-        }
-        if (prm.out_hi != nullptr && prm.out_fmt == MV3D_FMT_F16E5) {
-            // fp16 plane + byte plane [e5m2(h) x64 | e5m2(residual * 4096) x64] per 64-channel chunk (host checks
-            // N % 64 == 0, ld_out % 64 == 0, so every 32-column chunk is full and 16-byte aligned).  Same arithmetic as
-            // split_f16e5 (common.cuh), two elements per cvt instruction.
-            unsigned short* oh = reinterpret_cast<unsigned short*>(prm.out_hi) + p * prm.ld_out + col0;
-            uint8_t* ob = reinterpret_cast<uint8_t*>(prm.out_lo) + p * prm.ld_out * 2 + f16e5_off(col0);
-            uint32_t ph[16], p8[8], q8[8];
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+    } else {
+        const float sc = prm.acc_scale;
+        const float* bsrc = bias_s != nullptr ? bias_s : prm.bias;   // generic loads: shared copy (N <= kBiasSmem) or global
+        if (prm.bias != nullptr && full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                uint32_t a8[2], b8[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float x0 = fminf(fmaxf(f[j + 2 * e], -65504.f), 65504.f);
-                    const float x1 = fminf(fmaxf(f[j + 2 * e + 1], -65504.f), 65504.f);
-                    const uint32_t h2 = cvt_pack_f16x2(x0, x1);
-                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-                    ph[j / 2 + e] = h2;
-                    a8[e] = cvt_pack_e5m2x2(hf.x, hf.y);
-                    b8[e] = cvt_pack_e5m2x2((x0 - hf.x) * kF16E5Scale, (x1 - hf.y) * kF16E5Scale);
-                }
-                p8[j / 4] = a8[0] | (a8[1] << 16);
-                q8[j / 4] = b8[0] | (b8[1] << 16);
+                const float4 b4 = *reinterpret_cast<const float4*>(bsrc + col0 + j);
+                f[j] = __uint_as_float(v[j]) * sc + b4.x;
+                f[j + 1] = __uint_as_float(v[j + 1]) * sc + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) * sc + b4.z;
+                f[j + 3] = __uint_as_float(v[j + 3]) * sc + b4.w;
             }
-            // each thread owns one pixel row: 256-bit stores = whole 32-byte sectors (rows are >= 128 B apart, so a
-            // 16-byte store per lane would touch 32 half sectors per instruction -- the LSU transaction count, not the
-            // arithmetic, was what the epilogue spent its time on)
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]) * sc;
+                if (prm.bias != nullptr && col0 + j < prm.N) x += bsrc[col0 + j];
+                f[j] = x;
+            }
+        }
+        if (prm.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (col0 < prm.softmax_cols) {   // (bg, fg) score pairs -> probabilities; same arithmetic as softmax_pairs_kernel
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                if (col0 + j + 1 < prm.softmax_cols) {
+                    const float m = fmaxf(f[j], f[j + 1]);
+                    const float e0 = expf(f[j] - m), e1 = expf(f[j + 1] - m);
+                    const float sm = e0 + e1;
+                    f[j] = e0 / sm;
+                    f[j + 1] = e1 / sm;
+                }
+            }
+        }
+    }
+    if (prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
+        const float* ad = prm.addend + dense_row * prm.ld_addend + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < prm.N) f[j] += __ldg(ad + j);
+    }
+    if (prm.mask_hi != nullptr && !halo) {  // ReLU / dropout gate of the forward activation
+        const __nv_bfloat16* mk = prm.mask_hi + p * prm.ld_mask + col0;
+        if (full && (prm.ld_mask % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mk + j));
+                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                    const uint32_t a = mw[e] & 0xFFFFu, b = mw[e] >> 16;
+                    f[j + 2 * e] = (a != 0 && a < 0x8000u) ? f[j + 2 * e] * prm.mask_scale : 0.f;
+                    f[j + 2 * e + 1] = (b != 0 && b < 0x8000u) ? f[j + 2 * e + 1] * prm.mask_scale : 0.f;
+                }
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < prm.N) f[j] = (__bfloat162float(mk[j]) > 0.f) ? f[j] * prm.mask_scale : 0.f;
+        }
+    }
+    if (prm.out_hi != nullptr && prm.out_fmt == MV3D_FMT_F16E5) {
+        // fp16 plane + byte plane [e5m2(h) x64 | e5m2(residual * 4096) x64] per 64-channel chunk (host checks
+        // N % 64 == 0, ld_out % 64 == 0, so every 32-column chunk is full and 16-byte aligned).  Same arithmetic as
+        // split_f16e5 (common.cuh), two elements per cvt instruction.
+        unsigned short* oh = reinterpret_cast<unsigned short*>(prm.out_hi) + p * prm.ld_out + col0;
+        uint8_t* ob = reinterpret_cast<uint8_t*>(prm.out_lo) + p * prm.ld_out * 2 + f16e5_off(col0);
+        uint32_t ph[16], p8[8], q8[8];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            uint32_t a8[2], b8[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float x0 = fminf(fmaxf(f[j + 2 * e], -65504.f), 65504.f);
+                const float x1 = fminf(fmaxf(f[j + 2 * e + 1], -65504.f), 65504.f);
+                const uint32_t h2 = cvt_pack_f16x2(x0, x1);
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+                ph[j / 2 + e] = h2;
+                a8[e] = cvt_pack_e5m2x2(hf.x, hf.y);
+                b8[e] = cvt_pack_e5m2x2((x0 - hf.x) * kF16E5Scale, (x1 - hf.y) * kF16E5Scale);
+            }
+            p8[j / 4] = a8[0] | (a8[1] << 16);
+            q8[j / 4] = b8[0] | (b8[1] << 16);
+        }
+        // each thread owns one pixel row: 256-bit stores = whole 32-byte sectors (rows are >= 128 B apart, so a
+        // 16-byte store per lane would touch 32 half sectors per instruction -- the LSU transaction count, not the
+        // arithmetic, was what the epilogue spent its time on)
+        st_global_v8(oh, ph);
+        st_global_v8(oh + 16, ph + 8);
+        st_global_v8(ob, p8);
+        st_global_v8(ob + 64, q8);
+    } else if (prm.out_hi != nullptr) {
+        __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
+        __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
+        if (full && !(prm.dbg_flags & 8) && (prm.ld_out % 16 == 0) && ((reinterpret_cast<uintptr_t>(prm.out_hi) | reinterpret_cast<uintptr_t>(prm.out_lo)) & 31) == 0) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {   // = split_bf16 on two elements
+                const float x0 = f[2 * e], x1 = f[2 * e + 1];
+                const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
+                ph[e] = h2;
+                pl[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
+            }
             st_global_v8(oh, ph);
             st_global_v8(oh + 16, ph + 8);
-            st_global_v8(ob, p8);
-            st_global_v8(ob + 64, q8);
-        } else if (prm.out_hi != nullptr) {
-            __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
-            __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
-            if (full && !(prm.dbg_flags & 8) && (prm.ld_out % 16 == 0) && ((reinterpret_cast<uintptr_t>(prm.out_hi) | reinterpret_cast<uintptr_t>(prm.out_lo)) & 31) == 0) {
-                uint32_t ph[16], pl[16];
+            if (ol) {
+                st_global_v8(ol, pl);
+                st_global_v8(ol + 16, pl + 8);
+            }
+        } else if (full && (prm.ld_out % 8 == 0)) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {   // = split_bf16 on two elements
-                    const float x0 = f[2 * e], x1 = f[2 * e + 1];
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t ph4[4], pl4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float x0 = f[j + 2 * e], x1 = f[j + 2 * e + 1];
                     const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
-                    ph[e] = h2;
-                    pl[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
+                    ph4[e] = h2;
+                    pl4[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
                 }
-                st_global_v8(oh, ph);
-                st_global_v8(oh + 16, ph + 8);
-                if (ol) {
-                    st_global_v8(ol, pl);
-                    st_global_v8(ol + 16, pl + 8);
-                }
-            } else if (full && (prm.ld_out % 8 == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint32_t ph4[4], pl4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x0 = f[j + 2 * e], x1 = f[j + 2 * e + 1];
-                        const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
-                        ph4[e] = h2;
-                        pl4[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
-                    }
-                    *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
-                    if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
-                }
-            } else {
-                for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(f[j], h, l);
-                    oh[j] = h;
-                    if (ol) ol[j] = l;
-                }
+                *reinterpret_cast<uint4*>(oh + j) = make_uint4(ph4[0], ph4[1], ph4[2], ph4[3]);
+                if (ol) *reinterpret_cast<uint4*>(ol + j) = make_uint4(pl4[0], pl4[1], pl4[2], pl4[3]);
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < prm.N; ++j) {
+                __nv_bfloat16 h, l;
+                split_bf16(f[j], h, l);
+                oh[j] = h;
+                if (ol) ol[j] = l;
             }
         }
-        if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
-            float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
-            if (full && !(prm.dbg_flags & 8) && (prm.ld_f32 % 8 == 0) && (reinterpret_cast<uintptr_t>(prm.out_f32) & 31) == 0) {
+    }
+    if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
+        float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
+        if (full && !(prm.dbg_flags & 8) && (prm.ld_f32 % 8 == 0) && (reinterpret_cast<uintptr_t>(prm.out_f32) & 31) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) st_global_v8(o + j, reinterpret_cast<const uint32_t*>(f + j));
-            } else if (full && (prm.ld_f32 % 4 == 0)) {
+            for (int j = 0; j < 32; j += 8) st_global_v8(o + j, reinterpret_cast<const uint32_t*>(f + j));
+        } else if (full && (prm.ld_f32 % 4 == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-                for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+            for (int j = 0; j < 32 && col0 + j < prm.N; ++j) o[j] = f[j];
         }
+    }
+    };
+    // Two register buffers: the TMEM load of chunk k+1 is in flight while chunk k is rendered and stored (one tile per
+    // CTA pair in the 512-channel layers: the epilogue is an exposed, latency-bound tail).
+    uint32_t va[32], vb[32];
+    __syncwarp();
+    tmem_ld_32x32(taddr_row + half * 32, va);
+#pragma unroll 1
+    for (int k = 0; k < n_mine; k += 2) {
+        tmem_ld_wait_dep(va);
+        __syncwarp();
+        if (k + 1 < n_mine) tmem_ld_32x32(taddr_row + (half + 2 * (k + 1)) * 32, vb);
+        else release();
+        process(va, (half + 2 * k) * 32);
+        if (k + 1 >= n_mine) break;
+        tmem_ld_wait_dep(vb);
+        __syncwarp();
+        if (k + 2 < n_mine) tmem_ld_32x32(taddr_row + (half + 2 * (k + 2)) * 32, va);
+        else release();
+        process(vb, (half + 2 * k + 2) * 32);
     }
 }
 
@@ -321,6 +359,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint64_t* tmem_full = empty_bar + Cfg::kStages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const float* bias_s = stage_bias(prm, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -432,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = ((w / tiles_n) % tiles_m) * kBM;
-            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
         }
     }
     tc_fence_before();
@@ -468,7 +507,7 @@ struct ReuseCfg {
     static constexpr int kBudget = 200 * 1024;
     static constexpr int kNWRaw = (kBudget - kNA * kAEntry) / kWEntry;
     static constexpr int kNW = kNWRaw > 8 ? 8 : kNWRaw;
-    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512;
+    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512 + 4 * 512 /*bias*/;
     static constexpr int kAccCols = BN < 32 ? 32 : BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static_assert(kNW >= 3, "W ring too shallow");
@@ -492,6 +531,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     uint64_t* tmem_full = w_empty + Cfg::kNW;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const float* bias_s = stage_bias(prm, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -601,7 +641,7 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++tl) {
             const int n0 = (w % tiles_n) * BN;
             const int m0 = ((w / tiles_n) % tiles_m) * kBM;
-            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
         }
     }
     tc_fence_before();
@@ -636,7 +676,7 @@ struct PairCfg {
     static constexpr int kBudget = 200 * 1024;
     static constexpr int kNWRaw = (kBudget - kNA * kAEntry) / kWEntry;
     static constexpr int kNW = kNWRaw > 8 ? 8 : kNWRaw;
-    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512;
+    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512 + 4 * 512 /*bias*/;
     static constexpr int kAccCols = BN < 32 ? 32 : BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static_assert(kNW >= 3, "W ring too shallow");
@@ -662,6 +702,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     uint64_t* tmem_full = w_empty + Cfg::kNW;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const float* bias_s = stage_bias(prm, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -792,7 +833,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 mbar_wait(&tmem_full[tl & 1], (tl >> 1) & 1);
                 stamp(prm, 4);   // last accumulator complete (MMAs retired)
             }
-            epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl);
+            epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
         }
         if (warp == 2 && lane == 0) stamp(prm, 5);   // this warp's epilogue done
     }
@@ -1029,6 +1070,7 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = g_stamps;
+    p.softmax_cols = d->softmax_cols;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1137,6 +1179,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
+    p.softmax_cols = d->softmax_cols;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1189,6 +1232,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
+    p.softmax_cols = d->softmax_cols;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
@@ -1264,6 +1308,8 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(d->split_k <= 1 || d->d_out_f32);
     MV3D_REQUIRE(!d->f32_dense || d->Hp > 0);
     MV3D_REQUIRE(d->split_k <= 1 || (!d->d_mask_hi && !d->d_addend_f32));
+    MV3D_REQUIRE(d->softmax_cols >= 0 && d->softmax_cols <= d->N && d->softmax_cols % 2 == 0);
+    MV3D_REQUIRE(d->softmax_cols == 0 || (d->d_out_f32 && !d->d_out_hi && !d->relu && d->split_k <= 1 && !d->d_mask_hi && !d->d_addend_f32));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fc_swap_applicable(d)) return launch_fc_swapped(d, s);
     if (d->passes == 2) {

@@ -4,18 +4,9 @@
 // it as point_cloud_2_front / lidar_3d_to_fv) after the MV3D paper the reference's README.md:5 links.  All index math is
 // float64 so that the device and the numpy specification agree bit for bit away from measure-zero cell edges.
 #include "common.cuh"
+#include "geom.cuh"
 
 namespace mv3d {
-
-struct FvGeom {
-    int H, W;
-    double theta_min, dtheta, phi_max, dphi;  // radians
-};
-
-__device__ __forceinline__ void fv_coords(const FvGeom& g, double x, double y, double z, double& col, double& row) {
-    col = (atan2(y, x) - g.theta_min) / g.dtheta;
-    row = (g.phi_max - atan2(z, sqrt(x * x + y * y))) / g.dphi;
-}
 
 // pass 1: last writer per cell (largest point index), table pre-zeroed
 __global__ void fv_winner_kernel(const float* __restrict__ pts, int n, int stride, FvGeom g, int* __restrict__ table) {
@@ -79,31 +70,8 @@ __global__ void rois_to_fv_kernel(const float* __restrict__ rois_3d, int R, cons
     }
     const float* p = rois_3d + (size_t)i * 7;
     // corners exactly as lidar_3d_to_corners (transform.py:305-313): float32 half extents added to the centre
-    const float hl = __fdiv_rn(p[4], 2.f), hw = __fdiv_rn(p[5], 2.f), hh = __fdiv_rn(p[6], 2.f);
-    const float xs[2] = {__fadd_rn(hl, p[1]), __fadd_rn(-hl, p[1])};
-    const float ys[2] = {__fadd_rn(hw, p[2]), __fadd_rn(-hw, p[2])};
-    const float zs[2] = {__fadd_rn(hh, p[3]), __fadd_rn(-hh, p[3])};
-    double cmin = 0, cmax = 0, rmin = 0, rmax = 0;
-    bool bad = false;
-    for (int k = 0; k < 8; ++k) {
-        double col, row;
-        fv_coords(g, (double)xs[k & 1], (double)ys[(k >> 1) & 1], (double)zs[k >> 2], col, row);
-        col = floor(col);
-        row = floor(row);
-        if (!(isfinite(col) && isfinite(row))) bad = true;
-        if (k == 0) { cmin = cmax = col; rmin = rmax = row; }
-        else {
-            cmin = fmin(cmin, col); cmax = fmax(cmax, col);
-            rmin = fmin(rmin, row); rmax = fmax(rmax, row);
-        }
-    }
     o[0] = p[0];
-    if (bad) { o[1] = o[2] = o[3] = o[4] = 0.f; return; }
-    const double wmax = g.W - 1, hmax = g.H - 1;
-    o[1] = (float)fmin(fmax(cmin, 0.0), wmax);
-    o[2] = (float)fmin(fmax(rmin, 0.0), hmax);
-    o[3] = (float)fmin(fmax(cmax, 0.0), wmax);
-    o[4] = (float)fmin(fmax(rmax, 0.0), hmax);
+    extents_to_fv_box(g, box_extents(p[1], p[2], p[3], p[4], p[5], p[6]), o + 1);
 }
 
 }  // namespace mv3d

@@ -1,5 +1,6 @@
-// Geometry helpers shared by the proposal layer and the proposal-target layer: the reference's 8-corner image
-// projection (lib/utils/transform.py:290-315,369-386,483-500) with numpy's dtype pipeline.
+// Geometry helpers shared by the proposal layer, the proposal-target layer and the fused multi-view ROI pool: the
+// reference's BEV box (lib/utils/transform.py:113-142, numpy `//`), its 8-corner image projection
+// (transform.py:290-315,369-386,483-500) with numpy's dtype pipeline, and this project's front-view box.
 #pragma once
 #include <limits.h>
 
@@ -49,6 +50,98 @@ __device__ __forceinline__ void corners_to_img_box(const float* M, float xp, flo
     if (nan_v) vmin = vmax = nan("");
     img[0] = cast_i32_x86(umin); img[1] = cast_i32_x86(vmin);
     img[2] = cast_i32_x86(umax); img[3] = cast_i32_x86(vmax);
+}
+
+// numpy float64 floor_divide == npy_divmod (numpy/core/src/npymath/npy_math_internal.h): fmod based.
+__device__ __forceinline__ double npy_floor_divide(double a, double b) {
+    if (b == 0.0) return a / b;
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0) {
+        if ((b < 0) != (mod < 0)) div -= 1.0;
+    }
+    double floordiv;
+    if (div != 0.0) {
+        floordiv = floor(div);
+        if (div - floordiv > 0.5) floordiv += 1.0;
+    } else {
+        floordiv = copysign(0.0, a / b);
+    }
+    return floordiv;
+}
+
+// np.maximum(np.minimum(v, hi), 0) with numpy's NaN propagation.
+__device__ __forceinline__ float clip_np(float v, float hi) {
+    if (v != v) return v;
+    v = v < hi ? v : hi;
+    return v > 0.f ? v : 0.f;
+}
+
+// BEV grid constants of transform.py:3-20 + the clip bounds of clip_boxes (im_w - 1, im_h - 1 as float32).
+struct BevGrid {
+    double xn, yn, x_min, y_min, res;
+    float clip_x, clip_y;
+};
+
+// Half-extent sums of a 3-D box [x,y,z,l,w,h] (float32, as lidar_3d_to_bv / lidar_3d_to_corners form them).
+struct BoxExtents {
+    float xp, xm, yp, ym, zp, zm;
+};
+__device__ __forceinline__ BoxExtents box_extents(float px, float py, float pz, float pl, float pw, float ph) {
+    const float hl = __fmul_rn(pl, 0.5f), hw = __fmul_rn(pw, 0.5f), hh = __fmul_rn(ph, 0.5f);
+    BoxExtents e;
+    e.xp = __fadd_rn(px, hl); e.xm = __fsub_rn(px, hl);
+    e.yp = __fadd_rn(py, hw); e.ym = __fsub_rn(py, hw);
+    e.zp = __fadd_rn(pz, hh); e.zm = __fsub_rn(pz, hh);
+    return e;
+}
+
+// lidar_3d_to_bv (transform.py:132-140: f32 sums widened to f64, numpy `//`) + clip_boxes (bbox_transform.py:178-191)
+// -> (x1, y1, x2, y2) integral-valued float32.
+__device__ __forceinline__ void extents_to_bev_box(const BevGrid& g, const BoxExtents& e, float* bv) {
+    float x1 = (float)(g.yn - npy_floor_divide((double)e.yp - g.y_min, g.res));
+    float y1 = (float)(g.xn - npy_floor_divide((double)e.xp - g.x_min, g.res));
+    float x2 = (float)(g.yn - npy_floor_divide((double)e.ym - g.y_min, g.res));
+    float y2 = (float)(g.xn - npy_floor_divide((double)e.xm - g.x_min, g.res));
+    bv[0] = clip_np(x1, g.clip_x); bv[1] = clip_np(y1, g.clip_y);
+    bv[2] = clip_np(x2, g.clip_x); bv[3] = clip_np(y2, g.clip_y);
+}
+
+// Front view (no reference counterpart; DESIGN.md 'Front view'): cylindrical map geometry.
+struct FvGeom {
+    int H, W;
+    double theta_min, dtheta, phi_max, dphi;  // radians
+};
+
+__device__ __forceinline__ void fv_coords(const FvGeom& g, double x, double y, double z, double& col, double& row) {
+    col = (atan2(y, x) - g.theta_min) / g.dtheta;
+    row = (g.phi_max - atan2(z, sqrt(x * x + y * y))) / g.dphi;
+}
+
+// FV rectangle of a 3-D box: floor of the FV coordinates of its 8 corners, min/max, clamped to the map
+// -> [col_min, row_min, col_max, row_max]; a non-finite corner gives the empty rectangle (0,0,0,0).
+__device__ __forceinline__ void extents_to_fv_box(const FvGeom& g, const BoxExtents& e, float* o) {
+    const float xs[2] = {e.xp, e.xm}, ys[2] = {e.yp, e.ym}, zs[2] = {e.zp, e.zm};
+    double cmin = 0, cmax = 0, rmin = 0, rmax = 0;
+    bool bad = false;
+    for (int k = 0; k < 8; ++k) {
+        double col, row;
+        fv_coords(g, (double)xs[k & 1], (double)ys[(k >> 1) & 1], (double)zs[k >> 2], col, row);
+        col = floor(col);
+        row = floor(row);
+        if (!(isfinite(col) && isfinite(row))) bad = true;
+        if (k == 0) { cmin = cmax = col; rmin = rmax = row; }
+        else {
+            cmin = fmin(cmin, col); cmax = fmax(cmax, col);
+            rmin = fmin(rmin, row); rmax = fmax(rmax, row);
+        }
+    }
+    if (bad) { o[0] = o[1] = o[2] = o[3] = 0.f; return; }
+    const double wmax = g.W - 1, hmax = g.H - 1;
+    o[0] = (float)fmin(fmax(cmin, 0.0), wmax);
+    o[1] = (float)fmin(fmax(rmin, 0.0), hmax);
+    o[2] = (float)fmin(fmax(cmax, 0.0), wmax);
+    o[3] = (float)fmin(fmax(rmax, 0.0), hmax);
 }
 
 }  // namespace mv3d

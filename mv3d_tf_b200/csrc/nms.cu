@@ -2,11 +2,17 @@
 // lib/nms/nms_kernel.cu:34-144 (rule '>' in float; there the keep-chain is reduced on the HOST after an
 // 18 MB mask D2H -- here it never leaves the GPU).
 //
-//  nms_mask_kernel  : upper-triangular 64x64 tiles, one 64-bit suppression word per (box, column tile).
-//  nms_reduce_kernel: ONE CTA walks the keep chain 64 boxes at a time: thread 0 resolves the diagonal
-//                     tile serially in registers, then all threads OR the kept rows into the shared
-//                     `removed` bitmap.  Stops as soon as max_keep survivors exist (the reference
-//                     computes all survivors and slices [:post_nms_topN]; the prefix is identical).
+//  nms_mask_kernel  : one 256-thread CTA per UPPER-TRIANGULAR 64x64 tile (1-D grid over the T(T+1)/2 tiles, no
+//                     empty CTAs).  The 64 row boxes sit in shared memory; each lane keeps two column boxes (+ areas)
+//                     in registers (128-bit loads), each warp walks 8 rows: the row box is a shared-memory broadcast,
+//                     every lane evaluates its two IoUs and two __ballot_sync form the row's 64-bit suppression word.
+//  nms_reduce_kernel: ONE CTA walks the keep chain in super-blocks of S = 1024 candidates.  Per super-block ONE round
+//                     of independent global loads: (a) the `removed` bits of its candidates = OR of the mask rows of
+//                     every box kept so far (gathered, not scattered), (b) its S x S/64 diagonal tile into shared
+//                     memory.  Warp 0 then resolves the super-block with one step per KEPT box (not per candidate):
+//                     ballot over the 16 word lanes -> first un-suppressed candidate -> OR its diagonal row (one
+//                     shared-memory word per lane).  Stops as soon as max_keep survivors exist (the reference computes
+//                     all survivors and slices [:post_nms_topN]; the prefix is identical).
 //
 // IoU arithmetic is the reference's, float32 with IEEE roundings (file compiled with --fmad=false):
 //   area = (x2-x1+1)*(y2-y1+1); w = max(0, min(x2)-max(x1)+1); ovr = w*h / (area_i + area_j - w*h).
@@ -17,101 +23,135 @@
 namespace mv3d {
 
 constexpr int kNmsTile = 64;
-
-__device__ __forceinline__ float box_iou(const float4 a, const float a_area, const float4 b) {
-    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-    const float w = fmaxf(0.f, xx2 - xx1 + 1.f), h = fmaxf(0.f, yy2 - yy1 + 1.f);
-    const float inter = w * h;
-    const float b_area = (b.z - b.x + 1.f) * (b.w - b.y + 1.f);
-    return inter / (a_area + b_area - inter);
-}
+constexpr int kMaskThreads = 256;
 
 __device__ __forceinline__ float4 load_box(const float* boxes, int stride, int i) {
-    if (stride == 4) return *reinterpret_cast<const float4*>(boxes + (size_t)i * 4);
+    if (stride == 4) return __ldg(reinterpret_cast<const float4*>(boxes) + i);
     const float* p = boxes + (size_t)i * stride;
     return make_float4(p[0], p[1], p[2], p[3]);
 }
 
-__global__ void __launch_bounds__(kNmsTile)
+__device__ __forceinline__ bool suppresses(const float4 a, const float a_area, const float4 b, const float b_area,
+                                           const int rule_ge, const double thresh, const float thresh_f) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, xx2 - xx1 + 1.f), h = fmaxf(0.f, yy2 - yy1 + 1.f);
+    const float inter = w * h;
+    const float ovr = inter / (a_area + b_area - inter);
+    return rule_ge ? ((double)ovr >= thresh) : (ovr > thresh_f);
+}
+
+__global__ void __launch_bounds__(kMaskThreads)
 nms_mask_kernel(const float* __restrict__ boxes, int n_max, int stride, const int* __restrict__ d_n, double thresh,
                 int rule_ge, int nwords, unsigned long long* __restrict__ mask) {
-    const int col_blk = blockIdx.x, row_blk = blockIdx.y;
-    if (col_blk < row_blk) return;
+    // tile id -> (row_blk, col_blk >= row_blk): row r starts at r*T - r(r-1)/2
+    const int T = nwords;
+    const int t = blockIdx.x;
+    int row_blk = (int)((2.0f * T + 1.0f - sqrtf((2.0f * T + 1.0f) * (2.0f * T + 1.0f) - 8.0f * (float)t)) * 0.5f);
+    row_blk = max(0, min(row_blk, T - 1));
+    while (row_blk > 0 && row_blk * T - row_blk * (row_blk - 1) / 2 > t) --row_blk;
+    while ((row_blk + 1) * T - (row_blk + 1) * row_blk / 2 <= t) ++row_blk;
+    const int col_blk = row_blk + (t - (row_blk * T - row_blk * (row_blk - 1) / 2));
     int n = n_max;
     if (d_n) n = min(n, *d_n);
-    if (row_blk * kNmsTile >= n || col_blk * kNmsTile >= n) return;
-    __shared__ float4 cbox[kNmsTile];
-    const int t = threadIdx.x;
-    const int cj = col_blk * kNmsTile + t;
-    if (cj < n) cbox[t] = load_box(boxes, stride, cj);
-    __syncthreads();
-    const int i = row_blk * kNmsTile + t;
-    if (i >= n) return;
-    const float4 a = load_box(boxes, stride, i);
-    const float a_area = (a.z - a.x + 1.f) * (a.w - a.y + 1.f);
-    const int ncol = min(kNmsTile, n - col_blk * kNmsTile);
-    const float thresh_f = (float)thresh;
-    unsigned long long bits = 0;
-    const int start = (row_blk == col_blk) ? t + 1 : 0;
-    for (int j = start; j < ncol; ++j) {
-        const float ovr = box_iou(a, a_area, cbox[j]);
-        const bool sup = rule_ge ? ((double)ovr >= thresh) : (ovr > thresh_f);
-        if (sup) bits |= 1ull << j;
+    if (col_blk * kNmsTile >= n) return;   // (row_blk <= col_blk)
+    __shared__ float4 rbox[kNmsTile];
+    __shared__ float rarea[kNmsTile];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kNmsTile) {
+        const int i = row_blk * kNmsTile + tid;
+        const float4 a = i < n ? load_box(boxes, stride, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rbox[tid] = a;
+        rarea[tid] = (a.z - a.x + 1.f) * (a.w - a.y + 1.f);
     }
-    mask[(size_t)i * nwords + col_blk] = bits;
+    const int c0 = col_blk * kNmsTile + lane, c1 = c0 + 32;
+    const bool v0 = c0 < n, v1 = c1 < n;
+    const float4 b0 = v0 ? load_box(boxes, stride, c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b1 = v1 ? load_box(boxes, stride, c1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float area0 = (b0.z - b0.x + 1.f) * (b0.w - b0.y + 1.f), area1 = (b1.z - b1.x + 1.f) * (b1.w - b1.y + 1.f);
+    const float thresh_f = (float)thresh;
+    const bool diagonal = row_blk == col_blk;
+    __syncthreads();
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int rt = warp * 8 + r;                      // row inside the tile
+        const float4 a = rbox[rt];
+        const float a_area = rarea[rt];
+        bool s0 = v0 && suppresses(a, a_area, b0, area0, rule_ge, thresh, thresh_f);
+        bool s1 = v1 && suppresses(a, a_area, b1, area1, rule_ge, thresh, thresh_f);
+        if (diagonal) { s0 = s0 && lane > rt; s1 = s1 && lane + 32 > rt; }   // only later boxes can be suppressed
+        const unsigned lo = __ballot_sync(0xffffffffu, s0), hi = __ballot_sync(0xffffffffu, s1);
+        if (lane == r) mine = ((unsigned long long)hi << 32) | lo;
+    }
+    const int i = row_blk * kNmsTile + warp * 8 + lane;
+    if (lane < 8 && i < n) mask[(size_t)i * nwords + col_blk] = mine;
 }
 
 constexpr int kReduceThreads = 1024;
-constexpr int kMaxWords = 1024;  // up to 65536 boxes
+constexpr int kMaxWords = 1024;      // up to 65536 boxes
+constexpr int kSuper = 1024;         // candidates per super-block of the keep chain
+constexpr int kSuperWords = kSuper / kNmsTile;   // 16: one word lane each in the resolving warp
+constexpr int kReduceSmem = kSuper * kSuperWords * (int)sizeof(unsigned long long);   // 128 KB diagonal tile
 
 __global__ void __launch_bounds__(kReduceThreads)
 nms_reduce_kernel(const unsigned long long* __restrict__ mask, int n_max, const int* __restrict__ d_n, int nwords,
                   int max_keep, int* __restrict__ keep_out, int* __restrict__ num_out) {
-    __shared__ unsigned long long removed[kMaxWords];
-    __shared__ unsigned long long diag[kNmsTile];
-    __shared__ unsigned long long keepmask_s;
+    extern __shared__ unsigned long long diag[];               // [kSuper][kSuperWords]
+    __shared__ unsigned long long cur_s[kSuperWords];
     __shared__ int count_s;
     int n = n_max;
     if (d_n) n = min(n, *d_n);
     if (max_keep <= 0 || max_keep > n) max_keep = n;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < nwords; i += blockDim.x) removed[i] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) count_s = 0;
-    __syncthreads();
-    const int nblk = (n + kNmsTile - 1) / kNmsTile;
-    const int wlane = tid & 255, kq = tid >> 8;  // 256 word lanes x 4 row groups
-    for (int b = 0; b < nblk; ++b) {
-        if (tid < kNmsTile) {
-            const int row = b * kNmsTile + tid;
-            diag[tid] = row < n ? mask[(size_t)row * nwords + b] : ~0ull;
+    const int nsb = (n + kSuper - 1) / kSuper;
+    for (int B = 0; B < nsb; ++B) {
+        const int base = B * kSuper, w0 = B * kSuperWords;
+        const int nw = min(kSuperWords, nwords - w0);           // words of this super-block
+        const int rows = min(kSuper, n - base);
+        if (tid < kSuperWords) cur_s[tid] = 0;
+        __syncthreads();                                        // count_s / keep_out of the previous super-block visible
+        const int cnt = count_s;
+        {   // (a) removed bits of this super-block's candidates: OR of the rows of every box kept so far
+            const int w = tid & (kSuperWords - 1), g = tid >> 4;   // 16 word lanes x 64 row groups
+            unsigned long long acc = 0;
+            if (w < nw)
+                for (int k = g; k < cnt; k += kReduceThreads / kSuperWords)
+                    acc |= __ldg(mask + (size_t)keep_out[k] * nwords + w0 + w);
+            // (b) the diagonal tile; words left of a row's own 64-block were never written (upper-triangular mask)
+            for (int e = tid; e < rows * kSuperWords; e += kReduceThreads) {
+                const int r = e >> 4, ww = e & (kSuperWords - 1);
+                diag[e] = (ww < nw && ww >= (r >> 6)) ? __ldg(mask + (size_t)(base + r) * nwords + w0 + ww) : 0ull;
+            }
+            if (acc) atomicOr(&cur_s[w], acc);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long cur = removed[b], km = 0;
-            int cnt = count_s;
-            const int lim = min(kNmsTile, n - b * kNmsTile);
-            for (int k = 0; k < lim && cnt < max_keep; ++k) {
-                if (!((cur >> k) & 1ull)) {
-                    km |= 1ull << k;
-                    keep_out[cnt++] = b * kNmsTile + k;
-                    cur |= diag[k];
-                }
+        if (warp == 0) {   // resolve: one step per kept box
+            unsigned long long cur = ~0ull;
+            if (lane < nw) {
+                cur = cur_s[lane];
+                const int valid = rows - lane * kNmsTile;       // candidates of this word that exist
+                if (valid < kNmsTile) cur |= valid <= 0 ? ~0ull : (~0ull << valid);
             }
-            keepmask_s = km;
-            count_s = cnt;
+            int c = cnt;
+            while (c < max_keep) {
+                const unsigned long long avail = ~cur;          // not suppressed, not yet visited
+                const unsigned has = __ballot_sync(0xffffffffu, avail != 0ull);
+                if (has == 0u) break;
+                const int src = __ffs(has) - 1;
+                const unsigned long long a = __shfl_sync(0xffffffffu, avail, src);
+                const int bit = __ffsll((long long)a) - 1;
+                const int k = src * kNmsTile + bit;
+                if (lane == 0) keep_out[c] = base + k;
+                ++c;
+                if (lane < kSuperWords) cur |= diag[k * kSuperWords + lane];
+                if (lane == src) cur |= 1ull << bit;
+            }
+            if (lane == 0) count_s = c;
         }
         __syncthreads();
         if (count_s >= max_keep) break;
-        const unsigned long long km = keepmask_s;
-        for (int w = b + 1 + wlane; w < nwords; w += 256) {
-            unsigned long long acc = 0;
-#pragma unroll 4
-            for (int k = kq; k < kNmsTile; k += 4)
-                if ((km >> k) & 1ull) acc |= mask[(size_t)(b * kNmsTile + k) * nwords + w];
-            if (acc) atomicOr(&removed[w], acc);
-        }
-        __syncthreads();
     }
     __syncthreads();
     if (tid == 0) *num_out = count_s;
@@ -144,9 +184,16 @@ extern "C" __attribute__((visibility("default"))) int mv3d_nms(const float* d_bo
     MV3D_REQUIRE(nwords <= kMaxWords);
     if (!d_workspace || workspace_bytes < mv3d_nms_workspace_bytes(n_boxes)) return MV3D_ERR_WORKSPACE;
     unsigned long long* mask = static_cast<unsigned long long*>(d_workspace);
-    dim3 grid(nwords, nwords);
-    nms_mask_kernel<<<grid, kNmsTile, 0, s>>>(d_boxes, n_boxes, box_stride, d_n_boxes, thresh, rule_ge, nwords, mask);
-    nms_reduce_kernel<<<1, kReduceThreads, 0, s>>>(mask, n_boxes, d_n_boxes, nwords, max_keep, d_keep_out, d_num_out);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kReduceSmem);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    const int tiles = nwords * (nwords + 1) / 2;
+    nms_mask_kernel<<<tiles, kMaskThreads, 0, s>>>(d_boxes, n_boxes, box_stride, d_n_boxes, thresh, rule_ge, nwords, mask);
+    nms_reduce_kernel<<<1, kReduceThreads, kReduceSmem, s>>>(mask, n_boxes, d_n_boxes, nwords, max_keep, d_keep_out,
+                                                             d_num_out);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

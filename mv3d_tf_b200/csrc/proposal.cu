@@ -28,32 +28,8 @@ struct DecodeConst {
     float min_size;        // RPN_MIN_SIZE * im_scale (float32)
     int img_x_max, img_y_max;  // img_w + 50, img_h + 50
     int Hf, Wf, A, N;
+    int ld_prob, ld_deltas;  // floats between consecutive cells of prob / deltas (2A / 6A when dense)
 };
-
-// numpy float64 floor_divide == npy_divmod (numpy/core/src/npymath/npy_math_internal.h): fmod based.
-__device__ __forceinline__ double npy_floor_divide(double a, double b) {
-    if (b == 0.0) return a / b;
-    double mod = fmod(a, b);
-    double div = (a - mod) / b;
-    if (mod != 0.0) {
-        if ((b < 0) != (mod < 0)) div -= 1.0;
-    }
-    double floordiv;
-    if (div != 0.0) {
-        floordiv = floor(div);
-        if (div - floordiv > 0.5) floordiv += 1.0;
-    } else {
-        floordiv = copysign(0.0, a / b);
-    }
-    return floordiv;
-}
-
-// np.maximum(np.minimum(v, hi), 0) with numpy's NaN propagation.
-__device__ __forceinline__ float clip_np(float v, float hi) {
-    if (v != v) return v;
-    v = v < hi ? v : hi;
-    return v > 0.f ? v : 0.f;
-}
 
 __device__ __forceinline__ unsigned int orderable(float s) {
     const unsigned int u = __float_as_uint(s);
@@ -79,8 +55,8 @@ __device__ __forceinline__ Decoded decode_one(const float* __restrict__ prob, co
     Decoded o;
     const int a = i % k.A;
     const int cell = i / k.A;
-    o.score = prob[(size_t)cell * 2 * k.A + 2 * a + 1];                      // proposal_layer_tf.py:63
-    const float* d = deltas + (size_t)i * 6;                                   // :105
+    o.score = prob[(size_t)cell * k.ld_prob + 2 * a + 1];                    // proposal_layer_tf.py:63
+    const float* d = deltas + (size_t)cell * k.ld_deltas + a * 6;              // :105
     const float* an = anchors3d + (size_t)i * 6;
     // bbox_transform_inv_3d (bbox_transform.py:131-136): float32, mul then add
     const float px = __fadd_rn(__fmul_rn(d[0], an[3]), an[0]);
@@ -90,19 +66,14 @@ __device__ __forceinline__ Decoded decode_one(const float* __restrict__ prob, co
     const float pw = __fmul_rn((float)exp((double)d[4]), an[4]);
     const float ph = __fmul_rn((float)exp((double)d[5]), an[5]);
     o.p3d[0] = px; o.p3d[1] = py; o.p3d[2] = pz; o.p3d[3] = pl; o.p3d[4] = pw; o.p3d[5] = ph;
-    // lidar_3d_to_bv (transform.py:132-140): f32 sums widened to f64, numpy `//`
-    const float hl = __fmul_rn(pl, 0.5f), hw = __fmul_rn(pw, 0.5f), hh = __fmul_rn(ph, 0.5f);
-    const float xp = __fadd_rn(px, hl), xm = __fsub_rn(px, hl);
-    const float yp = __fadd_rn(py, hw), ym = __fsub_rn(py, hw);
-    const float zp = __fadd_rn(pz, hh), zm = __fsub_rn(pz, hh);
-    float x1 = (float)(k.yn - npy_floor_divide((double)yp - k.y_min, k.res));
-    float y1 = (float)(k.xn - npy_floor_divide((double)xp - k.x_min, k.res));
-    float x2 = (float)(k.yn - npy_floor_divide((double)ym - k.y_min, k.res));
-    float y2 = (float)(k.xn - npy_floor_divide((double)xm - k.x_min, k.res));
-    // clip_boxes (bbox_transform.py:178-191)
-    x1 = clip_np(x1, k.clip_x); y1 = clip_np(y1, k.clip_y);
-    x2 = clip_np(x2, k.clip_x); y2 = clip_np(y2, k.clip_y);
-    o.bv[0] = x1; o.bv[1] = y1; o.bv[2] = x2; o.bv[3] = y2;
+    // lidar_3d_to_bv (transform.py:132-140) + clip_boxes (bbox_transform.py:178-191): geom.cuh
+    const BoxExtents ex = box_extents(px, py, pz, pl, pw, ph);
+    BevGrid grid;
+    grid.xn = k.xn; grid.yn = k.yn; grid.x_min = k.x_min; grid.y_min = k.y_min; grid.res = k.res;
+    grid.clip_x = k.clip_x; grid.clip_y = k.clip_y;
+    extents_to_bev_box(grid, ex, o.bv);
+    const float x1 = o.bv[0], y1 = o.bv[1], x2 = o.bv[2], y2 = o.bv[3];
+    const float xp = ex.xp, xm = ex.xm, yp = ex.yp, ym = ex.ym, zp = ex.zp, zm = ex.zm;
     const float ws = __fadd_rn(__fsub_rn(x2, x1), 1.f), hs = __fadd_rn(__fsub_rn(y2, y1), 1.f);
     const bool keep_size = (ws >= k.min_size) && (hs >= k.min_size);           // _filter_boxes :336-341
     // lidar_3d_to_corners (transform.py:305-313) + lidar_cnr_to_img (:483-500, :369-386)
@@ -174,6 +145,16 @@ __global__ void proposal_scatter_kernel(const float* __restrict__ score, const u
     grouped[pos] = ((unsigned long long)orderable(s) << 32) | (unsigned int)i;
 }
 
+// Exact rank inside the score bin = position in the order the reference's NMS sees.  The reference sorts twice:
+// `scores.ravel().argsort()[::-1][:pre_nms_topN]` (proposal_layer_tf.py:161-163), then again inside nms()
+// (cpu_nms.pyx:25 / gpu_nms.pyx: `scores.argsort()[::-1]` on the already-descending array).  numpy's default sort leaves
+// tie order unspecified; the pinned rule (oracle.argsort_desc) is "stable ascending, reversed", under which
+// the first sort puts ties higher-index-first and the second one REVERSES every tie group that survived the top-N cut.
+// Both are applied here: r = #greater + #(equal, higher index) is the first sort's position; a box past the cut is
+// dropped; the tie group [#greater, min(#greater + #equal, M)) is then mirrored.
+// Cost: one pass over the bin per element (sum of bin_count^2 compares).  Scores concentrated in one bin (a freshly
+// initialised or a saturated RPN: ~35 k survivors in one bin) make that ~1e9 compares spread over ~35 k resident
+// threads, every load a warp broadcast: ~0.2 ms worst case instead of ~10 us -- bounded, so no second code path.
 __global__ void proposal_rank_kernel(const unsigned long long* __restrict__ grouped, const float* __restrict__ score,
                                      const int* __restrict__ bin_count, const int* __restrict__ bin_offset,
                                      const int* __restrict__ meta, const float4* __restrict__ pbv,
@@ -182,14 +163,24 @@ __global__ void proposal_rank_kernel(const unsigned long long* __restrict__ grou
     if (pos >= meta[0]) return;
     const unsigned long long key = grouped[pos];
     const int idx = (int)(key & 0xffffffffu);
+    const unsigned int skey = (unsigned int)(key >> 32);
     const int b = score_bin(score[idx]);
     const int beg = bin_offset[b];
     const int M = meta[1];
     if (beg >= M) return;  // the whole bin ranks past pre_nms_topN
     const int end = beg + bin_count[b];
-    int rank = beg;
-    for (int q = beg; q < end; ++q) rank += (grouped[q] > key) ? 1 : 0;
-    if (rank < M) {
+    int greater = beg, equal_hi = 0, equal = 0;
+    for (int q = beg; q < end; ++q) {
+        const unsigned long long other = grouped[q];
+        const unsigned int okey = (unsigned int)(other >> 32);
+        greater += (okey > skey) ? 1 : 0;
+        equal += (okey == skey) ? 1 : 0;
+        equal_hi += (okey == skey && other > key) ? 1 : 0;
+    }
+    const int first = greater + equal_hi;            // position after the first sort
+    if (first < M) {
+        const int last = min(greater + equal, M) - 1;  // the tie group's last position inside the cut
+        const int rank = greater + (last - first);      // mirrored by the second sort
         sorted_idx[rank] = idx;
         sorted_box[rank] = pbv[idx];
     }
@@ -262,6 +253,9 @@ static int make_decode_const(const mv3d_proposal_params* p, const float* h_proj,
     k->img_x_max = (int)p->img_w + 50;
     k->img_y_max = (int)p->img_h + 50;
     k->Hf = p->Hf; k->Wf = p->Wf; k->A = p->A; k->N = p->Hf * p->Wf * p->A;
+    k->ld_prob = p->ld_prob > 0 ? p->ld_prob : 2 * p->A;
+    k->ld_deltas = p->ld_deltas > 0 ? p->ld_deltas : 6 * p->A;
+    if (k->ld_prob < 2 * p->A || k->ld_deltas < 6 * p->A) return MV3D_ERR_ARG;
     return MV3D_OK;
 }
 

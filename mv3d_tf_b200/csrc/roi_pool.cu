@@ -9,9 +9,17 @@
 // Semantics kept bit-exact: round-half-away-from-zero of coord*scale, float32 bin sizes, floor/ceil,
 // clamp to [0,H]/[0,W], empty bin -> 0 / argmax -1, strict '>' so the first maximum in (h,w) order wins,
 // argmax = (h*W + w)*C + c inside the roi's image.
+//
+// roi_pool_fused_kernel (the inference path, north-star (iv)): ONE launch pools every view.  One CTA per (roi, view):
+// thread 0 PROJECTS the 3-D proposal into its view's plane in the kernel (BEV box + clip, 8-corner image box, FV box:
+// geom.cuh, the same device functions the proposal layer uses) -- or takes a given rectangle; the CTA then STAGES the
+// roi's whole window (all bins' cells, each read from global memory exactly once, 128-bit coalesced) in shared memory,
+// in channel slices when the window is large, and every 8-channel lane renders bins from shared memory: first maximum
+// in (h, w) order, split into the bf16 hi/lo operand of fc6 and written with 16-byte stores.
 #include <float.h>
 
 #include "common.cuh"
+#include "geom.cuh"
 
 namespace mv3d {
 
@@ -26,6 +34,14 @@ struct RoiViewDev {
     int* argmax;
     __nv_bfloat16* top_hi;
     __nv_bfloat16* top_lo;
+    int source;        // MV3D_ROI_GIVEN / _BEV / _IMG / _FV (fused kernel)
+    float* rois_out;   // optional (R,5): the rectangle that was pooled
+};
+struct RoiProjDev {
+    BevGrid bev;
+    float M[12];
+    const float* dM;
+    FvGeom fv;
 };
 struct RoiViews {
     RoiViewDev v[kMaxViews];
@@ -126,6 +142,155 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ top_diff, const in
     }
 }
 
+// ---- fused multi-view kernel -------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+constexpr int kStageBytes = 54 * 1024;   // shared-memory window slice; 4 CTAs per SM
+
+__device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* v) {
+    uint4 r;
+    r.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
+    r.y = (uint32_t)__bfloat16_as_ushort(v[2]) | ((uint32_t)__bfloat16_as_ushort(v[3]) << 16);
+    r.z = (uint32_t)__bfloat16_as_ushort(v[4]) | ((uint32_t)__bfloat16_as_ushort(v[5]) << 16);
+    r.w = (uint32_t)__bfloat16_as_ushort(v[6]) | ((uint32_t)__bfloat16_as_ushort(v[7]) << 16);
+    return r;
+}
+
+// grid (R, n_views), C % 8 == 0.  Rows >= *d_num_valid: zero outputs, argmax -1, zero rectangle.
+__global__ void __launch_bounds__(kFusedThreads)
+roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__ rois_3d, int R,
+                      const int* __restrict__ d_num_valid, int C, int PH, int PW) {
+    extern __shared__ float4 stage[];
+    __shared__ float roi_s[5];
+    const RoiViewDev& V = views.v[blockIdx.y];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const bool valid = d_num_valid ? (n < *d_num_valid) : true;
+    if (tid == 0) {
+        float roi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+            if (V.source == MV3D_ROI_GIVEN) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) roi[q] = V.rois[(size_t)n * 5 + q];
+            } else {
+                const float* p = rois_3d + (size_t)n * 7;
+                roi[0] = p[0];
+                const BoxExtents e = box_extents(p[1], p[2], p[3], p[4], p[5], p[6]);
+                if (V.source == MV3D_ROI_BEV) {
+                    extents_to_bev_box(proj.bev, e, roi + 1);
+                } else if (V.source == MV3D_ROI_IMG) {
+                    float Mloc[12];
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) Mloc[q] = proj.dM ? __ldg(proj.dM + q) : proj.M[q];
+                    int img[4];
+                    corners_to_img_box(Mloc, e.xp, e.xm, e.yp, e.ym, e.zp, e.zm, img);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) roi[1 + q] = (float)img[q];
+                } else {
+                    extents_to_fv_box(proj.fv, e, roi + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) roi_s[q] = roi[q];
+        if (V.rois_out) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) V.rois_out[(size_t)n * 5 + q] = roi[q];
+        }
+    }
+    __syncthreads();
+    const int nbins = PH * PW;
+    const int lanes_all = C / 8;
+    const size_t roi_base = (size_t)n * nbins * C;
+    if (!valid) {
+        for (int item = tid; item < nbins * lanes_all; item += kFusedThreads) {
+            const size_t o = roi_base + (size_t)item * 8;
+            if (V.top) { *reinterpret_cast<float4*>(V.top + o) = make_float4(0, 0, 0, 0); *reinterpret_cast<float4*>(V.top + o + 4) = make_float4(0, 0, 0, 0); }
+            if (V.argmax) { *reinterpret_cast<int4*>(V.argmax + o) = make_int4(-1, -1, -1, -1); *reinterpret_cast<int4*>(V.argmax + o + 4) = make_int4(-1, -1, -1, -1); }
+            if (V.top_hi) *reinterpret_cast<uint4*>(V.top_hi + o) = make_uint4(0, 0, 0, 0);
+            if (V.top_lo) *reinterpret_cast<uint4*>(V.top_lo + o) = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+    // the roi on the feature map: roi_pooling_op.cc:138-150 (round half away from zero, float32 bin sizes)
+    const int H = V.H, W = V.W;
+    const float scale = V.scale;
+    const int batch = (int)roi_s[0];
+    const int rsw = (int)roundf(roi_s[1] * scale), rsh = (int)roundf(roi_s[2] * scale);
+    const int rew = (int)roundf(roi_s[3] * scale), reh = (int)roundf(roi_s[4] * scale);
+    const int rw = max(rew - rsw + 1, 1), rh = max(reh - rsh + 1, 1);
+    const float bsh = (float)rh / (float)PH, bsw = (float)rw / (float)PW;
+    // window = union of all bins (bin bounds are monotone in ph / pw)
+    const int h0 = min(max(rsh, 0), H), h1 = min(max((int)ceilf((float)PH * bsh) + rsh, 0), H);
+    const int w0 = min(max(rsw, 0), W), w1 = min(max((int)ceilf((float)PW * bsw) + rsw, 0), W);
+    const int wh = max(h1 - h0, 0), ww = max(w1 - w0, 0);
+    const int cells = wh * ww;
+    const float* img = V.data + (size_t)batch * H * W * C;
+    // channel slice: as many channels (multiple of 8) as fit the stage next to `cells` window cells
+    int Cs = C;
+    if (cells > 0) {
+        const int fit = (kStageBytes / 4) / cells;     // floats per cell that fit
+        Cs = fit >= C ? C : (fit / 8) * 8;
+    }
+    const bool staged = Cs >= 32;                       // at least 128-byte cell slices
+    if (!staged) Cs = C;                                // very large window (> 432 cells): read global memory directly
+    for (int cb = 0; cb < C; cb += Cs) {
+        const int cs = min(Cs, C - cb), v4 = cs / 4, lanes = cs / 8;
+        if (staged && cells > 0) {
+            __syncthreads();                            // previous slice fully consumed
+            for (int idx = tid; idx < cells * v4; idx += kFusedThreads) {
+                const int cell = idx / v4, v = idx - cell * v4;
+                const int h = h0 + cell / ww, w = w0 + cell % ww;
+                stage[idx] = __ldg(reinterpret_cast<const float4*>(img + ((size_t)h * W + w) * C + cb) + v);
+            }
+            __syncthreads();
+        }
+        for (int item = tid; item < nbins * lanes; item += kFusedThreads) {
+            const int bin = item / lanes, lane = item - bin * lanes;
+            const int ph = bin / PW, pw = bin - ph * PW;
+            int hs = (int)floorf((float)ph * bsh), ws = (int)floorf((float)pw * bsw);
+            int he = (int)ceilf((float)(ph + 1) * bsh), we = (int)ceilf((float)(pw + 1) * bsw);
+            hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+            ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+            const bool empty = (he <= hs) || (we <= ws);
+            float mv[8];
+            int mi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { mv[e] = empty ? 0.f : -FLT_MAX; mi[e] = -1; }
+            for (int h = hs; h < he; ++h)
+                for (int w = ws; w < we; ++w) {
+                    const int idx0 = (h * W + w) * C + cb + lane * 8;
+                    float4 a, b;
+                    if (staged) {
+                        const float4* sp = stage + ((h - h0) * ww + (w - w0)) * v4 + lane * 2;
+                        a = sp[0]; b = sp[1];
+                    } else {
+                        a = __ldg(reinterpret_cast<const float4*>(img + idx0));
+                        b = __ldg(reinterpret_cast<const float4*>(img + idx0 + 4));
+                    }
+                    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (x[e] > mv[e]) { mv[e] = x[e]; mi[e] = idx0 + e; }
+                }
+            const size_t o = roi_base + (size_t)bin * C + cb + lane * 8;
+            if (V.top) {
+                *reinterpret_cast<float4*>(V.top + o) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+                *reinterpret_cast<float4*>(V.top + o + 4) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+            }
+            if (V.argmax) {
+                *reinterpret_cast<int4*>(V.argmax + o) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+                *reinterpret_cast<int4*>(V.argmax + o + 4) = make_int4(mi[4], mi[5], mi[6], mi[7]);
+            }
+            if (V.top_hi) {
+                __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16(mv[e], hi[e], lo[e]);
+                *reinterpret_cast<uint4*>(V.top_hi + o) = pack8_bf16(hi);
+                if (V.top_lo) *reinterpret_cast<uint4*>(V.top_lo + o) = pack8_bf16(lo);
+            }
+        }
+    }
+}
+
 static int launch_fwd(const RoiViews& views, int n_views, int R, const int* d_num_valid, int C, int PH, int PW,
                       cudaStream_t s) {
     if (R == 0) return MV3D_OK;
@@ -146,6 +311,38 @@ static int launch_fwd(const RoiViews& views, int n_views, int R, const int* d_nu
 
 using namespace mv3d;
 
+static int fill_views(const mv3d_roi_view* views, int n_views, bool fused, RoiViews* v) {
+    for (int i = 0; i < n_views; ++i) {
+        const int src = fused ? views[i].source : MV3D_ROI_GIVEN;
+        MV3D_REQUIRE(views[i].d_data && views[i].height > 0 && views[i].width > 0);
+        MV3D_REQUIRE(src >= MV3D_ROI_GIVEN && src <= MV3D_ROI_FV);
+        MV3D_REQUIRE(src != MV3D_ROI_GIVEN || views[i].d_rois);
+        MV3D_REQUIRE(views[i].d_top || views[i].d_top_hi);
+        v->v[i].data = views[i].d_data; v->v[i].rois = views[i].d_rois; v->v[i].H = views[i].height;
+        v->v[i].W = views[i].width; v->v[i].scale = views[i].spatial_scale; v->v[i].top = views[i].d_top;
+        v->v[i].argmax = views[i].d_argmax;
+        v->v[i].top_hi = static_cast<__nv_bfloat16*>(views[i].d_top_hi);
+        v->v[i].top_lo = static_cast<__nv_bfloat16*>(views[i].d_top_lo);
+        v->v[i].source = src;
+        v->v[i].rois_out = fused ? views[i].d_rois_out : nullptr;
+    }
+    return MV3D_OK;
+}
+
+static int launch_fused(const RoiViews& v, int n_views, const RoiProjDev& proj, const float* d_rois_3d, int R,
+                        const int* d_num_valid, int C, int PH, int PW, cudaStream_t s) {
+    if (R == 0) return MV3D_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(roi_pool_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    roi_pool_fused_kernel<<<dim3(R, n_views), kFusedThreads, kStageBytes, s>>>(v, proj, d_rois_3d, R, d_num_valid, C, PH, PW);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_forward(
     const float* d_bottom_data, float spatial_scale, int num_rois, int height, int width, int channels,
     int pooled_height, int pooled_width, const float* d_bottom_rois, float* d_top_data, int* d_argmax_data,
@@ -155,6 +352,12 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_forward(
     RoiViews v = {};
     v.v[0].data = d_bottom_data; v.v[0].rois = d_bottom_rois; v.v[0].H = height; v.v[0].W = width;
     v.v[0].scale = spatial_scale; v.v[0].top = d_top_data; v.v[0].argmax = d_argmax_data;
+    v.v[0].source = MV3D_ROI_GIVEN;
+    if (channels % 8 == 0) {
+        RoiProjDev proj = {};
+        return launch_fused(v, 1, proj, nullptr, num_rois, nullptr, channels, pooled_height, pooled_width,
+                            (cudaStream_t)stream);
+    }
     return launch_fwd(v, 1, num_rois, nullptr, channels, pooled_height, pooled_width, (cudaStream_t)stream);
 }
 
@@ -164,16 +367,40 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_multiview(
     MV3D_REQUIRE(views && n_views >= 1 && n_views <= kMaxViews && num_rois >= 0 && channels > 0);
     MV3D_REQUIRE(pooled_height > 0 && pooled_width > 0);
     RoiViews v = {};
-    for (int i = 0; i < n_views; ++i) {
-        MV3D_REQUIRE(views[i].d_data && views[i].d_rois && views[i].height > 0 && views[i].width > 0);
-        MV3D_REQUIRE(views[i].d_top || views[i].d_top_hi);
-        v.v[i].data = views[i].d_data; v.v[i].rois = views[i].d_rois; v.v[i].H = views[i].height;
-        v.v[i].W = views[i].width; v.v[i].scale = views[i].spatial_scale; v.v[i].top = views[i].d_top;
-        v.v[i].argmax = views[i].d_argmax;
-        v.v[i].top_hi = static_cast<__nv_bfloat16*>(views[i].d_top_hi);
-        v.v[i].top_lo = static_cast<__nv_bfloat16*>(views[i].d_top_lo);
+    const int rc = fill_views(views, n_views, false, &v);
+    if (rc != MV3D_OK) return rc;
+    if (channels % 8 == 0) {   // staged kernel, given rectangles
+        RoiProjDev proj = {};
+        return launch_fused(v, n_views, proj, nullptr, num_rois, d_num_valid, channels, pooled_height, pooled_width,
+                            (cudaStream_t)stream);
     }
     return launch_fwd(v, n_views, num_rois, d_num_valid, channels, pooled_height, pooled_width, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_fused(
+    const mv3d_roi_view* views, int n_views, const float* d_rois_3d, const mv3d_roi_projection* proj, int num_rois,
+    const int* d_num_valid, int channels, int pooled_height, int pooled_width, void* stream) {
+    MV3D_REQUIRE(views && n_views >= 1 && n_views <= kMaxViews && num_rois >= 0 && channels > 0 && channels % 8 == 0);
+    MV3D_REQUIRE(pooled_height > 0 && pooled_width > 0);
+    RoiViews v = {};
+    const int rc = fill_views(views, n_views, true, &v);
+    if (rc != MV3D_OK) return rc;
+    bool projected = false;
+    for (int i = 0; i < n_views; ++i) projected |= (v.v[i].source != MV3D_ROI_GIVEN);
+    MV3D_REQUIRE(!projected || (d_rois_3d && proj));
+    RoiProjDev pd = {};
+    if (proj) {
+        pd.bev.xn = proj->xn; pd.bev.yn = proj->yn; pd.bev.x_min = proj->x_min; pd.bev.y_min = proj->y_min;
+        pd.bev.res = proj->res;
+        pd.bev.clip_x = proj->im_w - 1.0f;   // im_shape[1] - 1 on a float32 array element (as the proposal layer)
+        pd.bev.clip_y = proj->im_h - 1.0f;
+        for (int q = 0; q < 12; ++q) pd.M[q] = proj->h_proj[q];
+        pd.dM = proj->d_proj;
+        pd.fv.H = proj->fv_h; pd.fv.W = proj->fv_w; pd.fv.theta_min = proj->fv_theta_min; pd.fv.dtheta = proj->fv_dtheta;
+        pd.fv.phi_max = proj->fv_phi_max; pd.fv.dphi = proj->fv_dphi;
+    }
+    return launch_fused(v, n_views, pd, d_rois_3d, num_rois, d_num_valid, channels, pooled_height, pooled_width,
+                        (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_backward(

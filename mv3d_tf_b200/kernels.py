@@ -181,7 +181,7 @@ def _run_gemm(_flops=0.0, **kw):
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
          out_f32_dense: bool = False, mask: Optional["PadAct"] = None, mask_scale: float = 1.0,
-         addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2):
+         addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2, softmax_cols: int = 0):
     """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None).
     mask / addend: the backward-data epilogue (out = (acc + addend) gated by mask > 0), see mv3d_gemm_desc."""
     assert w.cin_pad == a.c_pad, (w.cin_pad, a.c_pad)
@@ -209,7 +209,7 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
               ld_out=n_pad, d_out_f32=ptr(dense), ld_f32=w.cout, f32_dense=1 if out_f32_dense else 0, split_k=1,
               d_mask_hi=ptr(mask.hi) if mask is not None else None, ld_mask=mask.c_pad if mask is not None else 0,
               mask_scale=float(mask_scale), d_addend_f32=ptr(addend),
-              ld_addend=addend.shape[-1] if addend is not None else 0)
+              ld_addend=addend.shape[-1] if addend is not None else 0, softmax_cols=int(softmax_cols))
     return out, dense
 
 

@@ -11,11 +11,13 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 
 from .. import kernels as K
-from .._lib import RoiView, check, current_stream, lib, ptr
+from .._lib import (ROI_BEV, ROI_FV, ROI_GIVEN, ROI_IMG, RoiProjection, RoiView, check, current_stream, lib, ptr)
 from ..fast_rcnn.config import cfg
 from ..rpn_msr.anchor_target_layer_tf import AnchorTargetLayer
 from ..rpn_msr.proposal_layer_tf import ProposalLayer3D
@@ -92,6 +94,7 @@ class Network(object):
         self._anchor_target_layers: Dict[tuple, AnchorTargetLayer] = {}
         self._proposal_target_layer: Optional[ProposalTargetLayer3D] = None
         self._roi_nodes: List[Node] = []
+        self._needed_now = set()
         self.last_num_rois = None
         self.training = False           # True: roi_pool keeps argmax, dropout draws masks (set by the solver)
         self.native_fc_layout = False   # True: fc-after-roi_pool weights are stored with rows already in (H,W,C) order
@@ -258,12 +261,56 @@ class Network(object):
                 return Val(pad=out, dense=dense)
             if v.pad is None:
                 v.pad = K.pad_nhwc(v.dense, precise=self.precise)
+            cached = node.attrs.pop('result', None)
+            if cached is not None:
+                return cached
+            followers = [] if self.training else node.attrs.get('fused_followers', [])
+            if followers and not want_pad:
+                # sibling 1x1 heads on one input (rpn_cls_score | rpn_bbox_pred, MV3D_test.py:72-75): ONE GEMM over the
+                # concatenated output channels; when the leader only feeds reshape -> softmax -> reshape (:76-81) the
+                # pair softmax runs in that GEMM's epilogue and the three glue nodes pass the result through
+                key = name + '+' + '+'.join(f.name for f in followers)
+                pw = self._packed.get(key)
+                if pw is None:
+                    ws = [self.params[name]] + [self.params[f.name] for f in followers]
+                    pw = self._packed[key] = K.pack_weights(torch.cat([q['weights'] for q in ws], dim=3).contiguous(),
+                                                            torch.cat([q['biases'] for q in ws], dim=0).contiguous())
+                fold = self._softmax_chain(node) is not None
+                _, dense = K.conv(v.pad, pw, relu=False, precise=self.precise, out_pad=False, out_f32_dense=True,
+                                  softmax_cols=c_o if fold else 0)
+                off = c_o
+                for f in followers:
+                    f.attrs['result'] = Val(dense=dense[..., off:off + f.channels])
+                    off += f.channels
+                return Val(dense=dense[..., :c_o], extra=dict(softmax_folded=True) if fold else None)
             out, dense = K.conv(v.pad, self._weight(name, fmt=v.pad.fmt), relu=relu, precise=self.precise,
                                 out_pad=want_pad, out_f32_dense=want_dense, out_fmt=self._pad_out_fmt(node))
             return Val(pad=out, dense=dense)
         n = self._node(name, 'conv', [input], run, channels=c_o)
         n.attrs['k'] = (k_h, k_w)
+        n.attrs['relu'] = relu
+        if (k_h, k_w) == (1, 1) and not relu:   # fusion planning: an earlier linear 1x1 head on the same input
+            for m in self._program:
+                if m is not n and m.kind == 'conv' and m.attrs.get('k') == (1, 1) and not m.attrs.get('relu', True) \
+                        and m.inputs[0] is input and 'fused_into' not in m.attrs:
+                    m.attrs.setdefault('fused_followers', []).append(n)
+                    n.attrs['fused_into'] = m
+                    break
         return n
+
+    @staticmethod
+    def _softmax_chain(node):
+        """[reshape(2), softmax, reshape(C)] when `node` (a linear 1x1 conv) feeds exactly that chain and none of the
+        intermediate tensors is fetched; else None."""
+        chain, cur = [], node
+        for kind in ('reshape', 'softmax', 'reshape'):
+            if cur.attrs.get('fetched', False) or len(cur.consumer_nodes) != 1 or cur.consumer_nodes[0].kind != kind:
+                return None
+            cur = cur.consumer_nodes[0]
+            chain.append(cur)
+        if chain[0].channels != 2 or chain[2].channels != node.channels:
+            return None
+        return chain
 
     @layer
     def max_pool(self, input, k_h, k_w, s_h, s_w, name, padding=DEFAULT_PADDING):
@@ -278,14 +325,20 @@ class Network(object):
     @layer
     def reshape_layer(self, input, d, name):
         def run(vals, node):
-            x = vals[node.inputs[0]].dense
+            v = vals[node.inputs[0]]
+            if isinstance(v.extra, dict) and v.extra.get('softmax_folded'):
+                return v   # the fused head already holds the probabilities in the final (B,H,W,2A) arrangement
+            x = v.dense
             return Val(dense=x.reshape(x.shape[0], x.shape[1], -1, int(d)))
         return self._node(name, 'reshape', [input], run, channels=int(d))
 
     @layer
     def softmax(self, input, name):
         def run(vals, node):
-            x = vals[node.inputs[0]].dense
+            v = vals[node.inputs[0]]
+            if isinstance(v.extra, dict) and v.extra.get('softmax_folded'):
+                return v   # computed in the producing GEMM's epilogue
+            x = v.dense
             assert x.shape[-1] == 2, 'MV3D only ever takes 2-way softmaxes'
             return Val(dense=K.softmax_pairs(x, 1))
         return self._node(name, 'softmax', [input], run, channels=input.channels)
@@ -322,7 +375,8 @@ class Network(object):
                 bv = torch.cat([o['bv'] for o in outs]); img = torch.cat([o['img'] for o in outs])
                 p3d = torch.cat([o['p3d'] for o in outs]); num = torch.cat([o['num'] for o in outs])
             self.last_num_rois = num
-            return Val(extra=dict(bv=bv, img=img, p3d=p3d, num=num, per_frame=pl.capacity, outs=outs))
+            return Val(extra=dict(bv=bv, img=img, p3d=p3d, num=num, per_frame=pl.capacity, outs=outs,
+                                  layer=pl, calib=cb if B == 1 else None))
         n = self._node(name, 'proposal', list(input), run)
         # the reference returns the 4-tuple (rois_bv, rois_img, rois_3d, rois_3d)  (network.py:234)
         return (n, n, n, n)
@@ -336,16 +390,28 @@ class Network(object):
 
         def run(vals, node):
             e = vals[node.inputs[0]].extra
-            if target == 'fv' and 'fv' not in e:   # project the 3-D proposals into the front-view map
+            if target == 'fv' and 'fv' not in e:   # the 3-D proposals projected into the front-view map
                 p3d = e['p3d'].contiguous()
                 fv = torch.empty((p3d.shape[0], 5), dtype=torch.float32, device=p3d.device)
-                num = e['num'] if (e.get('num') is not None and e['num'].numel() == 1) else None
-                H, W, t0, dt, p1, dp = self.fv_geometry.c_args()
-                check(lib().mv3d_rois_to_fv(ptr(p3d), p3d.shape[0], ptr(num), H, W, t0, dt, p1, dp, ptr(fv),
-                                            current_stream()), 'mv3d_rois_to_fv')
                 e['fv'] = fv
+                pools = [c for c in node.consumer_nodes if c.kind == 'roi_pool' and c in self._needed_now]
+                if pools and self._fusable(e):
+                    e['fv_pending'] = True         # written by the fused ROI-pool launch (d_rois_out), no extra launch
+                else:
+                    num = e['num'] if (e.get('num') is not None and e['num'].numel() == 1) else None
+                    H, W, t0, dt, p1, dp = self.fv_geometry.c_args()
+                    check(lib().mv3d_rois_to_fv(ptr(p3d), p3d.shape[0], ptr(num), H, W, t0, dt, p1, dp, ptr(fv),
+                                                current_stream()), 'mv3d_rois_to_fv')
             return Val(dense=e[target], extra=e)
-        return self._node(name, 'rois', [src], run)
+        n = self._node(name, 'rois', [src], run)
+        n.attrs['target'] = target
+        return n
+
+    def _fusable(self, e) -> bool:
+        """In-kernel projection of the 3-D proposals (mv3d_roi_pool_fused) needs the proposal layer's own constants and
+        ONE projection matrix: single-frame inference."""
+        return (not self.training) and isinstance(e, dict) and e.get('layer') is not None and e.get('calib') is not None \
+            and e.get('p3d') is not None and e.get('num') is not None and e['num'].numel() == 1
 
     @layer
     def roi_pool(self, input, pooled_height, pooled_width, spatial_scale, name):
@@ -383,8 +449,33 @@ class Network(object):
             ph, pw, _ = node.attrs['cfg']
             e = vals[node.inputs[1]].extra
             num = e['num'] if (isinstance(e, dict) and e.get('num') is not None and e['num'].numel() == 1) else None
-            check(lib().mv3d_roi_pool_multiview(views, len(group), R, ptr(num), group[0].channels, ph, pw,
-                                                current_stream()), 'mv3d_roi_pool_multiview')
+            targets = [m.inputs[1].attrs.get('target') if isinstance(m.inputs[1], Node) else None for m in group]
+            if self._fusable(e) and all(t in ('bv', 'img', 'fv') for t in targets) and group[0].channels % 8 == 0 \
+                    and all(vals[m.inputs[1]].extra is e for m in group):
+                # north-star (iv): one launch projects every 3-D proposal into its view's plane and pools all views
+                pl, calib = e['layer'], e['calib']
+                pp = pl.params
+                proj = RoiProjection()
+                proj.xn, proj.yn, proj.x_min, proj.y_min, proj.res = pp.xn, pp.yn, pp.x_min, pp.y_min, pp.res
+                proj.im_h, proj.im_w = pp.im_h, pp.im_w
+                if isinstance(calib, torch.Tensor):
+                    proj.d_proj = calib.data_ptr()
+                else:
+                    from ..utils.transform import projection_matrix
+                    proj.h_proj = (C.c_float * 12)(*[float(x) for x in projection_matrix(calib).reshape(-1)])
+                    proj.d_proj = None
+                if self.fv_geometry is not None:
+                    (proj.fv_h, proj.fv_w, proj.fv_theta_min, proj.fv_dtheta, proj.fv_phi_max,
+                     proj.fv_dphi) = self.fv_geometry.c_args()
+                for k, t in enumerate(targets):
+                    views[k].source = {'bv': ROI_BEV, 'img': ROI_IMG, 'fv': ROI_FV}[t]
+                    views[k].d_rois_out = ptr(e['fv']) if (t == 'fv' and e.pop('fv_pending', False)) else None
+                p3d = e['p3d'].contiguous()
+                check(lib().mv3d_roi_pool_fused(views, len(group), ptr(p3d), C.byref(proj), R, ptr(num), group[0].channels,
+                                                ph, pw, current_stream()), 'mv3d_roi_pool_fused')
+            else:
+                check(lib().mv3d_roi_pool_multiview(views, len(group), R, ptr(num), group[0].channels, ph, pw,
+                                                    current_stream()), 'mv3d_roi_pool_multiview')
             mine = None
             for m, res in zip(group, results):
                 if m is node:
@@ -592,6 +683,7 @@ class Network(object):
                 t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
                 vals[node] = Val(dense=t.to(self.device, dtype=torch.float32).contiguous())
         needed = self._needed(fetch_nodes)
+        self._needed_now = needed
         main = torch.cuda.current_stream()
         # independent branches (attrs['side'] = k > 0: the RGB and FV trunks) run on their own streams, forked when first
         # reached and joined before the first node that may consume any of them

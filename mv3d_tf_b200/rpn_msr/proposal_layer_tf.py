@@ -55,7 +55,9 @@ class ProposalLayer3D:
         tensors (capacity rows, rows >= num are zero) and `num` (int32[1], device)."""
         assert prob.is_cuda and prob.dtype == torch.float32 and prob.numel() == self.N * 2
         assert deltas.is_cuda and deltas.dtype == torch.float32 and deltas.numel() == self.N * 6
-        prob, deltas = prob.contiguous(), deltas.contiguous()
+        # dense maps, or column ranges of one fused (Hf*Wf, 8A) head output: cells a fixed number of floats apart
+        prob, self.params.ld_prob = self._cells(prob, 2 * self.A)
+        deltas, self.params.ld_deltas = self._cells(deltas, 6 * self.A)
         if isinstance(calib, torch.Tensor):
             assert calib.is_cuda and calib.dtype == torch.float32 and calib.numel() == 12
             proj, self.params.d_proj = None, calib.data_ptr()
@@ -76,6 +78,13 @@ class ProposalLayer3D:
                                            ws.numel(), current_stream()), "mv3d_proposal_layer_3d")
         return out
 
+    def _cells(self, t: torch.Tensor, width: int):
+        """(tensor, pitch): `t` viewed as Hf*Wf cells of `width` contiguous floats, `pitch` floats apart (0 = dense)."""
+        t = t.reshape(self.Hf, self.Wf, width) if t.is_contiguous() else t
+        if t.dim() == 3 and t.stride(2) == 1 and t.stride(0) == self.Wf * t.stride(1) and t.stride(1) >= width:
+            return t, (0 if t.stride(1) == width else int(t.stride(1)))
+        return t.contiguous(), 0
+
     def decode(self, prob: torch.Tensor, deltas: torch.Tensor, calib: np.ndarray):
         """Stage outputs of the decode kernel for every anchor (parity tests)."""
         dev, N = self.device, self.N
@@ -85,6 +94,7 @@ class ProposalLayer3D:
         pimg = torch.empty((N, 4), dtype=torch.int32, device=dev)
         keep = torch.empty(N, dtype=torch.uint8, device=dev)
         proj = projection_matrix(calib)
+        self.params.ld_prob = self.params.ld_deltas = 0
         check(lib().mv3d_proposal_decode(ptr(prob.contiguous()), ptr(deltas.contiguous()), ptr(self.anchors3d),
                                          ptr(proj), C.byref(self.params), ptr(score), ptr(p3d), ptr(pbv), ptr(pimg),
                                          ptr(keep), current_stream()), "mv3d_proposal_decode")

@@ -103,4 +103,12 @@ def oracle_frame_errors(got, params, bv, img, im_info, calib, geom, cfg=None, fv
                                            np.asarray(calib), "TEST", cfg=cfg, geom=geom)
     exact["proposals_on_gpu_rpn_outputs"] = bool(rb.shape == got["roi_data_bv"].shape and np.array_equal(rb, got["roi_data_bv"])
                                                  and np.array_equal(ri, got["roi_data_img"]))
+    if not exact["proposals_on_gpu_rpn_outputs"]:   # keep the evidence for an offline look (scratch directory)
+        import os
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        np.savez_compressed(os.path.join(d, "parity_mismatch_%dviews.npz" % (3 if fv is not None else 2)),
+                            prob=got["rpn_cls_prob_reshape"], bbox=got["rpn_bbox_pred"], gpu_bv=got["roi_data_bv"],
+                            gpu_img=got["roi_data_img"], gpu_3d=got["rois_3d"], orc_bv=rb, orc_img=ri, orc_3d=r3,
+                            im_info=np.asarray(im_info), calib=np.asarray(calib))
     return errs, exact, prop
