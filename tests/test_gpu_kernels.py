@@ -241,3 +241,16 @@ def test_roi_pool_forward_backward(oracle, B, H, W, C, R):
                             torch.from_numpy(g).cuda(), 7, 7, 0.125).cpu().numpy()
         want = oracle.roi_pool_bwd(data.shape, rois, wa, g)
         assert np.allclose(got, want, rtol=1e-5, atol=2e-5)  # fp32 sum order differs (atomics)
+
+
+def test_roi_pool_golden_from_reference_op(golden_dir):
+    """Forward values + arg-max bit-exact, backward within fp32 summation order, against vectors produced by the
+    reference's own RoiPoolOp / RoiPoolGradOp CPU kernels (tests/golden/make_golden_roi_pool.py)."""
+    from mv3d_tf_b200.roi_pooling_layer.roi_pooling_op import roi_pool, roi_pool_grad
+
+    g = np.load(os.path.join(golden_dir, "roi_pool.npz"))
+    data, rois = torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["rois"]).cuda()
+    top, arg = roi_pool(data, rois, 7, 7, 0.125)
+    assert np.array_equal(top.cpu().numpy(), g["top"]) and np.array_equal(arg.cpu().numpy(), g["argmax"])
+    got = roi_pool_grad(data, rois, arg, torch.from_numpy(g["grad"]).cuda(), 7, 7, 0.125).cpu().numpy()
+    assert np.allclose(got, g["dbottom"], rtol=1e-5, atol=2e-5)

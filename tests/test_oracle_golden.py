@@ -134,3 +134,12 @@ def test_target_layers_golden(oracle, golden_dir):
     out = oracle.proposal_target_layer_3d(g["rois_bv"], g["rois_3d"], g["gt_bv"], g["gt_3d"], g["gt_cnr"], g["calib"], 2)
     for got, key in zip(out, ("pt_rois_bv", "pt_rois_img", "pt_labels", "pt_targets", "pt_rois_3d")):
         assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+
+
+def test_roi_pool_golden(oracle, golden_dir):
+    """tests/golden/roi_pool.npz was produced by the reference's own RoiPool / RoiPoolGrad CPU kernels
+    (tests/golden/make_golden_roi_pool.py); the C restatement must reproduce it bit for bit."""
+    g = np.load(os.path.join(golden_dir, "roi_pool.npz"))
+    top, arg = oracle.roi_pool_fwd(g["data"], g["rois"])
+    assert np.array_equal(top, g["top"]) and np.array_equal(arg, g["argmax"])
+    assert np.array_equal(oracle.roi_pool_bwd(g["data"].shape, g["rois"], g["argmax"], g["grad"]), g["dbottom"])

@@ -89,3 +89,27 @@ def test_box_detect_postprocessing_helpers(oracle, ref):
     assert np.array_equal(ref.transform.corners_to_bv(both), oracle.corners_to_bv(both))
     deltas = rng.normal(0, 0.1, (200, 48)).astype(np.float32)
     assert np.array_equal(ref.bbox_transform.bbox_transform_inv_cnr(cnr, deltas), oracle.bbox_transform_inv_cnr(cnr, deltas))
+
+
+def test_roi_pool_restatement_vs_reference_op(oracle):
+    """The reference's own RoiPoolOp / RoiPoolGradOp CPU kernels (roi_pooling_op.cc compiled unmodified against the
+    stand-in TF headers, oracle/build_ref_roi_pool.py) against the C restatement the GPU tests use -- forward values,
+    arg-max and the backward gather, at toy and at the reference's 75x75x512 / 46x155x512 shapes."""
+    from oracle import ref_roi_pool
+
+    assert ref_roi_pool.available()
+    rng = np.random.default_rng(0)
+    for (B, H, W, C, R) in [(1, 9, 11, 4, 6), (2, 20, 31, 7, 40), (1, 75, 75, 512, 300), (1, 46, 155, 512, 64)]:
+        data = rng.normal(size=(B, H, W, C)).astype(np.float32)
+        data[0, 0] = 1.25
+        x1, y1 = rng.integers(-60, W * 8, R), rng.integers(-60, H * 8, R)
+        rois = np.stack((rng.integers(0, B, R), x1, y1, x1 + rng.integers(0, 300, R), y1 + rng.integers(0, 200, R)), 1).astype(np.float32)
+        rois[0] = [0, -500, -500, -300, -300]
+        rois[1] = [0, 40, 40, 8, 8]
+        rois[2, 1:] += 0.5
+        wt, wa = ref_roi_pool.roi_pool_forward(data, rois)
+        ot, oa = oracle.roi_pool_fwd(data, rois)
+        assert np.array_equal(wt, ot) and np.array_equal(wa, oa)
+        if C <= 8:   # the reference's backward is O(H*W*C*R): small cases only
+            g = rng.normal(size=wt.shape).astype(np.float32)
+            assert np.array_equal(ref_roi_pool.roi_pool_backward(data, rois, wa, g), oracle.roi_pool_bwd(data.shape, rois, oa, g))
