@@ -6,9 +6,19 @@
 // index in a shared-memory table and streams its tile of the (H,W,C) output exactly once, coalesced.
 // HBM traffic ~= 16 B/point (+ a 4 B index write/read) + 4*H*W*C output bytes: the algorithmic minimum.
 //
+// float32 (H,W,C) output (mv3d_bev_raster, the configs[4] sweep): no binning at all -- the OUTPUT ITSELF is the winner
+// table.  After the zero fill every point marks its (cell, slice) slots with atomicMax of a key 0xFF800000 + index + 1
+// (a negative-NaN bit pattern: larger than the zero fill, ordered by point index, and never the bit pattern of a value
+// the raster stores), then every point re-reads its slots: the one whose key survived is the last writer and replaces
+// the key by z - h0; the winner of the cell's highest occupied slice also writes the reflectance.  Three launches
+// (fill, mark, resolve), each fully parallel over the output / the points; the two point passes move ~4 MB.
+// The PAD outputs (16-bit planes: no room for a key per element) keep the tile pipeline above.
+//
 // Exact semantics kept: float32 division for the cell index then truncation toward zero,
 // float64 slice bounds lo[i] <= z < hi[i] tested for EVERY slice, height = z - h0 in float32,
 // intensity = reflectance of the last writer of the highest occupied slice.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mv3d {
@@ -216,6 +226,52 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
     }
 }
 
+// ---- float32 output: mark / resolve in place ------------------------------------------------------------------
+constexpr unsigned int kKeyBase = 0xFF800000u;   // + (point index + 1) < 2^23: negative NaN patterns
+
+__global__ void raster_mark_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                   unsigned int* __restrict__ top_bits) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = pts + (size_t)i * stride;
+        const float4 q = (stride == 4) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(p[0], p[1], p[2], p[3]);
+        int row, col;
+        if (!point_cell(g, q.x, q.y, row, col)) continue;
+        const double z = (double)q.z;
+        int s_lo, s_hi;
+        slice_window(g, z, s_lo, s_hi);
+        unsigned int* cell = top_bits + ((size_t)row * g.W + col) * g.C;
+        for (int sl = s_lo; sl <= s_hi; ++sl)
+            if (z >= g.lo[sl] && z < g.hi[sl]) atomicMax(cell + sl, kKeyBase + (unsigned int)i + 1u);   // last index wins
+    }
+}
+
+__global__ void raster_resolve_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                      float* __restrict__ top) {
+    const unsigned int* bits = reinterpret_cast<const unsigned int*>(top);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = pts + (size_t)i * stride;
+        const float4 q = (stride == 4) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(p[0], p[1], p[2], p[3]);
+        int row, col;
+        if (!point_cell(g, q.x, q.y, row, col)) continue;
+        const double z = (double)q.z;
+        int s_lo, s_hi;
+        slice_window(g, z, s_lo, s_hi);
+        const size_t cell = ((size_t)row * g.W + col) * g.C;
+        const unsigned int key = kKeyBase + (unsigned int)i + 1u;
+        for (int sl = s_lo; sl <= s_hi; ++sl) {
+            if (!(z >= g.lo[sl] && z < g.hi[sl])) continue;
+            if (__ldcg(bits + cell + sl) != key) continue;           // another point wrote this (cell, slice) later
+            // highest occupied slice of the cell?  Slots above hold 0 (empty), a key, or a height > 0 -- never 0 once
+            // occupied (slice sl' >= 1 starts at h0 + sl' * zres), whichever of its two states a slot is in right now.
+            bool top_slice = true;
+            for (int up = sl + 1; up < g.nslices; ++up)
+                if (__ldcg(bits + cell + up) != 0u) { top_slice = false; break; }
+            top[cell + sl] = __fsub_rn(q.z, g.h0);                    // read_lidar.py:106,110
+            if (top_slice) top[cell + g.C - 1] = q.w;                 // :113: last writer of the highest occupied slice
+        }
+    }
+}
+
 static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, size_t* off_offset, size_t* off_cursor,
                                size_t* off_sorted) {
     size_t o = 0;
@@ -229,6 +285,12 @@ static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, siz
 }  // namespace mv3d
 
 using namespace mv3d;
+
+static bool raster_in_place_enabled() {   // MV3D_RASTER_INPLACE=0 keeps the tile pipeline for the float32 map (A/B)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MV3D_RASTER_INPLACE"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
 
 static int raster_impl(const float* d_points, int n_points, int point_stride, float* d_top, void* d_pad_hi,
                        void* d_pad_lo, int c_pad, int H, int W, int C, int nslices, const double* h_lo,
@@ -262,6 +324,8 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(n_tiles + 1), s);
     if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
     const int pgrid = n_points > 0 ? min(ceil_div(n_points, 256), 148 * 8) : 1;
+    // keys need index + 1 < 2^23 and a slice slot distinct from the intensity channel
+    const bool in_place = !pad && nslices < C && n_points < (1 << 23) - 1 && raster_in_place_enabled();
     {
         // output planes as 16-byte vectors (+ a scalar tail when the float32 map's size is not a multiple of 4)
         uint4 *va = nullptr, *vb = nullptr;
@@ -281,8 +345,16 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
                 return MV3D_ERR_ARG;  // torch allocations are 256-byte aligned; unaligned views are not supported
             }
         }
-        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, n_points, point_stride, g, count, va, na, vb, nb,
-                                                        tail, n_tail);
+        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, in_place ? 0 : n_points, point_stride, g, count, va, na,
+                                                        vb, nb, tail, n_tail);
+    }
+    if (in_place) {   // float32 map: the output is its own winner table (no binning)
+        if (n_points > 0) {
+            raster_mark_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, reinterpret_cast<unsigned int*>(d_top));
+            raster_resolve_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, d_top);
+        }
+        MV3D_CHECK_LAUNCH();
+        return MV3D_OK;
     }
     raster_scan_kernel<<<1, 1024, 0, s>>>(count, n_tiles, offset, cursor);
     if (n_points > 0)

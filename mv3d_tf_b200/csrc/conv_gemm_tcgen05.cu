@@ -114,7 +114,10 @@ __device__ __forceinline__ uint32_t cvt_pack_e5m2x2(float lo, float hi) {
     return r;
 }
 
-template <int BN, int ACC_COLS, bool PAIR = false>
+// LEAN: the forward-inference instantiation -- no split-K, addend, gate or timing-experiment paths and only the vector
+// stores (the host selects it when the descriptor allows); the dominant kernel's epilogue is a cold-code tail that
+// stalls on instruction fetch, so its footprint matters.
+template <int BN, int ACC_COLS, bool PAIR = false, bool LEAN = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tmem_base, int acc, int m0, int n0, int q,
                                               int half, int lane, uint64_t* tmem_full, uint64_t* tmem_empty, int tl,
                                               const float* bias_s) {
@@ -155,10 +158,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
     // One 32-column chunk: scale / bias / ReLU (/ addend / gate) -> operand rendering -> stores.
     auto process = [&](const uint32_t (&v)[32], const int c) {
     if (!in_range) return;
-    if (prm.dbg_flags & 4) return;   // MV3D_GEMM_DBG=4 (timing experiment): drain the accumulator, skip the math / stores
+    if (!LEAN && (prm.dbg_flags & 4)) return;   // MV3D_GEMM_DBG=4 (timing experiment): drain the accumulator, skip the math / stores
     const int col0 = n0 + c;
     if (col0 >= prm.N) return;
-    if (prm.split_k > 1) {
+    if (!LEAN && prm.split_k > 1) {
         if (halo) return;
         float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
 #pragma unroll
@@ -166,7 +169,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
             if (col0 + j < prm.N) atomicAdd(o + j, __uint_as_float(v[j]));
         return;
     }
-    const bool full = (col0 + 32 <= prm.N);
+    const bool full = LEAN || (col0 + 32 <= prm.N);
     float f[32];
     if (halo) {
 #pragma unroll
@@ -174,14 +177,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
     } else {
         const float sc = prm.acc_scale;
         const float* bsrc = bias_s != nullptr ? bias_s : prm.bias;   // generic loads: shared copy (N <= kBiasSmem) or global
-        if (prm.bias != nullptr && full) {
+        if (LEAN ? (prm.bias != nullptr) : (prm.bias != nullptr && full)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bsrc + col0 + j);
-                f[j] = __uint_as_float(v[j]) * sc + b4.x;
-                f[j + 1] = __uint_as_float(v[j + 1]) * sc + b4.y;
-                f[j + 2] = __uint_as_float(v[j + 2]) * sc + b4.z;
-                f[j + 3] = __uint_as_float(v[j + 3]) * sc + b4.w;
+                // acc_scale is 1 or 2^-12: the product is exact, so the fused multiply-add rounds exactly like mul + add
+                f[j] = __fmaf_rn(__uint_as_float(v[j]), sc, b4.x);
+                f[j + 1] = __fmaf_rn(__uint_as_float(v[j + 1]), sc, b4.y);
+                f[j + 2] = __fmaf_rn(__uint_as_float(v[j + 2]), sc, b4.z);
+                f[j + 3] = __fmaf_rn(__uint_as_float(v[j + 3]), sc, b4.w);
             }
         } else {
 #pragma unroll
@@ -195,7 +199,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (col0 < prm.softmax_cols) {   // (bg, fg) score pairs -> probabilities; same arithmetic as softmax_pairs_kernel
+        if (!LEAN && col0 < prm.softmax_cols) {   // (bg, fg) score pairs -> probabilities; same arithmetic as softmax_pairs_kernel
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 if (col0 + j + 1 < prm.softmax_cols) {
@@ -208,13 +212,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
             }
         }
     }
-    if (prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
+    if (!LEAN && prm.addend != nullptr && !halo) {  // second gradient path (dense rows), summed before the mask
         const float* ad = prm.addend + dense_row * prm.ld_addend + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             if (col0 + j < prm.N) f[j] += __ldg(ad + j);
     }
-    if (prm.mask_hi != nullptr && !halo) {  // ReLU / dropout gate of the forward activation
+    if (!LEAN && prm.mask_hi != nullptr && !halo) {  // ReLU / dropout gate of the forward activation
         const __nv_bfloat16* mk = prm.mask_hi + p * prm.ld_mask + col0;
         if (full && (prm.ld_mask % 8 == 0)) {
 #pragma unroll
@@ -267,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
     } else if (prm.out_hi != nullptr) {
         __nv_bfloat16* oh = prm.out_hi + p * prm.ld_out + col0;
         __nv_bfloat16* ol = prm.out_lo ? prm.out_lo + p * prm.ld_out + col0 : nullptr;
-        if (full && !(prm.dbg_flags & 8) && (prm.ld_out % 16 == 0) && ((reinterpret_cast<uintptr_t>(prm.out_hi) | reinterpret_cast<uintptr_t>(prm.out_lo)) & 31) == 0) {
+        if (LEAN || (full && !(prm.dbg_flags & 8) && (prm.ld_out % 16 == 0) && ((reinterpret_cast<uintptr_t>(prm.out_hi) | reinterpret_cast<uintptr_t>(prm.out_lo)) & 31) == 0)) {
             uint32_t ph[16], pl[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {   // = split_bf16 on two elements
@@ -307,7 +311,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
     }
     if (prm.out_f32 != nullptr && !(halo && prm.f32_dense)) {
         float* o = prm.out_f32 + (prm.f32_dense ? dense_row : p) * prm.ld_f32 + col0;
-        if (full && !(prm.dbg_flags & 8) && (prm.ld_f32 % 8 == 0) && (reinterpret_cast<uintptr_t>(prm.out_f32) & 31) == 0) {
+        if (LEAN || (full && !(prm.dbg_flags & 8) && (prm.ld_f32 % 8 == 0) && (reinterpret_cast<uintptr_t>(prm.out_f32) & 31) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) st_global_v8(o + j, reinterpret_cast<const uint32_t*>(f + j));
         } else if (full && (prm.ld_f32 % 4 == 0)) {
@@ -324,19 +328,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
     uint32_t va[32], vb[32];
     __syncwarp();
     tmem_ld_32x32(taddr_row + half * 32, va);
+    tmem_ld_wait_dep(va);
 #pragma unroll 1
-    for (int k = 0; k < n_mine; k += 2) {
-        tmem_ld_wait_dep(va);
+    for (int k = 0; k < n_mine; ++k) {
         __syncwarp();
         if (k + 1 < n_mine) tmem_ld_32x32(taddr_row + (half + 2 * (k + 1)) * 32, vb);
         else release();
-        process(va, (half + 2 * k) * 32);
-        if (k + 1 >= n_mine) break;
-        tmem_ld_wait_dep(vb);
-        __syncwarp();
-        if (k + 2 < n_mine) tmem_ld_32x32(taddr_row + (half + 2 * (k + 2)) * 32, va);
-        else release();
-        process(vb, (half + 2 * k + 2) * 32);
+        process(va, (half + 2 * k) * 32);          // ONE inlined copy of the rendering code (instruction-cache footprint)
+        if (k + 1 < n_mine) {
+            tmem_ld_wait_dep(vb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) va[j] = vb[j];
+        }
     }
 }
 
@@ -684,7 +687,7 @@ struct PairCfg {
     static_assert(BN % 16 == 0 && BN <= 256, "M=256 MMA: N multiple of 16, at most 256");
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool LEAN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -727,7 +730,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // hangs every few thousand launches under multi-stream load (cuda-gdb: CTA 0 past its alloc, lane 0 of CTA 1's
     // warp 1 spinning inside the alloc sequence).  For the same reason the pair's allocation permit is only given up
     // after both allocs have returned, and no CTA exits before both have run the dealloc sequence.
-    cluster_sync_all();
+    cluster_sync_relaxed();   // execution only: both CTAs are running
     if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA completion
@@ -833,18 +836,19 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 mbar_wait(&tmem_full[tl & 1], (tl >> 1) & 1);
                 stamp(prm, 4);   // last accumulator complete (MMAs retired)
             }
-            epilogue_tile<BN, Cfg::kAccCols, true>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
+            epilogue_tile<BN, Cfg::kAccCols, true, LEAN>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
         }
         if (warp == 2 && lane == 0) stamp(prm, 5);   // this warp's epilogue done
     }
     tc_fence_before();
-    cluster_sync_all();  // the leader's MMAs read the peer's shared memory / write its TMEM until the last commit
+    // (execution-only barriers: a release arrive = MEMBAR.ALL.GPU would wait for the epilogue's global stores to land)
+    cluster_sync_relaxed();  // the leader's MMAs read the peer's shared memory / write its TMEM until the last commit
     if (threadIdx.x == 0) stamp(prm, 6);   // all warps of both CTAs done
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
     }
-    cluster_sync_all();
+    cluster_sync_relaxed();
     if (threadIdx.x == 0) stamp(prm, 7);   // exit
 }
 
@@ -1038,8 +1042,8 @@ static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B com
     return g_pair_mode;
 }
 
-template <int BN, int PASSES>
-static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
+template <int BN, int PASSES, bool LEAN>
+static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     using Cfg = PairCfg<BN, PASSES>;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const uint64_t kcols = (uint64_t)9 * d->Cin;
@@ -1074,7 +1078,7 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
-    auto kern = conv3x3_pair_kernel<BN, PASSES>;
+    auto kern = conv3x3_pair_kernel<BN, PASSES, LEAN>;
     static int max_pairs = 0;  // per instantiation
     if (max_pairs == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -1091,6 +1095,20 @@ static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
     kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
+}
+
+// The forward-inference form of a descriptor (plain bias / ReLU epilogue, vector-store alignment) takes the LEAN kernel.
+static bool lean_epilogue_ok(const mv3d_gemm_desc* d) {
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    if (d->split_k > 1 || d->d_mask_hi || d->d_addend_f32 || d->softmax_cols > 0 || gemm_dbg_flags() != 0) return false;
+    if (d->d_out_hi && d->out_fmt == MV3D_FMT_BF16X2 && !(d->ld_out % 16 == 0 && al32(d->d_out_hi) && al32(d->d_out_lo))) return false;
+    if (d->d_out_f32 && !(d->ld_f32 % 8 == 0 && al32(d->d_out_f32))) return false;
+    return true;
+}
+
+template <int BN, int PASSES>
+static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    return lean_epilogue_ok(d) ? launch_pair_impl<BN, PASSES, true>(d, stream) : launch_pair_impl<BN, PASSES, false>(d, stream);
 }
 
 // CTA-pair tiles for the tap-reuse 3x3 convs whose channel count tiles exactly; pair tile N = min(N, 256).

@@ -122,6 +122,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only cluster barrier (no memory ordering): a release arrive is a MEMBAR.ALL.GPU, which at kernel teardown
+// stalls on every global store the epilogue still has in flight.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 // shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`.
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
