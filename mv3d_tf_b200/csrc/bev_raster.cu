@@ -17,6 +17,7 @@
 // Exact semantics kept: float32 division for the cell index then truncation toward zero,
 // float64 slice bounds lo[i] <= z < hi[i] tested for EVERY slice, height = z - h0 in float32,
 // intensity = reflectance of the last writer of the highest occupied slice.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -229,9 +230,9 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
 // ---- float32 output: mark / resolve in place ------------------------------------------------------------------
 constexpr unsigned int kKeyBase = 0xFF800000u;   // + (point index + 1) < 2^23: negative NaN patterns
 
-__global__ void raster_mark_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
-                                   unsigned int* __restrict__ top_bits) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void mark_points(const float* __restrict__ pts, int n, int stride, const RasterGeom& g,
+                                            unsigned int* __restrict__ top_bits, long long tid, long long nthr) {
+    for (long long i = tid; i < n; i += nthr) {
         const float* p = pts + (size_t)i * stride;
         const float4 q = (stride == 4) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(p[0], p[1], p[2], p[3]);
         int row, col;
@@ -245,10 +246,10 @@ __global__ void raster_mark_kernel(const float* __restrict__ pts, int n, int str
     }
 }
 
-__global__ void raster_resolve_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
-                                      float* __restrict__ top) {
+__device__ __forceinline__ void resolve_points(const float* __restrict__ pts, int n, int stride, const RasterGeom& g,
+                                               float* __restrict__ top, long long tid, long long nthr) {
     const unsigned int* bits = reinterpret_cast<const unsigned int*>(top);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (long long i = tid; i < n; i += nthr) {
         const float* p = pts + (size_t)i * stride;
         const float4 q = (stride == 4) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(p[0], p[1], p[2], p[3]);
         int row, col;
@@ -272,6 +273,34 @@ __global__ void raster_resolve_kernel(const float* __restrict__ pts, int n, int 
     }
 }
 
+__global__ void raster_mark_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                   unsigned int* __restrict__ top_bits) {
+    mark_points(pts, n, stride, g, top_bits, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+__global__ void raster_resolve_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
+                                      float* __restrict__ top) {
+    resolve_points(pts, n, stride, g, top, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// The three phases as ONE cooperative launch (all CTAs co-resident, grid-wide barriers instead of kernel boundaries):
+// zero fill at streaming-store speed -> mark -> resolve.
+__global__ void __launch_bounds__(512)
+raster_inplace_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g, float* __restrict__ top,
+                      long long vec4, int n_tail) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    uint4* out4 = reinterpret_cast<uint4*>(top);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long i = tid; i < vec4; i += nthr) __stcs(out4 + i, z);
+    if (tid < n_tail) top[vec4 * 4 + tid] = 0.f;
+    grid.sync();
+    mark_points(pts, n, stride, g, reinterpret_cast<unsigned int*>(top), tid, nthr);
+    grid.sync();
+    resolve_points(pts, n, stride, g, top, tid, nthr);
+}
+
 static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, size_t* off_offset, size_t* off_cursor,
                                size_t* off_sorted) {
     size_t o = 0;
@@ -286,11 +315,13 @@ static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, siz
 
 using namespace mv3d;
 
-static bool raster_in_place_enabled() {   // MV3D_RASTER_INPLACE=0 keeps the tile pipeline for the float32 map (A/B)
+// MV3D_RASTER_INPLACE: 0 keeps the tile pipeline for the float32 map, 1 (default) one cooperative launch, 2 three launches
+static int raster_in_place_mode() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MV3D_RASTER_INPLACE"); v = e ? atoi(e) : 1; }
-    return v != 0;
+    return v;
 }
+static bool raster_in_place_enabled() { return raster_in_place_mode() != 0; }
 
 static int raster_impl(const float* d_points, int n_points, int point_stride, float* d_top, void* d_pad_hi,
                        void* d_pad_lo, int c_pad, int H, int W, int C, int nslices, const double* h_lo,
@@ -321,11 +352,44 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
     int* cursor = reinterpret_cast<int*>(ws + ou);
     int* sorted = reinterpret_cast<int*>(ws + os);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(n_tiles + 1), s);
-    if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+    cudaError_t e;
     const int pgrid = n_points > 0 ? min(ceil_div(n_points, 256), 148 * 8) : 1;
     // keys need index + 1 < 2^23 and a slice slot distinct from the intensity channel
-    const bool in_place = !pad && nslices < C && n_points < (1 << 23) - 1 && raster_in_place_enabled();
+    const bool in_place = !pad && nslices < C && n_points < (1 << 23) - 1 && raster_in_place_enabled() &&
+                          (reinterpret_cast<uintptr_t>(d_top) & 15) == 0;
+    if (in_place) {   // float32 map: the output is its own winner table (no binning)
+        const long long elems = (long long)H * W * C;
+        long long vec4 = elems / 4;
+        int n_tail = (int)(elems - vec4 * 4);
+        static int coop_ctas = -1;   // co-resident CTAs of the one-launch form (0: not available)
+        if (coop_ctas < 0) {
+            int dev = 0, coop = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_inplace_kernel, 512, 0) == cudaSuccess && per_sm > 0)
+                { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); coop_ctas = sms * (per_sm > 2 ? 2 : per_sm); }
+            else
+                coop_ctas = 0;
+            cudaGetLastError();
+        }
+        if (coop_ctas > 0 && raster_in_place_mode() == 1) {
+            const float* a_pts = d_points; int a_n = n_points, a_stride = point_stride;
+            void* args[] = {&a_pts, &a_n, &a_stride, &g, &d_top, &vec4, &n_tail};
+            e = cudaLaunchCooperativeKernel((void*)raster_inplace_kernel, dim3(coop_ctas), dim3(512), args, 0, s);
+            if (e == cudaSuccess) return MV3D_OK;
+            cudaGetLastError();   // fall through to the three-launch form
+        }
+        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, 0, point_stride, g, count, reinterpret_cast<uint4*>(d_top), vec4,
+                                                        nullptr, 0, d_top + vec4 * 4, n_tail);
+        if (n_points > 0) {
+            raster_mark_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, reinterpret_cast<unsigned int*>(d_top));
+            raster_resolve_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, d_top);
+        }
+        MV3D_CHECK_LAUNCH();
+        return MV3D_OK;
+    }
+    e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)(n_tiles + 1), s);
+    if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
     {
         // output planes as 16-byte vectors (+ a scalar tail when the float32 map's size is not a multiple of 4)
         uint4 *va = nullptr, *vb = nullptr;
@@ -345,16 +409,8 @@ static int raster_impl(const float* d_points, int n_points, int point_stride, fl
                 return MV3D_ERR_ARG;  // torch allocations are 256-byte aligned; unaligned views are not supported
             }
         }
-        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, in_place ? 0 : n_points, point_stride, g, count, va, na,
-                                                        vb, nb, tail, n_tail);
-    }
-    if (in_place) {   // float32 map: the output is its own winner table (no binning)
-        if (n_points > 0) {
-            raster_mark_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, reinterpret_cast<unsigned int*>(d_top));
-            raster_resolve_kernel<<<pgrid, 256, 0, s>>>(d_points, n_points, point_stride, g, d_top);
-        }
-        MV3D_CHECK_LAUNCH();
-        return MV3D_OK;
+        raster_fill_count_kernel<<<148 * 8, 256, 0, s>>>(d_points, n_points, point_stride, g, count, va, na, vb, nb,
+                                                        tail, n_tail);
     }
     raster_scan_kernel<<<1, 1024, 0, s>>>(count, n_tiles, offset, cursor);
     if (n_points > 0)

@@ -282,6 +282,8 @@ class SolverWrapper(object):
             x = vals[src].pad
             K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
             K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
+            if self.exchange is not None:   # this layer's slice (and everything above it) is final: maybe a bucket
+                self.exchange.ready(self.grad, self.slices[node.name][0])
             if src.kind == 'placeholder':
                 continue
             gated = src.kind == 'conv'   # the dgrad epilogue applies the ReLU gate of the producing conv

@@ -46,28 +46,52 @@ def assign(frames: Sequence, rank: int, world: int) -> list:
 
 
 class FlatGradExchange:
-    """The training path's one exchange step: a sum over the flat fp32 gradient buffer, issued as two
-    collectives so that the tail of the buffer (the fusion head: fc6/fc7, finished first in backward) travels while the
-    trunks are still being differentiated.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    """The training path's one exchange step: a sum over the flat fp32 gradient buffer, issued as
+    BUCKETS while backward is still running.  Backward finalises the buffer from its tail to its head (fusion head
+    first, then the RPN, then the trunks last layer first), so `ready(buf, lo)` is called with a falling low-water
+    mark; whenever at least `bucket_bytes` of finished gradients have accumulated, that contiguous slice goes out as
+    one asynchronous all-reduce (NCCL: on the communicator's own stream, ordered after the producing kernels).  Nothing
+    blocks until `finish`, which flushes the remainder and makes the current stream wait for every bucket.  Works on
+    any backend (NCCL on the GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, bucket_bytes: int = 32 << 20):
         self.group = group
-        self._pending = None
+        self.bucket_bytes = int(bucket_bytes)
+        self._pending = []
+        self._hi = None          # elements [self._hi, end) are already on their way
+        self.buckets_last_step = 0
 
     @property
     def world(self) -> int:
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def start_tail(self, buf: torch.Tensor, off: int) -> None:
-        if self.world > 1 and off < buf.numel():
-            self._pending = dist.all_reduce(buf[off:], group=self.group, async_op=True)
+    def _send(self, buf: torch.Tensor, lo: int, hi: int) -> None:
+        if hi > lo:
+            self._pending.append(dist.all_reduce(buf[lo:hi], group=self.group, async_op=True))
 
-    def finish(self, buf: torch.Tensor, off: int) -> float:
-        """Reduce the head of the buffer, wait for the tail; returns the 1/world factor the optimizer applies."""
+    def ready(self, buf: torch.Tensor, lo: int, force: bool = False) -> None:
+        """Gradients in buf[lo:] are final."""
+        if self.world <= 1:
+            return
+        if self._hi is None:
+            self._hi = buf.numel()
+        lo = max(0, min(int(lo), self._hi))
+        if force or (self._hi - lo) * buf.element_size() >= self.bucket_bytes:
+            self._send(buf, lo, self._hi)
+            self._hi = lo
+
+    def start_tail(self, buf: torch.Tensor, off: int) -> None:   # the first bucket: everything from `off` to the end
+        self.ready(buf, off, force=True)
+
+    def finish(self, buf: torch.Tensor, off: int = 0) -> float:
+        """Send what is left, wait for every bucket; returns the 1/world factor the optimizer applies."""
         if self.world > 1:
-            if off > 0:
-                dist.all_reduce(buf[:off], group=self.group)
-            if self._pending is not None:
-                self._pending.wait()
-                self._pending = None
+            if self._hi is None:
+                self._hi = buf.numel()
+            self._send(buf, 0, self._hi)
+            self.buckets_last_step = len(self._pending)
+            for h in self._pending:
+                h.wait()
+            self._pending = []
+            self._hi = None
         return 1.0 / self.world

@@ -68,8 +68,15 @@ def _exchange_worker(rank, world, port, q):
     ex.start_tail(buf, off)                  # the head's gradients travel first ...
     buf[:off] += 0.5                         # ... while the "trunk backward" still writes its part
     scale = ex.finish(buf, off)
+    # bucketed form: backward hands over a falling low-water mark; slices go out whenever >= bucket_bytes are final
+    ex2 = FlatGradExchange(dist.group.WORLD, bucket_bytes=4 * 128)
+    b2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    marks = [900, 880, 700, 690, 400, 399, 120, 0]
+    for lo in marks:
+        ex2.ready(b2, lo)
+    ex2.finish(b2)
     if rank == 0:
-        q.put((buf.clone(), scale))
+        q.put((buf.clone(), scale, b2.clone(), ex2.buckets_last_step))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,10 +89,12 @@ def test_flat_gradient_exchange_two_ranks():
     procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    buf, scale = q.get(timeout=120)
+    buf, scale, b2, n_buckets = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     want = torch.arange(1000, dtype=torch.float32) * 3
     want[:300] += 1.0
     assert torch.equal(buf, want) and scale == 0.5
+    assert torch.equal(b2, torch.arange(1000, dtype=torch.float32) * 3)   # every element reduced exactly once
+    assert 3 <= n_buckets <= 6
