@@ -104,6 +104,8 @@ SIGNATURES = {
     "mv3d_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_pad_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_im2col3x3_pad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mv3d_conv3x3_small_cin": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                       c_void_p, c_int, c_int, c_void_p]),
     "mv3d_unpad_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mv3d_maxpool2x2_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mv3d_softmax_pairs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

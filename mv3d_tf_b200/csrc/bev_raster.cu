@@ -230,7 +230,15 @@ raster_tile_kernel(const float* __restrict__ pts, int stride, RasterGeom g, cons
 // ---- float32 output: mark / resolve in place ------------------------------------------------------------------
 constexpr unsigned int kKeyBase = 0xFF800000u;   // + (point index + 1) < 2^23: negative NaN patterns
 
+// (the slice bounds are read with a per-lane index: from shared memory -- the kernel-parameter constant bank would
+// serialise the divergent lanes)
+__device__ __forceinline__ void stage_bounds(const RasterGeom& g, double* slo, double* shi) {
+    for (int i = threadIdx.x; i < g.nslices; i += blockDim.x) { slo[i] = g.lo[i]; shi[i] = g.hi[i]; }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void mark_points(const float* __restrict__ pts, int n, int stride, const RasterGeom& g,
+                                            const double* slo, const double* shi,
                                             unsigned int* __restrict__ top_bits, long long tid, long long nthr) {
     for (long long i = tid; i < n; i += nthr) {
         const float* p = pts + (size_t)i * stride;
@@ -242,11 +250,12 @@ __device__ __forceinline__ void mark_points(const float* __restrict__ pts, int n
         slice_window(g, z, s_lo, s_hi);
         unsigned int* cell = top_bits + ((size_t)row * g.W + col) * g.C;
         for (int sl = s_lo; sl <= s_hi; ++sl)
-            if (z >= g.lo[sl] && z < g.hi[sl]) atomicMax(cell + sl, kKeyBase + (unsigned int)i + 1u);   // last index wins
+            if (z >= slo[sl] && z < shi[sl]) atomicMax(cell + sl, kKeyBase + (unsigned int)i + 1u);   // last index wins
     }
 }
 
 __device__ __forceinline__ void resolve_points(const float* __restrict__ pts, int n, int stride, const RasterGeom& g,
+                                               const double* slo, const double* shi,
                                                float* __restrict__ top, long long tid, long long nthr) {
     const unsigned int* bits = reinterpret_cast<const unsigned int*>(top);
     for (long long i = tid; i < n; i += nthr) {
@@ -260,7 +269,7 @@ __device__ __forceinline__ void resolve_points(const float* __restrict__ pts, in
         const size_t cell = ((size_t)row * g.W + col) * g.C;
         const unsigned int key = kKeyBase + (unsigned int)i + 1u;
         for (int sl = s_lo; sl <= s_hi; ++sl) {
-            if (!(z >= g.lo[sl] && z < g.hi[sl])) continue;
+            if (!(z >= slo[sl] && z < shi[sl])) continue;
             if (__ldcg(bits + cell + sl) != key) continue;           // another point wrote this (cell, slice) later
             // highest occupied slice of the cell?  Slots above hold 0 (empty), a key, or a height > 0 -- never 0 once
             // occupied (slice sl' >= 1 starts at h0 + sl' * zres), whichever of its two states a slot is in right now.
@@ -275,12 +284,16 @@ __device__ __forceinline__ void resolve_points(const float* __restrict__ pts, in
 
 __global__ void raster_mark_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
                                    unsigned int* __restrict__ top_bits) {
-    mark_points(pts, n, stride, g, top_bits, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+    __shared__ double slo[kMaxSlices], shi[kMaxSlices];
+    stage_bounds(g, slo, shi);
+    mark_points(pts, n, stride, g, slo, shi, top_bits, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 __global__ void raster_resolve_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g,
                                       float* __restrict__ top) {
-    resolve_points(pts, n, stride, g, top, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+    __shared__ double slo[kMaxSlices], shi[kMaxSlices];
+    stage_bounds(g, slo, shi);
+    resolve_points(pts, n, stride, g, slo, shi, top, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 // The three phases as ONE cooperative launch (all CTAs co-resident, grid-wide barriers instead of kernel boundaries):
@@ -289,6 +302,8 @@ __global__ void __launch_bounds__(512)
 raster_inplace_kernel(const float* __restrict__ pts, int n, int stride, RasterGeom g, float* __restrict__ top,
                       long long vec4, int n_tail) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double slo[kMaxSlices], shi[kMaxSlices];
+    stage_bounds(g, slo, shi);
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
     uint4* out4 = reinterpret_cast<uint4*>(top);
@@ -296,9 +311,9 @@ raster_inplace_kernel(const float* __restrict__ pts, int n, int stride, RasterGe
     for (long long i = tid; i < vec4; i += nthr) __stcs(out4 + i, z);
     if (tid < n_tail) top[vec4 * 4 + tid] = 0.f;
     grid.sync();
-    mark_points(pts, n, stride, g, reinterpret_cast<unsigned int*>(top), tid, nthr);
+    mark_points(pts, n, stride, g, slo, shi, reinterpret_cast<unsigned int*>(top), tid, nthr);
     grid.sync();
-    resolve_points(pts, n, stride, g, top, tid, nthr);
+    resolve_points(pts, n, stride, g, slo, shi, top, tid, nthr);
 }
 
 static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, size_t* off_offset, size_t* off_cursor,
@@ -315,10 +330,11 @@ static size_t raster_ws_layout(int n_points, int n_tiles, size_t* off_count, siz
 
 using namespace mv3d;
 
-// MV3D_RASTER_INPLACE: 0 keeps the tile pipeline for the float32 map, 1 (default) one cooperative launch, 2 three launches
+// MV3D_RASTER_INPLACE: 0 keeps the tile pipeline for the float32 map, 2 (default) three launches, 1 one cooperative
+// launch (measured: the two grid-wide barriers cost more than the two kernel boundaries they replace)
 static int raster_in_place_mode() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("MV3D_RASTER_INPLACE"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("MV3D_RASTER_INPLACE"); v = e ? atoi(e) : 2; }
     return v;
 }
 static bool raster_in_place_enabled() { return raster_in_place_mode() != 0; }

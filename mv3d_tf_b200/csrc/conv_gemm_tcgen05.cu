@@ -666,7 +666,10 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 // multicasts the "slot free" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both CTAs
 // arrive on the leader's tmem_empty barrier (count 8).
 // ------------------------------------------------------------------------------------------------
-template <int BN, int PASSES>
+// WRES (64 -> 64 channel layers: conv1_2, BEV conv1_1): all nine weight taps of the layer (72 KB per CTA) are loaded
+// ONCE and stay resident while the persistent CTA pair walks its ~30 tiles.  These layers are bound by the L2 -> SM
+// operand feed (176 KB per tile and CTA at ~37 B/clk/SM of the ~43 the chip delivers); the weights were 41 % of it.
+template <int BN, int PASSES, bool WRES = false>
 struct PairCfg {
     static constexpr int kOperands = (PASSES >= 2) ? 2 : 1;
     static constexpr int kAPlane = 18 * 1024;
@@ -678,21 +681,22 @@ struct PairCfg {
     static constexpr int kNA = (BN <= 64 ? 3 : 2) * (PASSES >= 2 ? 1 : 2);
     static constexpr int kBudget = 200 * 1024;
     static constexpr int kNWRaw = (kBudget - kNA * kAEntry) / kWEntry;
-    static constexpr int kNW = kNWRaw > 8 ? 8 : kNWRaw;
+    static constexpr int kNW = WRES ? 9 : (kNWRaw > 8 ? 8 : kNWRaw);   // WRES: entry = tap, never recycled
     static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512 + 4 * 512 /*bias*/;
     static constexpr int kAccCols = BN < 32 ? 32 : BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static_assert(kNW >= 3, "W ring too shallow");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory");
     static_assert(kTmemCols <= 512, "TMEM has 512 columns");
     static_assert(BN % 16 == 0 && BN <= 256, "M=256 MMA: N multiple of 16, at most 256");
 };
 
-template <int BN, int PASSES, bool LEAN = false>
+template <int BN, int PASSES, bool LEAN = false, bool WRES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const GemmParams prm) {
-    using Cfg = PairCfg<BN, PASSES>;
+    using Cfg = PairCfg<BN, PASSES, WRES>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic window starts at the same offset in both CTAs, so the aligned pointers are at equal offsets too
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -765,8 +769,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     if (PASSES >= 2) tma_load_2d_pair(ab + Cfg::kAPlane, &map_a_lo, afull, c0, arow);
                     }
                     for (int kw = 0; kw < 3; ++kw, ++iw) {
+                        if (WRES && iw >= 9) continue;             // the nine taps are resident after the first tile
                         const int ew = iw % Cfg::kNW;
-                        mbar_wait(&w_empty[ew], ((iw / Cfg::kNW) & 1) ^ 1);
+                        if (!WRES) mbar_wait(&w_empty[ew], ((iw / Cfg::kNW) & 1) ^ 1);
                         uint8_t* wb = w_ring + ew * Cfg::kWEntry;
                         const uint32_t wfull = mapa_u32(smem_u32(&w_full[ew]), 0);
                         if ((prm.dbg_flags & 1) && iw >= Cfg::kNW) {
@@ -799,8 +804,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     // descriptor low words: base of this A entry, advanced by whole rows (kw) and along K (k) with adds
                     const uint32_t da_base = kmajor_desc_lo(smem_u32(a_ring + ea * Cfg::kAEntry));
                     for (int kw = 0; kw < 3; ++kw, ++iw) {
-                        const int ew = iw % Cfg::kNW;
-                        mbar_wait(&w_full[ew], (iw / Cfg::kNW) & 1);
+                        const int ew = WRES ? g * 3 + kw : iw % Cfg::kNW;   // WRES: one 64-channel chunk, g = kh
+                        mbar_wait(&w_full[ew], WRES ? 0u : (uint32_t)((iw / Cfg::kNW) & 1));
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t da_kw = da_base + kw * (128 >> 4);
@@ -816,7 +821,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 if (PASSES == 2)
                                     mma_f8_pair_lo(d_tmem, da + (Cfg::kAPlane >> 4), db + (Cfg::kWPlane >> 4), idesc8, 1u);
                             }
-                            mma_commit_pair(&w_empty[ew], 3);
+                            if (!WRES) mma_commit_pair(&w_empty[ew], 3);
                             if (kw == 2) mma_commit_pair(&a_empty[ea], 3);
                             if (kw == 2 && g == n_groups - 1) mma_commit_pair(&tmem_full[acc], 3);
                         }
@@ -1042,9 +1047,9 @@ static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B com
     return g_pair_mode;
 }
 
-template <int BN, int PASSES, bool LEAN>
+template <int BN, int PASSES, bool LEAN, bool WRES = false>
 static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
-    using Cfg = PairCfg<BN, PASSES>;
+    using Cfg = PairCfg<BN, PASSES, WRES>;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const uint64_t kcols = (uint64_t)9 * d->Cin;
     int rc;
@@ -1078,7 +1083,7 @@ static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
-    auto kern = conv3x3_pair_kernel<BN, PASSES, LEAN>;
+    auto kern = conv3x3_pair_kernel<BN, PASSES, LEAN, WRES>;
     static int max_pairs = 0;  // per instantiation
     if (max_pairs == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -1106,8 +1111,19 @@ static bool lean_epilogue_ok(const mv3d_gemm_desc* d) {
     return true;
 }
 
+static int g_wres_mode = -1;
+static bool wres_mode() {   // MV3D_WRES=0: weights through the ring also in the 64 -> 64 layers (A/B comparisons)
+    if (g_wres_mode < 0) { const char* e = getenv("MV3D_WRES"); g_wres_mode = e ? atoi(e) : 1; }
+    return g_wres_mode != 0;
+}
+
 template <int BN, int PASSES>
 static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    if constexpr (BN == 64 && PASSES >= 2) {
+        if (d->Cin == 64 && wres_mode())
+            return lean_epilogue_ok(d) ? launch_pair_impl<BN, PASSES, true, true>(d, stream)
+                                       : launch_pair_impl<BN, PASSES, false, true>(d, stream);
+    }
     return lean_epilogue_ok(d) ? launch_pair_impl<BN, PASSES, true>(d, stream) : launch_pair_impl<BN, PASSES, false>(d, stream);
 }
 

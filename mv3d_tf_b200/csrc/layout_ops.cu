@@ -152,6 +152,85 @@ __global__ void im2col3x3_pad_kernel(const float* __restrict__ in, int B, int H,
     }
 }
 
+// First conv layer of an image-like input with a handful of channels (RGB / front view: Cin = 3, K = 27): 1.6 of the
+// frame's 920 GFLOP, but as a tensor-core GEMM it is an im2col pass plus a K = 32 GEMM whose time is all epilogue
+// (82 us together at 375x1242).  Here it is ONE direct kernel: 8 lanes per output pixel, each lane 8 output channels;
+// the 27 inputs are the same addresses for the 8 lanes (L1 broadcast), the weights sit in shared memory as
+// [tap*Cin + c][cout]; fp32 FMA accumulation in tap order, + bias, ReLU, then the consumer's operand rendering (f16e5
+// or bf16 hi/lo) with 16-byte stores straight into the PAD layout, halo pixels zero.  Bound by its 4 B/element output.
+template <int FMT>
+__global__ void __launch_bounds__(256)
+conv3x3_small_cin_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ w_hwio,
+                         const float* __restrict__ bias, int Cout, int relu, void* __restrict__ out_hi,
+                         void* __restrict__ out_lo, int c_pad) {
+    extern __shared__ float wsm[];                 // [9*C][Cout] + bias[Cout]
+    const int K = 9 * C;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) wsm[i] = w_hwio[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[K * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const float* bsm = wsm + K * Cout;
+    const int Hp = H + 1, Wp = W + 1, groups = c_pad / 8;
+    const long long total = (long long)B * Hp * Wp * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int gq = (int)(i % groups);
+        const long long pix = i / groups;
+        const int wp = (int)(pix % Wp);
+        const long long r = pix / Wp;
+        const int hp = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        const int co = gq * 8;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const bool inside = wp > 0 && hp < H && co < Cout;
+        if (inside) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = bsm[co + e];
+            const int h = hp, w = wp - 1;
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hh = h + kh - 1;
+                if (hh < 0 || hh >= H) continue;
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ww = w + kw - 1;
+                    if (ww < 0 || ww >= W) continue;
+                    const float* px = in + (((long long)b * H + hh) * W + ww) * C;
+                    const float* wt = wsm + (size_t)((kh * 3 + kw) * C) * Cout + co;
+                    for (int c = 0; c < C; ++c) {
+                        const float x = __ldg(px + c);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)c * Cout);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)c * Cout + 4);
+                        acc[0] = __fmaf_rn(x, w0.x, acc[0]); acc[1] = __fmaf_rn(x, w0.y, acc[1]);
+                        acc[2] = __fmaf_rn(x, w0.z, acc[2]); acc[3] = __fmaf_rn(x, w0.w, acc[3]);
+                        acc[4] = __fmaf_rn(x, w1.x, acc[4]); acc[5] = __fmaf_rn(x, w1.y, acc[5]);
+                        acc[6] = __fmaf_rn(x, w1.z, acc[6]); acc[7] = __fmaf_rn(x, w1.w, acc[7]);
+                    }
+                }
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+            }
+        }
+        if (FMT == MV3D_FMT_F16E5) {
+            unsigned short hh16[8];
+            uint8_t h8[8], l8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_f16e5(acc[e], hh16[e], h8[e], l8[e]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(hh16);
+            uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + pix * c_pad * 2 + f16e5_off(co);
+            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<uint2*>(h8);
+            *reinterpret_cast<uint2*>(row + 64) = *reinterpret_cast<uint2*>(l8);
+        } else {
+            __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(acc[e], vh[e], vl[e]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vh);
+            if (out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vl);
+        }
+    }
+}
+
 __global__ void unpad_nhwc_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, int B,
                                   int H, int W, int C, int c_pad, float* __restrict__ out) {
     const int Hp = H + 1, Wp = W + 1;
@@ -524,6 +603,29 @@ extern "C" __attribute__((visibility("default"))) int mv3d_bias_act(const float*
     bias_act_kernel<<<grid_for((long long)M * N, 256), 256, 0, (cudaStream_t)stream>>>(
         d_acc, M, N, ld_acc, d_bias, relu, (__nv_bfloat16*)d_out_hi, (__nv_bfloat16*)d_out_lo, ld_out, d_out_f32,
         ld_f32);
+    MV3D_CHECK_LAUNCH();
+    return MV3D_OK;
+}
+
+/* Direct 3x3 SAME conv (+bias, +ReLU) of a dense float32 (B,H,W,C) input with C <= 4 into the PAD layout in `fmt`
+ * (Network.conv on the RGB / front-view image, lib/networks/network.py:108-132 with MV3D_test.py:51): replaces
+ * mv3d_im2col3x3_pad + the K = 32 GEMM in inference.  d_w: HWIO (3,3,C,Cout) float32; Cout % 8 == 0, c_pad >= Cout. */
+extern "C" __attribute__((visibility("default"))) int mv3d_conv3x3_small_cin(
+    const float* d_in, int B, int H, int W, int C, const float* d_w, const float* d_bias, int Cout, int relu,
+    void* d_out_hi, void* d_out_lo, int c_pad, int fmt, void* stream) {
+    MV3D_REQUIRE(d_in && d_w && d_out_hi && B > 0 && H > 0 && W > 0 && C > 0 && C <= 4 && Cout > 0 && Cout % 8 == 0);
+    MV3D_REQUIRE(c_pad >= Cout && c_pad % 8 == 0);
+    MV3D_REQUIRE(fmt == MV3D_FMT_BF16X2 || (fmt == MV3D_FMT_F16E5 && d_out_lo && c_pad % 64 == 0));
+    const size_t smem = sizeof(float) * ((size_t)9 * C * Cout + Cout);
+    MV3D_REQUIRE(smem <= 48 * 1024);
+    const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
+    const int grid = grid_for(total, 256);
+    if (fmt == MV3D_FMT_F16E5)
+        conv3x3_small_cin_kernel<MV3D_FMT_F16E5><<<grid, 256, smem, (cudaStream_t)stream>>>(d_in, B, H, W, C, d_w, d_bias, Cout, relu,
+                                                                                          d_out_hi, d_out_lo, c_pad);
+    else
+        conv3x3_small_cin_kernel<MV3D_FMT_BF16X2><<<grid, 256, smem, (cudaStream_t)stream>>>(d_in, B, H, W, C, d_w, d_bias, Cout, relu,
+                                                                                           d_out_hi, d_out_lo, c_pad);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -31,14 +31,20 @@ __device__ __forceinline__ float4 load_box(const float* boxes, int stride, int i
     return make_float4(p[0], p[1], p[2], p[3]);
 }
 
+// thresh_ge = the smallest float32 t with (double)t >= thresh, so that `(double)ovr >= thresh` (cpu_nms.pyx:65) is the
+// single float compare `ovr >= t`; thresh_gt = (float)thresh for the CUDA rule `ovr > 0.7f` (nms_kernel.cu:31,71).
+// `positive` (thresh > 0, uniform): boxes that do not intersect have inter = 0 and ovr = +-0 or NaN, which never reaches
+// a positive threshold -- the division (most of the work: random pairs rarely intersect) is skipped for them.
 __device__ __forceinline__ bool suppresses(const float4 a, const float a_area, const float4 b, const float b_area,
-                                           const int rule_ge, const double thresh, const float thresh_f) {
+                                           const int rule_ge, const float thresh_ge, const float thresh_gt,
+                                           const bool positive) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
     const float w = fmaxf(0.f, xx2 - xx1 + 1.f), h = fmaxf(0.f, yy2 - yy1 + 1.f);
+    if (positive && !(w > 0.f && h > 0.f)) return false;
     const float inter = w * h;
     const float ovr = inter / (a_area + b_area - inter);
-    return rule_ge ? ((double)ovr >= thresh) : (ovr > thresh_f);
+    return rule_ge ? (ovr >= thresh_ge) : (ovr > thresh_gt);
 }
 
 __global__ void __launch_bounds__(kMaskThreads)
@@ -69,7 +75,10 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_max, int stride, const in
     const float4 b0 = v0 ? load_box(boxes, stride, c0) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b1 = v1 ? load_box(boxes, stride, c1) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float area0 = (b0.z - b0.x + 1.f) * (b0.w - b0.y + 1.f), area1 = (b1.z - b1.x + 1.f) * (b1.w - b1.y + 1.f);
-    const float thresh_f = (float)thresh;
+    const float thresh_gt = (float)thresh;
+    float thresh_ge = (float)thresh;
+    if ((double)thresh_ge < thresh) thresh_ge = nextafterf(thresh_ge, INFINITY);
+    const bool positive = thresh > 0.0;
     const bool diagonal = row_blk == col_blk;
     __syncthreads();
     unsigned long long mine = 0;
@@ -78,8 +87,8 @@ nms_mask_kernel(const float* __restrict__ boxes, int n_max, int stride, const in
         const int rt = warp * 8 + r;                      // row inside the tile
         const float4 a = rbox[rt];
         const float a_area = rarea[rt];
-        bool s0 = v0 && suppresses(a, a_area, b0, area0, rule_ge, thresh, thresh_f);
-        bool s1 = v1 && suppresses(a, a_area, b1, area1, rule_ge, thresh, thresh_f);
+        bool s0 = v0 && suppresses(a, a_area, b0, area0, rule_ge, thresh_ge, thresh_gt, positive);
+        bool s1 = v1 && suppresses(a, a_area, b1, area1, rule_ge, thresh_ge, thresh_gt, positive);
         if (diagonal) { s0 = s0 && lane > rt; s1 = s1 && lane + 32 > rt; }   // only later boxes can be suppressed
         const unsigned lo = __ballot_sync(0xffffffffu, s0), hi = __ballot_sync(0xffffffffu, s1);
         if (lane == r) mine = ((unsigned long long)hi << 32) | lo;
@@ -99,6 +108,7 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, int n_max, const 
                   int max_keep, int* __restrict__ keep_out, int* __restrict__ num_out) {
     extern __shared__ unsigned long long diag[];               // [kSuper][kSuperWords]
     __shared__ unsigned long long cur_s[kSuperWords];
+    __shared__ int kept_s[kSuper];                             // kept candidates of the current super-block
     __shared__ int count_s;
     int n = n_max;
     if (d_n) n = min(n, *d_n);
@@ -127,26 +137,30 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, int n_max, const 
             if (acc) atomicOr(&cur_s[w], acc);
         }
         __syncthreads();
-        if (warp == 0) {   // resolve: one step per kept box
-            unsigned long long cur = ~0ull;
-            if (lane < nw) {
-                cur = cur_s[lane];
-                const int valid = rows - lane * kNmsTile;       // candidates of this word that exist
+        if (warp == 0) {
+            // Resolve with the whole warp in lock-step (uniform registers, no ballots on the chain): inside one 64-candidate
+            // word the chain is ffs -> one broadcast shared-memory load of the kept row's word -> OR (~45 cycles per KEPT
+            // box); moving on to the next word, the lanes OR the rows of this super-block's kept boxes for that word in
+            // parallel (two 32-bit warp OR-reductions).
+            int c = cnt, m = 0;                                      // kept so far overall / in this super-block
+            for (int w = 0; w < nw && c < max_keep; ++w) {
+                unsigned long long acc = 0;                          // suppression of word w by this super-block's kept boxes
+                for (int i = lane; i < m; i += 32) acc |= diag[kept_s[i] * kSuperWords + w];
+                const unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)acc);
+                const unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(acc >> 32));
+                unsigned long long cur = cur_s[w] | ((unsigned long long)hi32 << 32) | lo32;
+                const int valid = rows - w * kNmsTile;               // candidates of this word that exist
                 if (valid < kNmsTile) cur |= valid <= 0 ? ~0ull : (~0ull << valid);
-            }
-            int c = cnt;
-            while (c < max_keep) {
-                const unsigned long long avail = ~cur;          // not suppressed, not yet visited
-                const unsigned has = __ballot_sync(0xffffffffu, avail != 0ull);
-                if (has == 0u) break;
-                const int src = __ffs(has) - 1;
-                const unsigned long long a = __shfl_sync(0xffffffffu, avail, src);
-                const int bit = __ffsll((long long)a) - 1;
-                const int k = src * kNmsTile + bit;
-                if (lane == 0) keep_out[c] = base + k;
-                ++c;
-                if (lane < kSuperWords) cur |= diag[k * kSuperWords + lane];
-                if (lane == src) cur |= 1ull << bit;
+                while (c < max_keep) {
+                    const unsigned long long avail = ~cur;           // not suppressed, not yet visited
+                    if (avail == 0ull) break;
+                    const int bit = __ffsll((long long)avail) - 1;
+                    const int k = w * kNmsTile + bit;
+                    if (lane == 0) { keep_out[c] = base + k; kept_s[m] = k; }
+                    ++c; ++m;
+                    cur |= diag[k * kSuperWords + w] | (1ull << bit);
+                }
+                __syncwarp();                                        // kept_s of this word visible to all lanes
             }
             if (lane == 0) count_s = c;
         }

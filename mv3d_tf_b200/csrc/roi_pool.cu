@@ -10,12 +10,12 @@
 // clamp to [0,H]/[0,W], empty bin -> 0 / argmax -1, strict '>' so the first maximum in (h,w) order wins,
 // argmax = (h*W + w)*C + c inside the roi's image.
 //
-// roi_pool_fused_kernel (the inference path, north-star (iv)): ONE launch pools every view.  One CTA per (roi, view):
-// thread 0 PROJECTS the 3-D proposal into its view's plane in the kernel (BEV box + clip, 8-corner image box, FV box:
-// geom.cuh, the same device functions the proposal layer uses) -- or takes a given rectangle; the CTA then STAGES the
-// roi's whole window (all bins' cells, each read from global memory exactly once, 128-bit coalesced) in shared memory,
-// in channel slices when the window is large, and every 8-channel lane renders bins from shared memory: first maximum
-// in (h, w) order, split into the bf16 hi/lo operand of fc6 and written with 16-byte stores.
+// roi_pool_fused_kernel (the inference path, north-star (iv)): ONE launch pools every view.  One CTA per (roi, view,
+// 64-channel slice): thread 0 PROJECTS the 3-D proposal into its view's plane in the kernel (BEV box + clip, 8-corner
+// image box, FV box: geom.cuh, the same device functions the proposal layer uses) -- or takes a given rectangle; the
+// CTA then STAGES its slice of the roi's whole window (all bins' cells, each read from global memory exactly once,
+// 128-bit coalesced, one round of independent loads) in shared memory and every 8-channel lane renders bins from
+// shared memory: first maximum in (h, w) order, split into the bf16 hi/lo operand of fc6, written with 16-byte stores.
 #include <float.h>
 
 #include "common.cuh"
@@ -144,7 +144,8 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ top_diff, const in
 
 // ---- fused multi-view kernel -------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 256;
-constexpr int kStageBytes = 54 * 1024;   // shared-memory window slice; 4 CTAs per SM
+constexpr int kSliceC = 64;              // channels per CTA (grid.z = C / 64): 8x the CTAs of one-per-roi
+constexpr int kStageBytes = 27 * 1024;   // shared-memory window slice: 108 cells x 64 channels; 8 CTAs per SM
 
 __device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* v) {
     uint4 r;
@@ -155,7 +156,10 @@ __device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* v) {
     return r;
 }
 
-// grid (R, n_views), C % 8 == 0.  Rows >= *d_num_valid: zero outputs, argmax -1, zero rectangle.
+// grid (R, n_views, ceil(C / 64)), C % 8 == 0.  Rows >= *d_num_valid: zero outputs, argmax -1, zero rectangle.
+// One CTA = one roi x one view x one 64-channel slice: the window's cells of that slice are staged in shared memory
+// in ONE round of independent 128-bit loads (narrower channel sub-slices when the window has more than 108 cells,
+// direct reads beyond 864), then 8-channel lanes render the 49 bins from shared memory.
 __global__ void __launch_bounds__(kFusedThreads)
 roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__ rois_3d, int R,
                       const int* __restrict__ d_num_valid, int C, int PH, int PW) {
@@ -163,6 +167,7 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
     __shared__ float roi_s[5];
     const RoiViewDev& V = views.v[blockIdx.y];
     const int n = blockIdx.x, tid = threadIdx.x;
+    const int c_lo = blockIdx.z * kSliceC, c_hi = min(C, c_lo + kSliceC);   // this CTA's channels
     const bool valid = d_num_valid ? (n < *d_num_valid) : true;
     if (tid == 0) {
         float roi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -191,18 +196,19 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
         }
 #pragma unroll
         for (int q = 0; q < 5; ++q) roi_s[q] = roi[q];
-        if (V.rois_out) {
+        if (V.rois_out && blockIdx.z == 0) {
 #pragma unroll
             for (int q = 0; q < 5; ++q) V.rois_out[(size_t)n * 5 + q] = roi[q];
         }
     }
     __syncthreads();
     const int nbins = PH * PW;
-    const int lanes_all = C / 8;
     const size_t roi_base = (size_t)n * nbins * C;
     if (!valid) {
-        for (int item = tid; item < nbins * lanes_all; item += kFusedThreads) {
-            const size_t o = roi_base + (size_t)item * 8;
+        const int lanes = (c_hi - c_lo) / 8;
+        for (int item = tid; item < nbins * lanes; item += kFusedThreads) {
+            const int bin = item / lanes, lane = item - bin * lanes;
+            const size_t o = roi_base + (size_t)bin * C + c_lo + lane * 8;
             if (V.top) { *reinterpret_cast<float4*>(V.top + o) = make_float4(0, 0, 0, 0); *reinterpret_cast<float4*>(V.top + o + 4) = make_float4(0, 0, 0, 0); }
             if (V.argmax) { *reinterpret_cast<int4*>(V.argmax + o) = make_int4(-1, -1, -1, -1); *reinterpret_cast<int4*>(V.argmax + o + 4) = make_int4(-1, -1, -1, -1); }
             if (V.top_hi) *reinterpret_cast<uint4*>(V.top_hi + o) = make_uint4(0, 0, 0, 0);
@@ -224,18 +230,19 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
     const int wh = max(h1 - h0, 0), ww = max(w1 - w0, 0);
     const int cells = wh * ww;
     const float* img = V.data + (size_t)batch * H * W * C;
-    // channel slice: as many channels (multiple of 8) as fit the stage next to `cells` window cells
-    int Cs = C;
+    // channel sub-slice: as many of this CTA's channels (multiple of 8) as fit the stage next to `cells` window cells
+    const int Cmine = c_hi - c_lo;
+    int Cs = Cmine;
     if (cells > 0) {
         const int fit = (kStageBytes / 4) / cells;     // floats per cell that fit
-        Cs = fit >= C ? C : (fit / 8) * 8;
+        Cs = fit >= Cmine ? Cmine : (fit / 8) * 8;
     }
-    const bool staged = Cs >= 32;                       // at least 128-byte cell slices
-    if (!staged) Cs = C;                                // very large window (> 432 cells): read global memory directly
-    for (int cb = 0; cb < C; cb += Cs) {
-        const int cs = min(Cs, C - cb), v4 = cs / 4, lanes = cs / 8;
+    const bool staged = Cs >= 8;
+    if (!staged) Cs = Cmine;                            // very large window (> 864 cells): read global memory directly
+    for (int cb = c_lo; cb < c_hi; cb += Cs) {
+        const int cs = min(Cs, c_hi - cb), v4 = cs / 4, lanes = cs / 8;
         if (staged && cells > 0) {
-            __syncthreads();                            // previous slice fully consumed
+            __syncthreads();                            // previous sub-slice fully consumed
             for (int idx = tid; idx < cells * v4; idx += kFusedThreads) {
                 const int cell = idx / v4, v = idx - cell * v4;
                 const int h = h0 + cell / ww, w = w0 + cell % ww;
@@ -338,7 +345,7 @@ static int launch_fused(const RoiViews& v, int n_views, const RoiProjDev& proj, 
         if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
         attr_set = true;
     }
-    roi_pool_fused_kernel<<<dim3(R, n_views), kFusedThreads, kStageBytes, s>>>(v, proj, d_rois_3d, R, d_num_valid, C, PH, PW);
+    roi_pool_fused_kernel<<<dim3(R, n_views, ceil_div(C, kSliceC)), kFusedThreads, kStageBytes, s>>>(v, proj, d_rois_3d, R, d_num_valid, C, PH, PW);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

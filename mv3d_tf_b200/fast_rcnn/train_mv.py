@@ -59,6 +59,9 @@ class SolverWrapper(object):
         net._on_weights_changed.append(self._dpacked.clear)   # Network.load on a live solver (resume)
         self.loss = torch.zeros(4, dtype=torch.float32, device=net.device)  # rpn_cls, rpn_box, cls, box
         self.last_grad_events = None
+        self._side = None
+        if self.exchange is not None:
+            self._set_exchange_regions()
 
     # ------------------------------------------------------------------ parameters
     def _flatten_parameters(self):
@@ -102,6 +105,19 @@ class SolverWrapper(object):
         self._head_off = self.slices['fc6_1'][0] if 'fc6_1' in self.slices else total
         assert all(self.slices[n][0] >= self._head_off for n in self.names if n.startswith(('fc', 'cls_score', 'bbox_pred')))
         assert all(self.slices[n][0] < self._head_off for n in self.names if n.startswith(('conv', 'rpn')))
+
+    def _set_exchange_regions(self):
+        """Gradient-buffer regions by producing stream: the side-stream trunk's parameters, and everything else."""
+        net = self.net
+        side_names = [n.name for n in net._program if n.kind == 'conv' and n.attrs.get('side') and n.name in self.slices]
+        if not side_names or not net.use_side_stream:
+            self.exchange.set_regions({})
+            return
+        lo = min(self.slices[n][0] for n in side_names)
+        hi = max(self.slices[n][0] + (self.slices[n][1] + self.slices[n][2] + 3) // 4 * 4 for n in side_names)
+        total = self.theta.numel()
+        # [0, lo) main-stream trunk, [lo, hi) side-stream trunk, [hi, total) RPN + head (main stream, finished first)
+        self.exchange.set_regions({'low': (0, lo), 'side': (lo, hi), 0: (hi, total)})
 
     def export_params(self):
         """{layer: {'weights', 'biases'}} numpy dict in the reference's variable layouts (the `.npy` format of
@@ -162,6 +178,14 @@ class SolverWrapper(object):
                 net.calib: blobs['calib']}
         fetch = ['cls_score', 'bbox_pred', 'rpn_cls_score', 'rpn_bbox_pred', 'rpn_data', 'roi_data_3d']
         net.training = True
+        bv = blobs['lidar_bv_data']
+        if hasattr(bv, 'B'):
+            B, Hb, Wb = bv.B, bv.H, bv.W
+        else:
+            B, Hb, Wb = int(bv.shape[0]), int(bv.shape[1]), int(bv.shape[2])
+        # the RPN targets do not depend on the network: compute them (and take their host sync) off the critical path
+        net.precompute_anchor_targets(B, Hb // 2 // 2 // 2, Wb // 2 // 2 // 2, 8, blobs['gt_boxes_bv'], blobs['gt_boxes_3d'],
+                                      blobs['im_info'])
         net.run([_node(net, f) for f in fetch], feed)
         vals = net.last_vals
         self.grad.zero_()
@@ -259,37 +283,64 @@ class SolverWrapper(object):
                         precise=precise, out_pad=True, mask=rc, use_bias=False)
 
         # ---------------- trunks, last layer first ----------------
+        # The two trunks are independent below conv5: the RGB trunk's backward runs on a side stream next to the BEV
+        # trunk's (forward does the same), and each hands its finished gradient slices to the exchange on its own stream.
         grads: Dict[Node, K.PadAct] = {_node(net, 'rpn_conv/3x3'): grc}
         dense_in: Dict[Node, torch.Tensor] = {_node(net, 'conv5_3'): vals[_node(net, 'pool_5')].extra['dfeat'],
                                               _node(net, 'conv5_3_2'): vals[_node(net, 'pool_5_2')].extra['dfeat']}
+        main = torch.cuda.current_stream()
+        side = None
+        if net.use_side_stream:
+            # the stream the forward pass ran this trunk on (its activations live in that stream's allocator pool)
+            side = (net._side_stream or {}).get(1)
+            if side is None:
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                side = self._side
+            side.wait_stream(main)      # the ROI-path gradient of conv5_3_2 is ready
         for node in reversed(net._program):
-            if node.kind == 'max_pool':
-                gp = grads.pop(node, None)
-                if gp is None:
-                    continue
-                src = node.inputs[0]
-                grads[src] = K.maxpool2x2_bwd(vals[src].pad, gp)   # routed + gated by the producing conv's ReLU
-                continue
-            if node.kind != 'conv' or node.name in ('rpn_cls_score', 'rpn_bbox_pred'):
-                continue
-            gn = grads.pop(node, None)
-            if gn is None:
-                d = dense_in.pop(node, None)
-                if d is None:
-                    continue
-                gn = K.pad_nhwc_masked(d, vals[node].pad, precise=precise)   # only the ROI path feeds this layer
+            on_side = side is not None and bool(node.attrs.get('side'))
+            with torch.cuda.stream(side if on_side else main):
+                self._backward_node(node, vals, grads, dense_in, g, precise)
+        if side is not None:
+            main.wait_stream(side)
+
+    def _region_of(self, off):
+        for key, (lo, hi) in self.exchange._regions.items():
+            if lo <= off < hi:
+                return key
+        return 0
+
+    def _backward_node(self, node, vals, grads, dense_in, g, precise):
+        net = self.net
+        if node.kind == 'max_pool':
+            gp = grads.pop(node, None)
+            if gp is None:
+                return
             src = node.inputs[0]
-            x = vals[src].pad
-            K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
-            K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
-            if self.exchange is not None:   # this layer's slice (and everything above it) is final: maybe a bucket
-                self.exchange.ready(self.grad, self.slices[node.name][0])
-            if src.kind == 'placeholder':
-                continue
-            gated = src.kind == 'conv'   # the dgrad epilogue applies the ReLU gate of the producing conv
-            gsrc, _ = K.conv(gn, self._dweight(node.name, [node.name]), relu=False, precise=precise, out_pad=True,
-                             mask=x if gated else None, addend=dense_in.pop(src, None), use_bias=False)
-            grads[src] = gsrc
+            grads[src] = K.maxpool2x2_bwd(vals[src].pad, gp)   # routed + gated by the producing conv's ReLU
+            return
+        if node.kind != 'conv' or node.name in ('rpn_cls_score', 'rpn_bbox_pred'):
+            return
+        gn = grads.pop(node, None)
+        if gn is None:
+            d = dense_in.pop(node, None)
+            if d is None:
+                return
+            gn = K.pad_nhwc_masked(d, vals[node].pad, precise=precise)   # only the ROI path feeds this layer
+        src = node.inputs[0]
+        x = vals[src].pad
+        K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
+        K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
+        if self.exchange is not None:   # this layer's slice (and everything above it in its region) is final
+            off = self.slices[node.name][0]
+            self.exchange.ready(self.grad, off, key=self._region_of(off))
+        if src.kind == 'placeholder':
+            return
+        gated = src.kind == 'conv'   # the dgrad epilogue applies the ReLU gate of the producing conv
+        gsrc, _ = K.conv(gn, self._dweight(node.name, [node.name]), relu=False, precise=precise, out_pad=True,
+                         mask=x if gated else None, addend=dense_in.pop(src, None), use_bias=False)
+        grads[src] = gsrc
 
     # ------------------------------------------------------------------ reference-shaped loop
     def train_model(self, sess=None, max_iters=10000, data=None, display=None):

@@ -81,6 +81,24 @@ def im2col3x3(x: torch.Tensor, precise: bool = True, k_pad: int = 32) -> PadAct:
     return PadAct(hi, lo, B, H, W, 9 * Cc)
 
 
+def conv3x3_small_cin(x: torch.Tensor, w_hwio: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
+                      precise: bool = True, out_fmt: int = FMT_BF16X2) -> PadAct:
+    """First conv layer on a dense (B,H,W,C<=4) float32 image: one direct kernel -> PAD activation in `out_fmt`."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, H, W, Cc = x.shape
+    cout = w_hwio.shape[-1]
+    assert tuple(w_hwio.shape[:3]) == (3, 3, Cc) and cout % 8 == 0 and w_hwio.is_contiguous()
+    n_pad = pad_channels(cout)
+    hi, lo = _new_pad(B, H, W, n_pad, precise or out_fmt == FMT_F16E5, x.device)
+    if n_pad != cout:
+        hi.zero_()
+        if lo is not None:
+            lo.zero_()
+    check(lib().mv3d_conv3x3_small_cin(ptr(x), B, H, W, Cc, ptr(w_hwio), ptr(bias), cout, int(relu), ptr(hi), ptr(lo),
+                                       n_pad, out_fmt, current_stream()), "mv3d_conv3x3_small_cin")
+    return PadAct(hi, lo, B, H, W, cout, out_fmt)
+
+
 def unpad_nhwc(a: PadAct) -> torch.Tensor:
     out = torch.empty((a.B, a.H, a.W, a.C), dtype=torch.float32, device=a.hi.device)
     check(lib().mv3d_unpad_nhwc_fmt(ptr(a.hi), ptr(a.lo), a.B, a.H, a.W, a.C, a.c_pad, ptr(out), a.fmt, current_stream()),

@@ -12,7 +12,7 @@ anchor_scales = [1.0, 1.0]
 class MV3D_train(MV3D_test):
     def setup(self):
         self._vgg_trunk('lidar_bv_data', '')     # MV3D_train.py:44-61
-        self._vgg_trunk('image_data', '_2')      # :63-80
+        self._vgg_trunk('image_data', '_2', side=1)      # :63-80 (independent of the BEV trunk: its own stream)
         # ========= RPN ============  (:84-110)
         (self.feed('conv5_3')
              .conv(3, 3, 512, 1, 1, name='rpn_conv/3x3')

@@ -95,6 +95,9 @@ class Network(object):
         self._proposal_target_layer: Optional[ProposalTargetLayer3D] = None
         self._roi_nodes: List[Node] = []
         self._needed_now = set()
+        self._anchor_pre = None
+        self._aux_stream = None
+        self.node_events = None         # list -> Network.run appends (name, kind, start event, end event) per node
         self.last_num_rois = None
         self.training = False           # True: roi_pool keeps argmax, dropout draws masks (set by the solver)
         self.native_fc_layout = False   # True: fc-after-roi_pool weights are stored with rows already in (H,W,C) order
@@ -246,9 +249,17 @@ class Network(object):
             want_pad = any(c in ('conv', 'max_pool') for c in node.consumers) or self.training
             want_dense = (not want_pad) or any(c not in ('conv', 'max_pool') for c in node.consumers) \
                 or node.attrs.get('fetched', False)
+            if (k_h, k_w) == (3, 3) and c_i <= 4 and c_o % 8 == 0 and v.dense is not None and v.pad is None \
+                    and not self.training and want_pad and not want_dense:
+                # tiny-channel first layer (RGB / front view, K = 27): one direct kernel straight into the consumer's
+                # operand format instead of im2col + a K = 32 GEMM whose time is all epilogue.  (Training keeps the
+                # nine-tap GEMM form: its backward-filter expects the PAD input.)
+                p = self.params[name]
+                return Val(pad=K.conv3x3_small_cin(v.dense, p['weights'].contiguous(), p['biases'], relu=relu,
+                                                   precise=self.precise, out_fmt=self._pad_out_fmt(node)))
             if (k_h, k_w) == (3, 3) and 9 * c_i <= 32 and v.dense is not None and v.pad is None and not self.training:
-                # tiny-channel first layer (RGB / front view): im2col once, then ONE K=32 GEMM instead of nine taps of
-                # 13/16 zero padding.  (Training keeps the nine-tap form: its backward-filter expects the PAD input.)
+                # same layer when its dense output is wanted too: im2col once, then ONE K=32 GEMM instead of nine taps
+                # of 13/16 zero padding
                 col = v.extra if isinstance(v.extra, K.PadAct) else K.im2col3x3(v.dense, precise=self.precise)
                 v.extra = col
                 pw = self._packed.get(name + '/im2col')
@@ -617,8 +628,13 @@ class Network(object):
             if al is None:
                 al = self._anchor_target_layers[key] = AnchorTargetLayer(H, W, int(_feat_stride), geom=self.geometry,
                                                                          device=self.device)
-            outs = [al(self._dev(gt_bv[b]), self._dev(gt_3d[b]), im_info[min(b, im_info.shape[0] - 1)],
-                       want_rois=node.attrs.get('fetched', False)) for b in range(B)]
+            pre = self._anchor_pre
+            self._anchor_pre = None
+            if pre is not None and pre[0] == (B, H, W, int(_feat_stride)):
+                outs = pre[1]   # computed ahead of the trunks by precompute_anchor_targets (same RNG draws, same order)
+            else:
+                outs = [al(self._dev(gt_bv[b]), self._dev(gt_3d[b]), im_info[min(b, im_info.shape[0] - 1)],
+                           want_rois=node.attrs.get('fetched', False)) for b in range(B)]
             return Val(extra=dict(labels=torch.stack([o['labels'] for o in outs]),
                                   targets=torch.stack([o['targets'] for o in outs]),
                                   counts=torch.stack([o['counts'] for o in outs]), outs=outs, A=al.N // (H * W)))
@@ -650,6 +666,26 @@ class Network(object):
                                   targets=cat('targets'), num=None, frame_counts=counts, B=B))
         n = self._node(name, 'proposal_target', list(i[0] if isinstance(i, tuple) else i for i in input), run)
         return (n, n, n, n, n)
+
+    def precompute_anchor_targets(self, B, Hf, Wf, feat_stride, gt_bv, gt_3d, im_info):
+        """anchor_target_layer reads only the ground truth and the feature-map SIZE (anchor_target_layer_tf.py:59-98: the
+        score tensor is used for its shape), so a training step can run it -- kernel, 35 kB D2H, host `npr.choice` -- on a
+        side stream BEFORE the trunks are enqueued instead of stalling the pipeline behind them.  The draws from numpy's
+        global stream happen in the same order as when the node runs in place (before the proposal-target layer)."""
+        key = (Hf, Wf, int(feat_stride))
+        al = self._anchor_target_layers.get(key)
+        if al is None:
+            al = self._anchor_target_layers[key] = AnchorTargetLayer(Hf, Wf, int(feat_stride), geom=self.geometry,
+                                                                     device=self.device)
+        gt_bv, gt_3d = self._per_frame(gt_bv, B), self._per_frame(gt_3d, B)
+        im_info = np.asarray(im_info, dtype=np.float32).reshape(-1, 3)
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._aux_stream):
+            outs = [al(self._dev(gt_bv[b]), self._dev(gt_3d[b]), im_info[min(b, im_info.shape[0] - 1)]) for b in range(B)]
+        main.wait_stream(self._aux_stream)
+        self._anchor_pre = ((B, Hf, Wf, int(feat_stride)), outs)
 
     def _dev(self, a):
         if isinstance(a, torch.Tensor):
@@ -687,7 +723,7 @@ class Network(object):
         main = torch.cuda.current_stream()
         # independent branches (attrs['side'] = k > 0: the RGB and FV trunks) run on their own streams, forked when first
         # reached and joined before the first node that may consume any of them
-        use_side = self.use_side_stream and not self.training
+        use_side = self.use_side_stream
         forked, joined = {}, set()
 
         def join_all():
@@ -715,6 +751,13 @@ class Network(object):
             # (roi_pool launches are fused across views, so any roi_pool node may read a side branch's output)
             if forked and (n.kind == 'roi_pool' or any(isinstance(i, Node) and i.attrs.get('side') for i in n.inputs)):
                 join_all()
+            if self.node_events is not None:   # measurement hook (tools/node_times.py): CUDA events around every node
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
+                vals[n] = n.fn(vals, n)
+                e1.record(main)
+                self.node_events.append((n.name, n.kind, e0, e1))
+                continue
             vals[n] = n.fn(vals, n)
         join_all()
         self.last_vals = vals if self.training else None

@@ -58,40 +58,52 @@ class FlatGradExchange:
         self.group = group
         self.bucket_bytes = int(bucket_bytes)
         self._pending = []
-        self._hi = None          # elements [self._hi, end) are already on their way
+        self._hi = {}            # region key -> elements [hi, region end) of that region are already on their way
+        self._regions = {}       # region key -> (lo, hi) element bounds; key 0 = the whole buffer unless narrowed
         self.buckets_last_step = 0
 
     @property
     def world(self) -> int:
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
+    def set_regions(self, regions: dict) -> None:
+        """Disjoint element ranges {key: (lo, hi)} that together cover the buffer.  Each region is finalised from its top
+        to its bottom by ONE stream (the two trunks run their backward on two streams), with its own low-water mark."""
+        self._regions = {k: (int(a), int(b)) for k, (a, b) in regions.items()}
+
     def _send(self, buf: torch.Tensor, lo: int, hi: int) -> None:
         if hi > lo:
             self._pending.append(dist.all_reduce(buf[lo:hi], group=self.group, async_op=True))
 
-    def ready(self, buf: torch.Tensor, lo: int, force: bool = False) -> None:
-        """Gradients in buf[lo:] are final."""
+    def _bounds(self, buf, key):
+        return self._regions.get(key, (0, buf.numel()))
+
+    def ready(self, buf: torch.Tensor, lo: int, force: bool = False, key=0) -> None:
+        """Gradients in buf[lo : end of region `key`] are final.  Call it on the stream that produced them: the
+        collective is ordered after that stream's work."""
         if self.world <= 1:
             return
-        if self._hi is None:
-            self._hi = buf.numel()
-        lo = max(0, min(int(lo), self._hi))
-        if force or (self._hi - lo) * buf.element_size() >= self.bucket_bytes:
-            self._send(buf, lo, self._hi)
-            self._hi = lo
+        rlo, rhi = self._bounds(buf, key)
+        hi = self._hi.get(key, rhi)
+        lo = max(rlo, min(int(lo), hi))
+        if force or (hi - lo) * buf.element_size() >= self.bucket_bytes:
+            self._send(buf, lo, hi)
+            self._hi[key] = lo
 
-    def start_tail(self, buf: torch.Tensor, off: int) -> None:   # the first bucket: everything from `off` to the end
-        self.ready(buf, off, force=True)
+    def start_tail(self, buf: torch.Tensor, off: int, key=0) -> None:   # first bucket: everything from `off` to the region end
+        self.ready(buf, off, force=True, key=key)
 
     def finish(self, buf: torch.Tensor, off: int = 0) -> float:
-        """Send what is left, wait for every bucket; returns the 1/world factor the optimizer applies."""
+        """Send what is left of every region, wait for every bucket; returns the 1/world factor the optimizer applies.
+        Call it after the producing streams were joined into the current one."""
         if self.world > 1:
-            if self._hi is None:
-                self._hi = buf.numel()
-            self._send(buf, 0, self._hi)
+            keys = list(self._regions) if self._regions else [0]
+            for key in keys:
+                rlo, rhi = self._bounds(buf, key)
+                self._send(buf, rlo, self._hi.get(key, rhi))
             self.buckets_last_step = len(self._pending)
             for h in self._pending:
                 h.wait()
             self._pending = []
-            self._hi = None
+            self._hi = {}
         return 1.0 / self.world

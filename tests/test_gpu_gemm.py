@@ -124,6 +124,35 @@ def test_first_layer_im2col_conv(B, H, W, Cout, passes):
     assert float(out.hi[:, :, 0, :].abs().max()) == 0 and float(out.hi[:, H, :, :].abs().max()) == 0
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,fmt", [(1, 9, 11, 3, 64, 0), (2, 37, 50, 3, 64, 1), (1, 64, 96, 3, 64, 1),
+                                                 (1, 33, 40, 1, 64, 0), (1, 20, 31, 4, 128, 1)])
+def test_first_layer_direct_kernel(B, H, W, Cin, Cout, fmt):
+    """conv1_1 on an image-like input through the direct small-Cin kernel (fp32 FMA accumulation) vs torch in float64;
+    the PAD output carries the consumer's operand format (0 = bf16 hi/lo, 1 = f16e5) and zero halos."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cin)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g) * 50
+    w = torch.randn(3, 3, Cin, Cout, device="cuda", generator=g) * 0.2
+    b = torch.randn(Cout, device="cuda", generator=g)
+    out = k.conv3x3_small_cin(x, w, b, relu=True, precise=True, out_fmt=fmt)
+    torch.cuda.synchronize()
+    assert out.fmt == fmt and out.c_pad == Cout
+    ref = torch.relu(torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), b.double(),
+                                                padding=1)).permute(0, 2, 3, 1)
+    # operand rendering keeps ~2^-15 (f16e5) / 2^-17 (bf16 hi/lo) of each value; the fp32 accumulation itself ~1e-7
+    assert _relerr(k.unpad_nhwc(out), ref) < (8e-5 if fmt else 2e-5)
+    # the rendering is exactly that of the generic path applied to the same float32 values
+    dense = k.unpad_nhwc(out)
+    again = k.pad_nhwc(dense, precise=True, fmt=fmt)
+    assert torch.equal(k.unpad_nhwc(again), dense)
+    hi = out.hi.view(torch.int16)
+    assert int(hi[:, :, 0, :].abs().max()) == 0 and int(hi[:, H, :, :].abs().max()) == 0
+    if out.lo is not None:
+        lo = out.lo.view(torch.int16)
+        assert int(lo[:, :, 0, :].abs().max()) == 0 and int(lo[:, H, :, :].abs().max()) == 0
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [
     (1, 12, 13, 64, 64, 3), (1, 23, 50, 128, 256, 3), (1, 23, 50, 128, 256, 1), (1, 30, 33, 256, 512, 3),
     (2, 75, 75, 64, 128, 3), (1, 200, 300, 64, 64, 3), (1, 87, 100, 512, 512, 3),
