@@ -18,26 +18,33 @@ __device__ __forceinline__ int cast_i32_x86(double v) {
 // lidar_3d_to_corners (transform.py:305-313) + lidar_cnr_to_img (:483-500, :369-386): corners from the float32
 // half-extent sums (xp = x + l/2, xm = x - l/2, ...), projected with the float32 3x4 matrix M in float64, divided by
 // the third row (no abs), min/max over the 8 corners, cast to int32 with x86 semantics -> [xmin, ymin, xmax, ymax].
-__device__ __forceinline__ void corners_to_img_box(const float* M, float xp, float xm, float yp, float ym, float zp,
-                                                   float zm, int* img) {
+// One corner c (0..7) of the box in the reference's order -> its image coordinates (u, v) in float64.
+__device__ __forceinline__ void img_corner_uv(const float* M, float xp, float xm, float yp, float ym, float zp, float zm,
+                                              int c, double& u, double& v) {
+    const bool sx = (c == 0 || c == 1 || c == 4 || c == 5);
+    const bool sy = (c == 0 || c == 3 || c == 4 || c == 7);
+    const bool sz = (c >= 4);
+    const double X = sx ? xp : xm, Y = sy ? yp : ym, Z = sz ? zp : zm;
+    double r[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double acc = __dmul_rn((double)M[4 * q], X);
+        acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 1], Y));
+        acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 2], Z));
+        acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 3], 0.0));
+        r[q] = acc;
+    }
+    u = r[0] / r[2];
+    v = r[1] / r[2];
+}
+
+// min / max over the 8 corners' (u, v) in corner order with numpy's NaN propagation, int32 cast with x86 semantics.
+__device__ __forceinline__ void img_box_from_uv(const double* u8, const double* v8, int* img) {
     double umin = 0, umax = 0, vmin = 0, vmax = 0;
     bool nan_u = false, nan_v = false;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const bool sx = (c == 0 || c == 1 || c == 4 || c == 5);
-        const bool sy = (c == 0 || c == 3 || c == 4 || c == 7);
-        const bool sz = (c >= 4);
-        const double X = sx ? xp : xm, Y = sy ? yp : ym, Z = sz ? zp : zm;
-        double r[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            double acc = __dmul_rn((double)M[4 * q], X);
-            acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 1], Y));
-            acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 2], Z));
-            acc = __dadd_rn(acc, __dmul_rn((double)M[4 * q + 3], 0.0));
-            r[q] = acc;
-        }
-        const double u = r[0] / r[2], v = r[1] / r[2];
+        const double u = u8[c], v = v8[c];
         nan_u |= (u != u);
         nan_v |= (v != v);
         if (c == 0) { umin = umax = u; vmin = vmax = v; }
@@ -50,6 +57,14 @@ __device__ __forceinline__ void corners_to_img_box(const float* M, float xp, flo
     if (nan_v) vmin = vmax = nan("");
     img[0] = cast_i32_x86(umin); img[1] = cast_i32_x86(vmin);
     img[2] = cast_i32_x86(umax); img[3] = cast_i32_x86(vmax);
+}
+
+__device__ __forceinline__ void corners_to_img_box(const float* M, float xp, float xm, float yp, float ym, float zp,
+                                                   float zm, int* img) {
+    double u8[8], v8[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) img_corner_uv(M, xp, xm, yp, ym, zp, zm, c, u8[c], v8[c]);
+    img_box_from_uv(u8, v8, img);
 }
 
 // numpy float64 floor_divide == npy_divmod (numpy/core/src/npymath/npy_math_internal.h): fmod based.
@@ -98,13 +113,17 @@ __device__ __forceinline__ BoxExtents box_extents(float px, float py, float pz, 
 
 // lidar_3d_to_bv (transform.py:132-140: f32 sums widened to f64, numpy `//`) + clip_boxes (bbox_transform.py:178-191)
 // -> (x1, y1, x2, y2) integral-valued float32.
+// coordinate q of the box: 0 = x1 (from y + w/2), 1 = y1 (from x + l/2), 2 = x2 (y - w/2), 3 = y2 (x - l/2)
+__device__ __forceinline__ float bev_coord(const BevGrid& g, const BoxExtents& e, int q) {
+    const bool is_x = (q & 1) == 0;
+    const float src = q == 0 ? e.yp : (q == 1 ? e.xp : (q == 2 ? e.ym : e.xm));
+    const float raw = is_x ? (float)(g.yn - npy_floor_divide((double)src - g.y_min, g.res))
+                           : (float)(g.xn - npy_floor_divide((double)src - g.x_min, g.res));
+    return clip_np(raw, is_x ? g.clip_x : g.clip_y);
+}
 __device__ __forceinline__ void extents_to_bev_box(const BevGrid& g, const BoxExtents& e, float* bv) {
-    float x1 = (float)(g.yn - npy_floor_divide((double)e.yp - g.y_min, g.res));
-    float y1 = (float)(g.xn - npy_floor_divide((double)e.xp - g.x_min, g.res));
-    float x2 = (float)(g.yn - npy_floor_divide((double)e.ym - g.y_min, g.res));
-    float y2 = (float)(g.xn - npy_floor_divide((double)e.xm - g.x_min, g.res));
-    bv[0] = clip_np(x1, g.clip_x); bv[1] = clip_np(y1, g.clip_y);
-    bv[2] = clip_np(x2, g.clip_x); bv[3] = clip_np(y2, g.clip_y);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = bev_coord(g, e, q);
 }
 
 // Front view (no reference counterpart; DESIGN.md 'Front view'): cylindrical map geometry.
@@ -120,15 +139,18 @@ __device__ __forceinline__ void fv_coords(const FvGeom& g, double x, double y, d
 
 // FV rectangle of a 3-D box: floor of the FV coordinates of its 8 corners, min/max, clamped to the map
 // -> [col_min, row_min, col_max, row_max]; a non-finite corner gives the empty rectangle (0,0,0,0).
-__device__ __forceinline__ void extents_to_fv_box(const FvGeom& g, const BoxExtents& e, float* o) {
-    const float xs[2] = {e.xp, e.xm}, ys[2] = {e.yp, e.ym}, zs[2] = {e.zp, e.zm};
+// floor'd FV coordinates of corner k (0..7)
+__device__ __forceinline__ void fv_corner(const FvGeom& g, const BoxExtents& e, int k, double& col, double& row) {
+    const float x = (k & 1) ? e.xm : e.xp, y = ((k >> 1) & 1) ? e.ym : e.yp, z = (k >> 2) ? e.zm : e.zp;
+    fv_coords(g, (double)x, (double)y, (double)z, col, row);
+    col = floor(col);
+    row = floor(row);
+}
+__device__ __forceinline__ void fv_box_from_corners(const FvGeom& g, const double* col8, const double* row8, float* o) {
     double cmin = 0, cmax = 0, rmin = 0, rmax = 0;
     bool bad = false;
     for (int k = 0; k < 8; ++k) {
-        double col, row;
-        fv_coords(g, (double)xs[k & 1], (double)ys[(k >> 1) & 1], (double)zs[k >> 2], col, row);
-        col = floor(col);
-        row = floor(row);
+        const double col = col8[k], row = row8[k];
         if (!(isfinite(col) && isfinite(row))) bad = true;
         if (k == 0) { cmin = cmax = col; rmin = rmax = row; }
         else {
@@ -142,6 +164,11 @@ __device__ __forceinline__ void extents_to_fv_box(const FvGeom& g, const BoxExte
     o[1] = (float)fmin(fmax(rmin, 0.0), hmax);
     o[2] = (float)fmin(fmax(cmax, 0.0), wmax);
     o[3] = (float)fmin(fmax(rmax, 0.0), hmax);
+}
+__device__ __forceinline__ void extents_to_fv_box(const FvGeom& g, const BoxExtents& e, float* o) {
+    double col8[8], row8[8];
+    for (int k = 0; k < 8; ++k) fv_corner(g, e, k, col8[k], row8[k]);
+    fv_box_from_corners(g, col8, row8, o);
 }
 
 }  // namespace mv3d

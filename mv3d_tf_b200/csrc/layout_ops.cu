@@ -154,79 +154,105 @@ __global__ void im2col3x3_pad_kernel(const float* __restrict__ in, int B, int H,
 
 // First conv layer of an image-like input with a handful of channels (RGB / front view: Cin = 3, K = 27): 1.6 of the
 // frame's 920 GFLOP, but as a tensor-core GEMM it is an im2col pass plus a K = 32 GEMM whose time is all epilogue
-// (82 us together at 375x1242).  Here it is ONE direct kernel: 8 lanes per output pixel, each lane 8 output channels;
-// the 27 inputs are the same addresses for the 8 lanes (L1 broadcast), the weights sit in shared memory as
-// [tap*Cin + c][cout]; fp32 FMA accumulation in tap order, + bias, ReLU, then the consumer's operand rendering (f16e5
-// or bf16 hi/lo) with 16-byte stores straight into the PAD layout, halo pixels zero.  Bound by its 4 B/element output.
-template <int FMT>
+// (82 us together at 375x1242).  Here it is ONE direct kernel, register-tiled: a thread owns 4 consecutive pixels of a
+// row x 8 output channels (32 fp32 accumulators); the 3 x 6 x C input window is loaded once into registers, every
+// weight vector (shared memory, [tap*C + c][cout]) is used for 4 pixels (1 LDS.128 per 16 FMAs); fp32 FMA accumulation
+// in tap order, + bias, ReLU, then the consumer's operand rendering (f16e5 or bf16 hi/lo) with 16-byte stores straight
+// into the PAD layout, halo pixels zero.  Bound by its 4 B/element output.
+constexpr int kSmallPx = 4;
+
+template <int FMT, int C>
 __global__ void __launch_bounds__(256)
-conv3x3_small_cin_kernel(const float* __restrict__ in, int B, int H, int W, int C, const float* __restrict__ w_hwio,
+conv3x3_small_cin_kernel(const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w_hwio,
                          const float* __restrict__ bias, int Cout, int relu, void* __restrict__ out_hi,
                          void* __restrict__ out_lo, int c_pad) {
     extern __shared__ float wsm[];                 // [9*C][Cout] + bias[Cout]
-    const int K = 9 * C;
+    constexpr int K = 9 * C;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) wsm[i] = w_hwio[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) wsm[K * Cout + i] = bias ? bias[i] : 0.f;
     __syncthreads();
     const float* bsm = wsm + K * Cout;
     const int Hp = H + 1, Wp = W + 1, groups = c_pad / 8;
-    const long long total = (long long)B * Hp * Wp * groups;
+    const int wq = (Wp + kSmallPx - 1) / kSmallPx;              // 4-pixel segments per PAD row (halo column included)
+    const long long total = (long long)B * Hp * wq * groups;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int gq = (int)(i % groups);
-        const long long pix = i / groups;
-        const int wp = (int)(pix % Wp);
-        const long long r = pix / Wp;
+        long long r = i / groups;
+        const int seg = (int)(r % wq);
+        r /= wq;
         const int hp = (int)(r % Hp);
         const int b = (int)(r / Hp);
         const int co = gq * 8;
-        float acc[8];
+        const int wp0 = seg * kSmallPx;                         // first PAD column of the segment; pixel w = wp - 1
+        float acc[kSmallPx][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        const bool inside = wp > 0 && hp < H && co < Cout;
-        if (inside) {
+        for (int p = 0; p < kSmallPx; ++p)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = bsm[co + e];
-            const int h = hp, w = wp - 1;
+            for (int e = 0; e < 8; ++e) acc[p][e] = 0.f;
+        const bool row_inside = hp < H && co < Cout;
+        if (row_inside) {
+            // input window: rows hp-1..hp+1, image columns (wp0-1)-1 .. (wp0-1)+4, zero outside the image
+            float x[3][kSmallPx + 2][C];
+#pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-                const int hh = h + kh - 1;
-                if (hh < 0 || hh >= H) continue;
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int ww = w + kw - 1;
-                    if (ww < 0 || ww >= W) continue;
-                    const float* px = in + (((long long)b * H + hh) * W + ww) * C;
-                    const float* wt = wsm + (size_t)((kh * 3 + kw) * C) * Cout + co;
-                    for (int c = 0; c < C; ++c) {
-                        const float x = __ldg(px + c);
-                        const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)c * Cout);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)c * Cout + 4);
-                        acc[0] = __fmaf_rn(x, w0.x, acc[0]); acc[1] = __fmaf_rn(x, w0.y, acc[1]);
-                        acc[2] = __fmaf_rn(x, w0.z, acc[2]); acc[3] = __fmaf_rn(x, w0.w, acc[3]);
-                        acc[4] = __fmaf_rn(x, w1.x, acc[4]); acc[5] = __fmaf_rn(x, w1.y, acc[5]);
-                        acc[6] = __fmaf_rn(x, w1.z, acc[6]); acc[7] = __fmaf_rn(x, w1.w, acc[7]);
-                    }
+                const int hh = hp + kh - 1;
+#pragma unroll
+                for (int q = 0; q < kSmallPx + 2; ++q) {
+                    const int ww = wp0 - 2 + q;
+                    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+                    const float* px = in + (((long long)b * H + (ok ? hh : 0)) * W + (ok ? ww : 0)) * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) x[kh][q][c] = ok ? __ldg(px + c) : 0.f;
                 }
             }
-            if (relu) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
-            }
+            for (int p = 0; p < kSmallPx; ++p)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[p][e] = bsm[co + e];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float* wt = wsm + (size_t)((kh * 3 + kw) * C + c) * Cout + co;
+                        const float4 w0 = *reinterpret_cast<const float4*>(wt);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int p = 0; p < kSmallPx; ++p) {
+                            const float xv = x[kh][p + kw][c];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[p][e] = __fmaf_rn(xv, wv[e], acc[p][e]);
+                        }
+                    }
         }
-        if (FMT == MV3D_FMT_F16E5) {
-            unsigned short hh16[8];
-            uint8_t h8[8], l8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_f16e5(acc[e], hh16[e], h8[e], l8[e]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(hh16);
-            uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + pix * c_pad * 2 + f16e5_off(co);
-            *reinterpret_cast<uint2*>(row) = *reinterpret_cast<uint2*>(h8);
-            *reinterpret_cast<uint2*>(row + 64) = *reinterpret_cast<uint2*>(l8);
-        } else {
-            __nv_bfloat16 vh[8], vl[8];
+        for (int p = 0; p < kSmallPx; ++p) {
+            const int wp = wp0 + p;
+            if (wp >= Wp) break;
+            const bool inside = row_inside && wp > 0;
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) split_bf16(acc[e], vh[e], vl[e]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vh);
-            if (out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vl);
+            for (int e = 0; e < 8; ++e) v[e] = inside ? (relu ? fmaxf(acc[p][e], 0.f) : acc[p][e]) : 0.f;
+            const long long pix = ((long long)b * Hp + hp) * Wp + wp;
+            if (FMT == MV3D_FMT_F16E5) {
+                unsigned short hh16[8];
+                uint8_t h8[8], l8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_f16e5(v[e], hh16[e], h8[e], l8[e]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(hh16);
+                uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + pix * c_pad * 2 + f16e5_off(co);
+                *reinterpret_cast<uint2*>(row) = *reinterpret_cast<uint2*>(h8);
+                *reinterpret_cast<uint2*>(row + 64) = *reinterpret_cast<uint2*>(l8);
+            } else {
+                __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16(v[e], vh[e], vl[e]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vh);
+                if (out_lo) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_lo) + pix * c_pad + co) = *reinterpret_cast<uint4*>(vl);
+            }
         }
     }
 }
@@ -618,14 +644,19 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv3x3_small_cin(
     MV3D_REQUIRE(fmt == MV3D_FMT_BF16X2 || (fmt == MV3D_FMT_F16E5 && d_out_lo && c_pad % 64 == 0));
     const size_t smem = sizeof(float) * ((size_t)9 * C * Cout + Cout);
     MV3D_REQUIRE(smem <= 48 * 1024);
-    const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
+    const long long total = (long long)B * (H + 1) * ((W + 1 + kSmallPx - 1) / kSmallPx) * (c_pad / 8);
     const int grid = grid_for(total, 256);
-    if (fmt == MV3D_FMT_F16E5)
-        conv3x3_small_cin_kernel<MV3D_FMT_F16E5><<<grid, 256, smem, (cudaStream_t)stream>>>(d_in, B, H, W, C, d_w, d_bias, Cout, relu,
-                                                                                          d_out_hi, d_out_lo, c_pad);
-    else
-        conv3x3_small_cin_kernel<MV3D_FMT_BF16X2><<<grid, 256, smem, (cudaStream_t)stream>>>(d_in, B, H, W, C, d_w, d_bias, Cout, relu,
-                                                                                           d_out_hi, d_out_lo, c_pad);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MV3D_SMALL_CIN(FMT, CC) \
+    conv3x3_small_cin_kernel<FMT, CC><<<grid, 256, smem, st>>>(d_in, B, H, W, d_w, d_bias, Cout, relu, d_out_hi, d_out_lo, c_pad)
+    if (fmt == MV3D_FMT_F16E5) {
+        if (C == 1) MV3D_SMALL_CIN(MV3D_FMT_F16E5, 1); else if (C == 2) MV3D_SMALL_CIN(MV3D_FMT_F16E5, 2);
+        else if (C == 3) MV3D_SMALL_CIN(MV3D_FMT_F16E5, 3); else MV3D_SMALL_CIN(MV3D_FMT_F16E5, 4);
+    } else {
+        if (C == 1) MV3D_SMALL_CIN(MV3D_FMT_BF16X2, 1); else if (C == 2) MV3D_SMALL_CIN(MV3D_FMT_BF16X2, 2);
+        else if (C == 3) MV3D_SMALL_CIN(MV3D_FMT_BF16X2, 3); else MV3D_SMALL_CIN(MV3D_FMT_BF16X2, 4);
+    }
+#undef MV3D_SMALL_CIN
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
 }

@@ -123,18 +123,27 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, int n_max, const 
         if (tid < kSuperWords) cur_s[tid] = 0;
         __syncthreads();                                        // count_s / keep_out of the previous super-block visible
         const int cnt = count_s;
-        {   // (a) removed bits of this super-block's candidates: OR of the rows of every box kept so far
-            const int w = tid & (kSuperWords - 1), g = tid >> 4;   // 16 word lanes x 64 row groups
-            unsigned long long acc = 0;
-            if (w < nw)
-                for (int k = g; k < cnt; k += kReduceThreads / kSuperWords)
-                    acc |= __ldg(mask + (size_t)keep_out[k] * nwords + w0 + w);
+        {   // (a) removed bits of this super-block's candidates: OR of the rows of every box kept so far.  One LANE per
+            //     kept box: its index, then its 16 words -- independent loads, two round trips in all -- and the warp
+            //     combines each word with two 32-bit OR-reductions (the kept list is at most a few thousand long).
+            for (int k0 = warp * 32; k0 < cnt; k0 += kReduceThreads) {
+                const int k = k0 + lane;
+                const unsigned long long* row = (k < cnt) ? mask + (size_t)keep_out[k] * nwords + w0 : nullptr;
+                unsigned long long v[kSuperWords];
+#pragma unroll
+                for (int w = 0; w < kSuperWords; ++w) v[w] = (row != nullptr && w < nw) ? __ldg(row + w) : 0ull;
+#pragma unroll
+                for (int w = 0; w < kSuperWords; ++w) {
+                    const unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)v[w]);
+                    const unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(v[w] >> 32));
+                    if (lane == w && (lo32 | hi32)) atomicOr(&cur_s[w], ((unsigned long long)hi32 << 32) | lo32);
+                }
+            }
             // (b) the diagonal tile; words left of a row's own 64-block were never written (upper-triangular mask)
             for (int e = tid; e < rows * kSuperWords; e += kReduceThreads) {
                 const int r = e >> 4, ww = e & (kSuperWords - 1);
                 diag[e] = (ww < nw && ww >= (r >> 6)) ? __ldg(mask + (size_t)(base + r) * nwords + w0 + ww) : 0ull;
             }
-            if (acc) atomicOr(&cur_s[w], acc);
         }
         __syncthreads();
         if (warp == 0) {

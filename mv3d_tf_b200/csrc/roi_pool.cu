@@ -169,36 +169,48 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
     const int n = blockIdx.x, tid = threadIdx.x;
     const int c_lo = blockIdx.z * kSliceC, c_hi = min(C, c_lo + kSliceC);   // this CTA's channels
     const bool valid = d_num_valid ? (n < *d_num_valid) : true;
-    if (tid == 0) {
+    __shared__ double part_s[16];
+    if (tid < 32) {   // warp 0: eight lanes do the per-corner (per-coordinate) float64 work, lane 0 combines in corner order
         float roi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-            if (V.source == MV3D_ROI_GIVEN) {
+        if (valid && V.source == MV3D_ROI_GIVEN) {
+            if (tid == 0) {
 #pragma unroll
                 for (int q = 0; q < 5; ++q) roi[q] = V.rois[(size_t)n * 5 + q];
-            } else {
-                const float* p = rois_3d + (size_t)n * 7;
-                roi[0] = p[0];
-                const BoxExtents e = box_extents(p[1], p[2], p[3], p[4], p[5], p[6]);
-                if (V.source == MV3D_ROI_BEV) {
-                    extents_to_bev_box(proj.bev, e, roi + 1);
-                } else if (V.source == MV3D_ROI_IMG) {
+            }
+        } else if (valid) {
+            const float* p = rois_3d + (size_t)n * 7;
+            roi[0] = p[0];
+            const BoxExtents e = box_extents(p[1], p[2], p[3], p[4], p[5], p[6]);
+            if (V.source == MV3D_ROI_BEV) {
+                if (tid < 4) part_s[tid] = (double)bev_coord(proj.bev, e, tid);
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) roi[1 + q] = (float)part_s[q];
+            } else if (V.source == MV3D_ROI_IMG) {
+                if (tid < 8) {
                     float Mloc[12];
 #pragma unroll
                     for (int q = 0; q < 12; ++q) Mloc[q] = proj.dM ? __ldg(proj.dM + q) : proj.M[q];
-                    int img[4];
-                    corners_to_img_box(Mloc, e.xp, e.xm, e.yp, e.ym, e.zp, e.zm, img);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) roi[1 + q] = (float)img[q];
-                } else {
-                    extents_to_fv_box(proj.fv, e, roi + 1);
+                    img_corner_uv(Mloc, e.xp, e.xm, e.yp, e.ym, e.zp, e.zm, tid, part_s[tid], part_s[8 + tid]);
                 }
+                __syncwarp();
+                int img[4];
+                img_box_from_uv(part_s, part_s + 8, img);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) roi[1 + q] = (float)img[q];
+            } else {
+                if (tid < 8) fv_corner(proj.fv, e, tid, part_s[tid], part_s[8 + tid]);
+                __syncwarp();
+                fv_box_from_corners(proj.fv, part_s, part_s + 8, roi + 1);
             }
         }
+        if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) roi_s[q] = roi[q];
-        if (V.rois_out && blockIdx.z == 0) {
+            for (int q = 0; q < 5; ++q) roi_s[q] = roi[q];
+            if (V.rois_out && blockIdx.z == 0) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) V.rois_out[(size_t)n * 5 + q] = roi[q];
+                for (int q = 0; q < 5; ++q) V.rois_out[(size_t)n * 5 + q] = roi[q];
+            }
         }
     }
     __syncthreads();

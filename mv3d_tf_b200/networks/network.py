@@ -12,6 +12,7 @@ from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -478,8 +479,11 @@ class Network(object):
                 if self.fv_geometry is not None:
                     (proj.fv_h, proj.fv_w, proj.fv_theta_min, proj.fv_dtheta, proj.fv_phi_max,
                      proj.fv_dphi) = self.fv_geometry.c_args()
+                # MV3D_ROI_PROJECT=0: BEV / image rectangles are taken from the proposal layer's blobs (bit-identical to the
+                # in-kernel projection; A/B switch for the cost of recomputing them), the FV box is always made here
+                given = os.environ.get('MV3D_ROI_PROJECT', '1') == '0'
                 for k, t in enumerate(targets):
-                    views[k].source = {'bv': ROI_BEV, 'img': ROI_IMG, 'fv': ROI_FV}[t]
+                    views[k].source = ROI_GIVEN if (given and t != 'fv') else {'bv': ROI_BEV, 'img': ROI_IMG, 'fv': ROI_FV}[t]
                     views[k].d_rois_out = ptr(e['fv']) if (t == 'fv' and e.pop('fv_pending', False)) else None
                 p3d = e['p3d'].contiguous()
                 check(lib().mv3d_roi_pool_fused(views, len(group), ptr(p3d), C.byref(proj), R, ptr(num), group[0].channels,
