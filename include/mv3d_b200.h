@@ -223,6 +223,11 @@ typedef struct {
      * lib/networks/MV3D_test.py:76-81, network.py:399-405) -- used to fold rpn_cls_score | rpn_bbox_pred into ONE
      * N = 32 GEMM whose output is (prob x 8 | deltas x 24).  Requires d_out_f32, relu = 0, split_k <= 1, even. */
     int softmax_cols;
+    /* 1: Network.max_pool(2,2,2,2,'VALID') (network.py:181-188) of this 3x3 conv's output is taken in the epilogue
+     * (CTA pair = 2 image rows x 128 columns, row maxima exchanged through distributed shared memory); d_out_hi / d_out_lo
+     * are then the POOLED PAD planes (B, H/2 + 1, W/2 + 1, ld_out), halos zeroed by the kernel; the un-pooled activation
+     * is never written.  N = 64 or 128, Cin % 64 == 0, passes 2 or 3, no float32 / gate / addend output. */
+    int pool;
 } mv3d_gemm_desc;
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
 /* A/B switch for the CTA-pair (tcgen05 cta_group::2, 256 x N tiles) form of the tap-reuse 3x3 conv kernel: on (default,

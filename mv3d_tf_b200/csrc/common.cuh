@@ -62,6 +62,16 @@ __device__ __forceinline__ void split_f16e5(float x, unsigned short& h, uint8_t&
 __device__ __forceinline__ float join_f16e5(unsigned short h, uint8_t l8) {
     return __half2float(__ushort_as_half(h)) + from_e5m2(l8) * (1.f / kF16E5Scale);
 }
+// Two values at once with the packed conversion instructions (same roundings as split_f16e5): h2 = fp16x2 (x0 low),
+// h8 / l8 = e5m2x2 of the fp16 values / of the scaled residuals.
+__device__ __forceinline__ void split_f16e5_x2(float x0, float x1, uint32_t& h2, unsigned short& h8, unsigned short& l8) {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x1), "f"(x0));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(h8) : "f"(hf.y), "f"(hf.x));
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(l8) : "f"((x1 - hf.y) * kF16E5Scale), "f"((x0 - hf.x) * kF16E5Scale));
+}
 // weights: fp16 plane = fp16(4096 w), byte plane = [e5m2(4096 w - fp16 plane) | e5m2(w)]
 __device__ __forceinline__ void split_f16e5_weight(float w, unsigned short& h, uint8_t& l8, uint8_t& h8) {
     const float ws = fminf(fmaxf(w * kF16E5Scale, -65504.f), 65504.f);

@@ -56,6 +56,7 @@ struct GemmParams {
                       // loads after the first lap of each ring (pure MMA rate on stale shared memory), 4 = the epilogue
                       // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
     int softmax_cols;   // mv3d_gemm_desc::softmax_cols
+    int pool, pool_Ho, pool_Wo, pool_nblk;   // fused 2x2 max-pool (pair kernel, POOL): pooled size, 128-column blocks per row
     long long* stamps;  // measurement only (mv3d_gemm_set_stamps): clock64 of pair 0's phases, see conv3x3_pair_kernel
 };
 
@@ -340,6 +341,162 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& prm, uint32_t tm
 #pragma unroll
             for (int j = 0; j < 32; ++j) va[j] = vb[j];
         }
+    }
+}
+
+// Work item -> first output pixel (flat PAD index) of CTA `rank`.  Plain: 256 consecutive pixels per pair.  POOL: item =
+// (frame b, row pair i, 128-column block k); CTA r owns pixels (2i + r, 128k .. 128k + 127).
+__device__ __forceinline__ int tile_m0(const GemmParams& prm, int w, int tiles_n, int rank, int& pb, int& pi, int& pk) {
+    if (prm.pool) {
+        pk = w % prm.pool_nblk;
+        const int t = w / prm.pool_nblk;
+        pi = t % prm.pool_Ho;
+        pb = t / prm.pool_Ho;
+        return (pb * prm.Hp + 2 * pi + rank) * prm.Wp + 128 * pk + 1;
+    }
+    pb = pi = pk = 0;
+    return (w / tiles_n) * (2 * kBM) + rank * kBM;
+}
+
+// Epilogue of one POOL tile (see PairCfg).  Warp (q, half) reads its TMEM quarter's chunks half, half + 2, ...:
+// bias + ReLU, horizontal max of the pixel pair (lanes 2j, 2j+1).  The CTA of rank r FINALISES the chunks whose warps
+// have half == r: the other CTA's warps of the same (q, half) -- holding the other image row -- send their 16 x 32
+// values per chunk into this CTA's exchange buffer (st.async, bytes counted on x_full); the finaliser takes the vertical
+// max, renders the operand format and stores the pooled pixel (+ the zero halo column / row of the pooled PAD tensor).
+// x_empty (in the sender's CTA, one arrival per finalising warp of the peer) frees the buffer two tiles later.
+template <int BN, int ACC_COLS>
+__device__ __forceinline__ void epilogue_tile_pool(const GemmParams& prm, uint32_t tmem_base, int acc, int pb, int pi,
+                                                   int pk, int rank, int q, int half, int lane, uint64_t* tmem_full,
+                                                   uint64_t* tmem_empty, int tl, const float* bias_s, float* xbuf,
+                                                   uint64_t* x_full, uint64_t* x_empty) {
+    constexpr int kMine = BN / 64;                      // chunks per warp
+    const bool finalizer = (half == rank);
+    const int ph = tl & 1;
+    const uint32_t par = (tl >> 1) & 1;
+    const uint32_t peer = (uint32_t)(rank ^ 1);
+    if (finalizer && q == 0 && lane == 0) mbar_arrive_expect_tx(&x_full[ph], kMine * 8192);
+    mbar_wait(&tmem_full[acc], par);
+    tc_fence_after();
+    if (!finalizer) mbar_wait(&x_empty[ph], par ^ 1);   // the peer has read what was sent two tiles ago
+    const uint32_t taddr_row = tmem_base + acc * ACC_COLS + (uint32_t(q * 32) << 16);
+    const float sc = prm.acc_scale;
+    const float* bsrc = bias_s != nullptr ? bias_s : prm.bias;
+    const int Ho = prm.pool_Ho, Wo = prm.pool_Wo;
+    const int jj = 64 * pk + 16 * q + (lane >> 1);      // pooled column of this lane pair
+    const bool even = (lane & 1) == 0;
+#pragma unroll 1
+    for (int k = 0; k < kMine; ++k) {
+        const int c = (half + 2 * k) * 32;              // first channel of the chunk (n0 = 0: N == BN)
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr_row + c, v);
+        tmem_ld_wait();
+        if (k == kMine - 1) {                           // accumulator drained by this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            x = (prm.bias != nullptr) ? __fmaf_rn(x, sc, bsrc[c + j]) : x * sc;
+            if (prm.relu) x = fmaxf(x, 0.f);
+            f[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));        // max over the pixel pair (w, w+1), w even
+        }
+        float* slot = xbuf + ((size_t)((ph * kMine + k) * 4 + q) * 16 + (lane >> 1)) * 32;
+        if (!finalizer) {
+            if (even) {
+                const uint32_t dst = mapa_u32(smem_u32(slot), peer), bar = mapa_u32(smem_u32(&x_full[ph]), peer);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    st_async_v4(dst + j * 4, __float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]),
+                                __float_as_uint(f[j + 3]), bar);
+            }
+            continue;
+        }
+        if (k == 0) mbar_wait(&x_full[ph], par);        // every chunk of this tile has landed
+        if (!even || jj >= Wo) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 o = *reinterpret_cast<const float4*>(slot + j);
+            f[j] = fmaxf(f[j], o.x); f[j + 1] = fmaxf(f[j + 1], o.y);
+            f[j + 2] = fmaxf(f[j + 2], o.z); f[j + 3] = fmaxf(f[j + 3], o.w);
+        }
+        // pooled pixel (pi, jj) of frame pb in the pooled PAD tensor, and the halo positions this thread zeroes
+        const long long row0 = ((long long)pb * (Ho + 1) + pi) * (Wo + 1);
+        const long long qo = row0 + jj + 1;
+        uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (prm.out_fmt == MV3D_FMT_F16E5) {
+            unsigned short* oh = reinterpret_cast<unsigned short*>(prm.out_hi);
+            uint8_t* ob = reinterpret_cast<uint8_t*>(prm.out_lo);
+            uint32_t ph16[16], p8[8], q8[8];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                uint32_t a8[2], b8[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float x0 = fminf(f[j + 2 * e], 65504.f), x1 = fminf(f[j + 2 * e + 1], 65504.f);
+                    const float y0 = fmaxf(x0, -65504.f), y1 = fmaxf(x1, -65504.f);
+                    const uint32_t h2 = cvt_pack_f16x2(y0, y1);
+                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+                    ph16[j / 2 + e] = h2;
+                    a8[e] = cvt_pack_e5m2x2(hf.x, hf.y);
+                    b8[e] = cvt_pack_e5m2x2((y0 - hf.x) * kF16E5Scale, (y1 - hf.y) * kF16E5Scale);
+                }
+                p8[j / 4] = a8[0] | (a8[1] << 16);
+                q8[j / 4] = b8[0] | (b8[1] << 16);
+            }
+            auto put = [&](long long pix, const uint32_t* h, const uint32_t* a, const uint32_t* b) {
+                unsigned short* dh = oh + pix * prm.ld_out + c;
+                uint8_t* db = ob + pix * prm.ld_out * 2 + f16e5_off(c);
+                st_global_v8(dh, h);
+                st_global_v8(dh + 16, h + 8);
+                st_global_v8(db, a);
+                st_global_v8(db + 64, b);
+            };
+            uint32_t zero16[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) zero16[e] = 0u;
+            put(qo, ph16, p8, q8);
+            if (jj == 0) put(row0, zero16, zero8, zero8);
+            if (pi == Ho - 1) {
+                put(qo + (Wo + 1), zero16, zero8, zero8);
+                if (jj == 0) put(row0 + (Wo + 1), zero16, zero8, zero8);
+            }
+        } else {
+            __nv_bfloat16* oh = prm.out_hi;
+            __nv_bfloat16* ol = prm.out_lo;
+            uint32_t phb[16], plb[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float x0 = f[2 * e], x1 = f[2 * e + 1];
+                const uint32_t h2 = cvt_pack_bf16x2(x0, x1);
+                phb[e] = h2;
+                plb[e] = cvt_pack_bf16x2(x0 - __uint_as_float(h2 << 16), x1 - __uint_as_float(h2 & 0xFFFF0000u));
+            }
+            auto put = [&](long long pix, const uint32_t* h, const uint32_t* l) {
+                st_global_v8(oh + pix * prm.ld_out + c, h);
+                st_global_v8(oh + pix * prm.ld_out + c + 16, h + 8);
+                if (ol) {
+                    st_global_v8(ol + pix * prm.ld_out + c, l);
+                    st_global_v8(ol + pix * prm.ld_out + c + 16, l + 8);
+                }
+            };
+            uint32_t zero16[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) zero16[e] = 0u;
+            put(qo, phb, plb);
+            if (jj == 0) put(row0, zero16, zero16);
+            if (pi == Ho - 1) {
+                put(qo + (Wo + 1), zero16, zero16);
+                if (jj == 0) put(row0 + (Wo + 1), zero16, zero16);
+            }
+        }
+    }
+    if (finalizer) {   // this warp has read its slots of the buffer: the peer may refill it
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_cta(mapa_u32(smem_u32(&x_empty[ph]), peer));
     }
 }
 
@@ -669,7 +826,11 @@ conv3x3_reuse_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 // WRES (64 -> 64 channel layers: conv1_2, BEV conv1_1): all nine weight taps of the layer (72 KB per CTA) are loaded
 // ONCE and stay resident while the persistent CTA pair walks its ~30 tiles.  These layers are bound by the L2 -> SM
 // operand feed (176 KB per tile and CTA at ~37 B/clk/SM of the ~43 the chip delivers); the weights were 41 % of it.
-template <int BN, int PASSES, bool WRES = false>
+// POOL (conv1_2 / conv2_2 followed by Network.max_pool(2,2,2,2,'VALID')): the pair tile is 2 image rows x 128 columns
+// (CTA r = row 2i + r), each CTA takes the horizontal pair maximum with a lane shuffle and the two CTAs exchange half
+// of their channel chunks through distributed shared memory (st.async + complete_tx), so every 2x2 window is reduced
+// on chip and only the pooled activation (1/4 of the bytes) is written -- these layers are bound by their HBM write.
+template <int BN, int PASSES, bool WRES = false, bool POOL = false>
 struct PairCfg {
     static constexpr int kOperands = (PASSES >= 2) ? 2 : 1;
     static constexpr int kAPlane = 18 * 1024;
@@ -680,9 +841,12 @@ struct PairCfg {
     static constexpr int kWEntry = kWPlane * kOperands;
     static constexpr int kNA = (BN <= 64 ? 3 : 2) * (PASSES >= 2 ? 1 : 2);
     static constexpr int kBudget = 200 * 1024;
-    static constexpr int kNWRaw = (kBudget - kNA * kAEntry) / kWEntry;
+    static constexpr int kXChunks = BN / 64;                          // channel chunks a warp sends / receives per tile
+    static constexpr int kXPhase = kXChunks * 8192;                   // exchange bytes per tile: 4 warps x 16 columns x 32 ch x 4 B
+    static constexpr int kXBytes = POOL ? 2 * kXPhase : 0;            // double-buffered
+    static constexpr int kNWRaw = (kBudget - kNA * kAEntry - kXBytes) / kWEntry;
     static constexpr int kNW = WRES ? 9 : (kNWRaw > 8 ? 8 : kNWRaw);   // WRES: entry = tap, never recycled
-    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + 1024 + 512 + 4 * 512 /*bias*/;
+    static constexpr int kSmemBytes = kNA * kAEntry + kNW * kWEntry + kXBytes + 1024 + 512 + 4 * 512 /*bias*/;
     static constexpr int kAccCols = BN < 32 ? 32 : BN;
     static constexpr int kTmemCols = 2 * kAccCols;
     static_assert(kNW >= 3, "W ring too shallow");
@@ -691,24 +855,27 @@ struct PairCfg {
     static_assert(BN % 16 == 0 && BN <= 256, "M=256 MMA: N multiple of 16, at most 256");
 };
 
-template <int BN, int PASSES, bool LEAN = false, bool WRES = false>
+template <int BN, int PASSES, bool LEAN = false, bool WRES = false, bool POOL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const GemmParams prm) {
-    using Cfg = PairCfg<BN, PASSES, WRES>;
+    using Cfg = PairCfg<BN, PASSES, WRES, POOL>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic window starts at the same offset in both CTAs, so the aligned pointers are at equal offsets too
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* w_ring = smem + Cfg::kNA * Cfg::kAEntry;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_ring + Cfg::kNW * Cfg::kWEntry);
+    float* xbuf = reinterpret_cast<float*>(w_ring + Cfg::kNW * Cfg::kWEntry);   // POOL: exchange buffer (else empty)
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(w_ring + Cfg::kNW * Cfg::kWEntry + Cfg::kXBytes);
     uint64_t* a_empty = a_full + Cfg::kNA;
     uint64_t* w_full = a_empty + Cfg::kNA;
     uint64_t* w_empty = w_full + Cfg::kNW;
     uint64_t* tmem_full = w_empty + Cfg::kNW;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* x_full = tmem_empty + 2;     // [2] POOL
+    uint64_t* x_empty = x_full + 2;        // [2] POOL
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 2);
     const float* bias_s = stage_bias(prm, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + 512));
 
     const int warp = threadIdx.x >> 5;
@@ -726,6 +893,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         for (int i = 0; i < Cfg::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < Cfg::kNW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&x_full[a], 1); mbar_init(&x_empty[a], 4); }   // POOL exchange
         fence_barrier_init();
     }
     // tcgen05.alloc.cta_group::2 is a two-party protocol that ptxas expands into messages through the RESERVED shared
@@ -751,7 +919,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             int ia = 0, iw = 0;
             for (int w = pair_id; w < n_work; w += n_pairs) {
                 const int n0 = (w % tiles_n) * BN + (int)rank * Cfg::kWRows;
-                const int m0 = (w / tiles_n) * (2 * kBM) + (int)rank * kBM;
+                int pb, pi, pk;
+                const int m0 = tile_m0(prm, w, tiles_n, (int)rank, pb, pi, pk);
                 for (int g = 0; g < n_groups; ++g, ++ia) {
                     const int chunk = g / 3, kh = g - chunk * 3;
                     const int c0 = chunk * 64;
@@ -836,12 +1005,17 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         int tl = 0;
         for (int w = pair_id; w < n_work; w += n_pairs, ++tl) {
             const int n0 = (w % tiles_n) * BN;
-            const int m0 = (w / tiles_n) * (2 * kBM) + (int)rank * kBM;
+            int pb, pi, pk;
+            const int m0 = tile_m0(prm, w, tiles_n, (int)rank, pb, pi, pk);
             if (w + n_pairs >= n_work && warp == 2 && lane == 0 && prm.stamps != nullptr && blockIdx.x == 0) {
                 mbar_wait(&tmem_full[tl & 1], (tl >> 1) & 1);
                 stamp(prm, 4);   // last accumulator complete (MMAs retired)
             }
-            epilogue_tile<BN, Cfg::kAccCols, true, LEAN>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
+            if constexpr (POOL)
+                epilogue_tile_pool<BN, Cfg::kAccCols>(prm, tmem_base, tl & 1, pb, pi, pk, (int)rank, q, (warp - 2) >> 2, lane,
+                                                      tmem_full, tmem_empty, tl, bias_s, xbuf, x_full, x_empty);
+            else
+                epilogue_tile<BN, Cfg::kAccCols, true, LEAN>(prm, tmem_base, tl & 1, m0, n0, q, (warp - 2) >> 2, lane, tmem_full, tmem_empty, tl, bias_s);
         }
         if (warp == 2 && lane == 0) stamp(prm, 5);   // this warp's epilogue done
     }
@@ -1047,9 +1221,9 @@ static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B com
     return g_pair_mode;
 }
 
-template <int BN, int PASSES, bool LEAN, bool WRES = false>
+template <int BN, int PASSES, bool LEAN, bool WRES = false, bool POOL = false>
 static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
-    using Cfg = PairCfg<BN, PASSES, WRES>;
+    using Cfg = PairCfg<BN, PASSES, WRES, POOL>;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const uint64_t kcols = (uint64_t)9 * d->Cin;
     int rc;
@@ -1080,10 +1254,20 @@ static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = g_stamps;
     p.softmax_cols = d->softmax_cols;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
-    auto kern = conv3x3_pair_kernel<BN, PASSES, LEAN, WRES>;
+    if (POOL) {   // work items: (frame, row pair, 128-column block), one N tile
+        p.pool = 1;
+        p.pool_Ho = (d->Hp - 1) / 2; p.pool_Wo = (d->Wp - 1) / 2;
+        p.pool_nblk = ceil_div(2 * p.pool_Wo, 128);
+        p.tiles_n = 1;
+        p.tiles_m = (d->M / (d->Hp * d->Wp)) * p.pool_Ho * p.pool_nblk;
+        p.n_work = p.tiles_m;
+    }
+    auto kern = conv3x3_pair_kernel<BN, PASSES, LEAN, WRES, POOL>;
     static int max_pairs = 0;  // per instantiation
     if (max_pairs == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -1119,6 +1303,14 @@ static bool wres_mode() {   // MV3D_WRES=0: weights through the ring also in the
 
 template <int BN, int PASSES>
 static int launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream) {
+    if constexpr ((BN == 64 || BN == 128) && PASSES >= 2) {
+        if (d->pool) {   // 2x2 max-pool fused into the epilogue (validated by mv3d_conv_gemm)
+            if constexpr (BN == 64) {
+                if (d->Cin == 64 && wres_mode()) return launch_pair_impl<BN, PASSES, true, true, true>(d, stream);
+            }
+            return launch_pair_impl<BN, PASSES, true, false, true>(d, stream);
+        }
+    }
     if constexpr (BN == 64 && PASSES >= 2) {
         if (d->Cin == 64 && wres_mode())
             return lean_epilogue_ok(d) ? launch_pair_impl<BN, PASSES, true, true>(d, stream)
@@ -1214,6 +1406,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
     p.softmax_cols = d->softmax_cols;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1267,6 +1460,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
     p.softmax_cols = d->softmax_cols;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
@@ -1343,6 +1537,10 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     MV3D_REQUIRE(!d->f32_dense || d->Hp > 0);
     MV3D_REQUIRE(d->split_k <= 1 || (!d->d_mask_hi && !d->d_addend_f32));
     MV3D_REQUIRE(d->softmax_cols >= 0 && d->softmax_cols <= d->N && d->softmax_cols % 2 == 0);
+    // fused 2x2 max-pool: CTA-pair tap-reuse kernel, one N tile of 64 / 128 channels, operand output only, plain epilogue
+    MV3D_REQUIRE(!d->pool || (d->taps == 9 && (d->N == 64 || d->N == 128) && d->Cin % 64 == 0 && d->passes >= 2 && d->d_out_hi &&
+                              !d->d_out_f32 && d->split_k <= 1 && d->Hp > 2 && d->Wp > 2 && pair_mode() != 0 &&
+                              lean_epilogue_ok(d) && (d->out_fmt == MV3D_FMT_F16E5 || d->ld_out % 16 == 0)));
     MV3D_REQUIRE(d->softmax_cols == 0 || (d->d_out_f32 && !d->d_out_hi && !d->relu && d->split_k <= 1 && !d->d_mask_hi && !d->d_addend_f32));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fc_swap_applicable(d)) return launch_fc_swapped(d, s);

@@ -238,14 +238,14 @@ conv3x3_small_cin_kernel(const float* __restrict__ in, int B, int H, int W, cons
             for (int e = 0; e < 8; ++e) v[e] = inside ? (relu ? fmaxf(acc[p][e], 0.f) : acc[p][e]) : 0.f;
             const long long pix = ((long long)b * Hp + hp) * Wp + wp;
             if (FMT == MV3D_FMT_F16E5) {
-                unsigned short hh16[8];
-                uint8_t h8[8], l8[8];
+                uint32_t h2[4];
+                unsigned short h8[4], l8[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split_f16e5(v[e], hh16[e], h8[e], l8[e]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out_hi) + pix * c_pad + co) = *reinterpret_cast<uint4*>(hh16);
+                for (int e = 0; e < 4; ++e) split_f16e5_x2(v[2 * e], v[2 * e + 1], h2[e], h8[e], l8[e]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out_hi) + pix * c_pad + co) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
                 uint8_t* row = reinterpret_cast<uint8_t*>(out_lo) + pix * c_pad * 2 + f16e5_off(co);
-                *reinterpret_cast<uint2*>(row) = *reinterpret_cast<uint2*>(h8);
-                *reinterpret_cast<uint2*>(row + 64) = *reinterpret_cast<uint2*>(l8);
+                *reinterpret_cast<uint2*>(row) = make_uint2(h8[0] | ((uint32_t)h8[1] << 16), h8[2] | ((uint32_t)h8[3] << 16));
+                *reinterpret_cast<uint2*>(row + 64) = make_uint2(l8[0] | ((uint32_t)l8[1] << 16), l8[2] | ((uint32_t)l8[3] << 16));
             } else {
                 __nv_bfloat16 vh[8], vl[8];
 #pragma unroll

@@ -141,6 +141,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive on a barrier of another CTA of the cluster with the default semantics (release at CTA scope: orders this
+// thread's earlier shared-memory reads, no GPU-wide fence) -- the consumer-release of a buffer the peer refills.
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 16-byte asynchronous store into the shared memory of a CTA of the cluster; its bytes are counted on an mbarrier of THAT
+// CTA (complete_tx), so the reader needs no fence: it waits for the barrier phase.
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t bar_cluster_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar_cluster_addr)
+                 : "memory");
+}
 // TMA load into THIS CTA's shared memory whose byte count completes on an mbarrier that may live in the peer CTA
 // of the pair (`bar_cluster_addr` is a shared::cluster address).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,

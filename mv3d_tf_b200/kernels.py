@@ -199,7 +199,8 @@ def _run_gemm(_flops=0.0, **kw):
 
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
          out_f32_dense: bool = False, mask: Optional["PadAct"] = None, mask_scale: float = 1.0,
-         addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2, softmax_cols: int = 0):
+         addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2, softmax_cols: int = 0,
+         pool: bool = False):
     """3x3 SAME or 1x1 convolution (+bias, +ReLU) on the PAD layout.  Returns (PadAct | None, dense f32 | None).
     mask / addend: the backward-data epilogue (out = (acc + addend) gated by mask > 0), see mv3d_gemm_desc."""
     assert w.cin_pad == a.c_pad, (w.cin_pad, a.c_pad)
@@ -210,6 +211,16 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
     dev = a.hi.device
     n_pad = pad_channels(w.cout)
     out = None
+    if pool:   # 2x2/2 VALID max-pool fused into the epilogue: only the pooled PAD activation is written
+        assert pool_fusable(a, w) and out_pad and not out_f32_dense and mask is None and addend is None
+        hi, lo = _new_pad(a.B, a.H // 2, a.W // 2, n_pad, precise or out_fmt == FMT_F16E5, dev)
+        out = PadAct(hi, lo, a.B, a.H // 2, a.W // 2, w.cout, out_fmt)
+        _run_gemm(_flops=2.0 * a.B * a.H * a.W * w.taps * min(a.C, w.cin) * w.cout,
+                  M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=passes, out_fmt=out_fmt,
+                  d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo),
+                  d_bias=ptr(w.bias) if use_bias else None, relu=int(relu), d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad,
+                  d_out_f32=None, ld_f32=0, f32_dense=0, split_k=1, pool=1)
+        return out, None
     if out_pad:
         assert out_fmt == FMT_BF16X2 or w.cout % 64 == 0
         hi, lo = _new_pad(a.B, a.H, a.W, n_pad, precise or out_fmt == FMT_F16E5, dev)
@@ -229,6 +240,21 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
               mask_scale=float(mask_scale), d_addend_f32=ptr(addend),
               ld_addend=addend.shape[-1] if addend is not None else 0, softmax_cols=int(softmax_cols))
     return out, dense
+
+
+POOL_FUSION = os.environ.get("MV3D_POOL_FUSION", "1") != "0"   # A/B switch
+POOL_MAX_WASTE = 1.15   # tiles are 128 columns wide: fuse only where the ragged last block costs < 15 % extra MMA work
+
+
+def pool_fusable(a: PadAct, w: PackedWeight) -> bool:
+    """Can maxpool2x2(conv3x3(a, w)) run as ONE kernel (mv3d_gemm_desc.pool)?  CTA-pair kernel with a single 64- or
+    128-channel N tile, operands in a 2-/3-pass format, and a width that 128-column blocks cover without much waste."""
+    if not (POOL_FUSION and PAIR_MODE and w.taps == 9 and w.cout in (64, 128) and a.c_pad % 64 == 0 and a.lo is not None):
+        return False
+    if a.H < 2 or a.W < 2:
+        return False
+    wo2 = 2 * (a.W // 2)
+    return (-(-wo2 // 128)) * 128 <= POOL_MAX_WASTE * wo2
 
 
 def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, relu: bool, precise: bool = True,

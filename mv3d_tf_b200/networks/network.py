@@ -295,7 +295,13 @@ class Network(object):
                     f.attrs['result'] = Val(dense=dense[..., off:off + f.channels])
                     off += f.channels
                 return Val(dense=dense[..., :c_o], extra=dict(softmax_folded=True) if fold else None)
-            out, dense = K.conv(v.pad, self._weight(name, fmt=v.pad.fmt), relu=relu, precise=self.precise,
+            pw = self._weight(name, fmt=v.pad.fmt)
+            if (k_h, k_w) == (3, 3) and self.precise and not self.training and want_pad and not want_dense \
+                    and [c.kind for c in node.consumer_nodes] == ['max_pool'] and K.pool_fusable(v.pad, pw):
+                # conv + Network.max_pool as one kernel: the un-pooled activation (4x the bytes) is never written
+                out, _ = K.conv(v.pad, pw, relu=relu, precise=self.precise, out_fmt=self._pad_out_fmt(node), pool=True)
+                return Val(pad=out, extra=dict(pooled=True))
+            out, dense = K.conv(v.pad, pw, relu=relu, precise=self.precise,
                                 out_pad=want_pad, out_f32_dense=want_dense, out_fmt=self._pad_out_fmt(node))
             return Val(pad=out, dense=dense)
         n = self._node(name, 'conv', [input], run, channels=c_o)
@@ -331,6 +337,8 @@ class Network(object):
 
         def run(vals, node):
             v = vals[node.inputs[0]]
+            if isinstance(v.extra, dict) and v.extra.get('pooled'):
+                return Val(pad=v.pad)   # taken in the producing conv's epilogue
             return Val(pad=K.maxpool2x2(v.pad))
         return self._node(name, 'max_pool', [input], run, channels=input.channels)
 

@@ -35,7 +35,9 @@ def iou_match_fraction(ref_boxes, got_boxes, thr=0.9):
     return float((iou.max(axis=1) >= thr).mean())
 
 
-FEATURES = ("conv1_2", "conv3_3", "conv5_3", "conv1_2_2", "conv3_3_2", "conv5_3_2", "rpn_bbox_pred")
+# conv2_1 (not conv1_2): fetching a layer's dense output switches its pool fusion off, and the fused conv1_2 + pool1
+# kernel is what production runs -- conv2_1 sits right behind it
+FEATURES = ("conv2_1", "conv3_3", "conv5_3", "conv2_1_2", "conv3_3_2", "conv5_3_2", "rpn_bbox_pred")
 
 
 def gpu_frame_outputs(net, raster, pts_dev, img, im_info, calib, fv_raster=None, features=FEATURES):

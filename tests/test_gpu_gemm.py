@@ -251,3 +251,44 @@ def test_conv3x3_f16e5(B, H, W, Cin, Cout, pair):
         assert _relerr(k.unpad_nhwc(o2), d2) < 1e-5   # bf16 hi/lo rendering of the output for bf16x3 consumers
     finally:
         k.set_pair_mode(prev)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,fmt", [(1, 40, 250, 64, 64, 1), (1, 41, 251, 64, 64, 1), (2, 25, 130, 64, 64, 0),
+                                                 (1, 37, 621, 128, 128, 1), (1, 16, 128, 64, 128, 0), (1, 2, 2, 64, 64, 1),
+                                                 (1, 187, 1242, 64, 64, 1)])
+def test_conv3x3_fused_maxpool(B, H, W, Cin, Cout, fmt):
+    """mv3d_gemm_desc.pool: conv3x3 + bias + ReLU + 2x2/2 VALID max-pool in one kernel (CTA pair = two image rows, row maxima
+    exchanged through distributed shared memory) against the same conv followed by the stand-alone pool kernel, and against
+    torch in float64.  Odd H / W drop the last row / column (VALID); the pooled PAD halos must be zero."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(3, 3, Cin, Cout, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    a = k.pad_nhwc(x, precise=True, fmt=fmt)
+    pw = k.pack_weights(w, b, fmt=fmt)
+    saved = k.POOL_MAX_WASTE
+    k.POOL_MAX_WASTE = 1e9       # exercise ragged widths too
+    try:
+        assert k.pool_fusable(a, pw)
+        fused, _ = k.conv(a, pw, relu=True, precise=True, out_fmt=fmt, pool=True)
+    finally:
+        k.POOL_MAX_WASTE = saved
+    plain, _ = k.conv(a, pw, relu=True, precise=True, out_fmt=fmt)
+    want = k.maxpool2x2(plain)
+    torch.cuda.synchronize()
+    assert (fused.H, fused.W, fused.fmt) == (H // 2, W // 2, fmt)
+    got_d, want_d = k.unpad_nhwc(fused), k.unpad_nhwc(want)
+    # same accumulators, same rendering; the two orders (render then max / max then render) agree except where two window
+    # elements render to neighbouring values -- bounded by one rendering step
+    assert float((got_d - want_d).abs().max()) <= 2.0 ** -12 * float(want_d.abs().max())
+    assert float((got_d != want_d).float().mean()) < 1e-3
+    xq = k.unpad_nhwc(a).double()
+    ref = torch.relu(torch.nn.functional.conv2d(xq.permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), b.double(), padding=1))
+    ref = torch.nn.functional.max_pool2d(ref, 2, 2).permute(0, 2, 3, 1)
+    assert _relerr(got_d, ref) < (3e-4 if fmt else 5e-5)
+    hi = fused.hi.view(torch.int16)
+    assert int(hi[:, :, 0, :].abs().max()) == 0 and int(hi[:, H // 2, :, :].abs().max()) == 0
+    lo = fused.lo.view(torch.int16)
+    assert int(lo[:, :, 0, :].abs().max()) == 0 and int(lo[:, H // 2, :, :].abs().max()) == 0
