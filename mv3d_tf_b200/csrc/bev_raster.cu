@@ -71,9 +71,11 @@ __global__ void raster_fill_count_kernel(const float* __restrict__ pts, int n, i
                                          int n_tail) {
     const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long nthr = (long long)gridDim.x * blockDim.x;
+    // plain 16-byte stores: measured on the B200, a write-only fill with default caching reaches ~7 TB/s (torch's fill),
+    // the .cs streaming hint used here before ran the same loop at 2.9 TB/s
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (long long i = tid; i < vec_a; i += nthr) __stcs(out_a + i, z);
-    for (long long i = tid; i < vec_b; i += nthr) __stcs(out_b + i, z);
+    for (long long i = tid; i < vec_a; i += nthr) out_a[i] = z;
+    for (long long i = tid; i < vec_b; i += nthr) out_b[i] = z;
     if (tid < n_tail) tail[tid] = 0.f;
     for (long long i = tid; i < n; i += nthr) {
         const float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1];
@@ -308,7 +310,7 @@ raster_inplace_kernel(const float* __restrict__ pts, int n, int stride, RasterGe
     const long long nthr = (long long)gridDim.x * blockDim.x;
     uint4* out4 = reinterpret_cast<uint4*>(top);
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (long long i = tid; i < vec4; i += nthr) __stcs(out4 + i, z);
+    for (long long i = tid; i < vec4; i += nthr) out4[i] = z;
     if (tid < n_tail) top[vec4 * 4 + tid] = 0.f;
     grid.sync();
     mark_points(pts, n, stride, g, slo, shi, reinterpret_cast<unsigned int*>(top), tid, nthr);
