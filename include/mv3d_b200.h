@@ -157,6 +157,10 @@ typedef struct {
     void* d_top_lo;
     int source;           /* MV3D_ROI_* (mv3d_roi_pool_fused only; mv3d_roi_pool_multiview always reads d_rois) */
     float* d_rois_out;    /* optional (R,5) [batch,x1,y1,x2,y2]: the rectangle the kernel pooled (fused form) */
+    /* fused form, optional: read the feature map from the PAD operand planes the producing conv already writes
+     * ((B, H+1, W+1, pad_c), pad_fmt = MV3D_FMT_*) instead of a dense float32 copy (d_data may then be NULL); the values
+     * pooled are the operand renderings (what Network.run returns for that layer when fetched) */
+    const void* d_pad_hi; const void* d_pad_lo; int pad_fmt, pad_c;
 } mv3d_roi_view;
 /* projection constants of the fused form: BEV grid (transform.py:3-20) + clip bounds (im_info), the float32 3x4 image
  * projection (P2.R0).Tr by value or as a device pointer (graph replay), the FV map geometry (radians) */

@@ -36,6 +36,11 @@ struct RoiViewDev {
     __nv_bfloat16* top_lo;
     int source;        // MV3D_ROI_GIVEN / _BEV / _IMG / _FV (fused kernel)
     float* rois_out;   // optional (R,5): the rectangle that was pooled
+    // optional: the feature map in the PAD operand layout the producing conv writes for its other consumers
+    // ((B, H+1, W+1, pad_c) 16-bit planes, fmt MV3D_FMT_*); read instead of `data` when set
+    const unsigned short* pad_hi;
+    const unsigned short* pad_lo;
+    int pad_fmt, pad_c;
 };
 struct RoiProjDev {
     BevGrid bev;
@@ -156,6 +161,39 @@ __device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* v) {
     return r;
 }
 
+// 8 consecutive channels of feature-map cell (h, w) of frame `batch` as float32: from the dense NHWC map, or rebuilt from
+// the PAD operand planes (f16e5: fp16 + e5m2 residual / 4096; bf16 pair: hi + lo -- both sums are exact in float32).
+__device__ __forceinline__ void load_cell8(const RoiViewDev& V, int batch, int h, int w, int C, int c0, float* x) {
+    if (V.pad_hi == nullptr) {
+        const float* p = V.data + (((size_t)batch * V.H + h) * V.W + w) * C + c0;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        return;
+    }
+    const size_t pix = ((size_t)batch * (V.H + 1) + h) * (V.W + 1) + w + 1;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(V.pad_hi + pix * V.pad_c + c0));
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    if (V.pad_fmt == MV3D_FMT_F16E5) {
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(V.pad_lo) + pix * V.pad_c * 2 + f16e5_off(c0) + 64;
+        const uint2 lv = __ldg(reinterpret_cast<const uint2*>(row));
+        const uint32_t lw[2] = {lv.x, lv.y};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned short h16 = (unsigned short)(hw[e >> 1] >> ((e & 1) * 16));
+            const uint8_t l8 = (uint8_t)(lw[e >> 2] >> ((e & 3) * 8));
+            x[e] = join_f16e5(h16, l8);
+        }
+    } else {
+        const uint4 lv = __ldg(reinterpret_cast<const uint4*>(V.pad_lo + pix * V.pad_c + c0));
+        const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t hb = (hw[e >> 1] >> ((e & 1) * 16)) << 16, lb = (lw[e >> 1] >> ((e & 1) * 16)) << 16;
+            x[e] = __uint_as_float(hb) + __uint_as_float(lb);
+        }
+    }
+}
+
 // grid (R, n_views, ceil(C / 64)), C % 8 == 0.  Rows >= *d_num_valid: zero outputs, argmax -1, zero rectangle.
 // One CTA = one roi x one view x one 64-channel slice: the window's cells of that slice are staged in shared memory
 // in ONE round of independent 128-bit loads (narrower channel sub-slices when the window has more than 108 cells,
@@ -241,7 +279,6 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
     const int w0 = min(max(rsw, 0), W), w1 = min(max((int)ceilf((float)PW * bsw) + rsw, 0), W);
     const int wh = max(h1 - h0, 0), ww = max(w1 - w0, 0);
     const int cells = wh * ww;
-    const float* img = V.data + (size_t)batch * H * W * C;
     // channel sub-slice: as many of this CTA's channels (multiple of 8) as fit the stage next to `cells` window cells
     const int Cmine = c_hi - c_lo;
     int Cs = Cmine;
@@ -255,10 +292,13 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
         const int cs = min(Cs, c_hi - cb), v4 = cs / 4, lanes = cs / 8;
         if (staged && cells > 0) {
             __syncthreads();                            // previous sub-slice fully consumed
-            for (int idx = tid; idx < cells * v4; idx += kFusedThreads) {
-                const int cell = idx / v4, v = idx - cell * v4;
+            for (int idx = tid; idx < cells * lanes; idx += kFusedThreads) {
+                const int cell = idx / lanes, v = idx - cell * lanes;
                 const int h = h0 + cell / ww, w = w0 + cell % ww;
-                stage[idx] = __ldg(reinterpret_cast<const float4*>(img + ((size_t)h * W + w) * C + cb) + v);
+                float x[8];
+                load_cell8(V, batch, h, w, C, cb + v * 8, x);
+                stage[cell * v4 + 2 * v] = make_float4(x[0], x[1], x[2], x[3]);
+                stage[cell * v4 + 2 * v + 1] = make_float4(x[4], x[5], x[6], x[7]);
             }
             __syncthreads();
         }
@@ -277,15 +317,14 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
             for (int h = hs; h < he; ++h)
                 for (int w = ws; w < we; ++w) {
                     const int idx0 = (h * W + w) * C + cb + lane * 8;
-                    float4 a, b;
+                    float x[8];
                     if (staged) {
                         const float4* sp = stage + ((h - h0) * ww + (w - w0)) * v4 + lane * 2;
-                        a = sp[0]; b = sp[1];
+                        const float4 a = sp[0], b = sp[1];
+                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
                     } else {
-                        a = __ldg(reinterpret_cast<const float4*>(img + idx0));
-                        b = __ldg(reinterpret_cast<const float4*>(img + idx0 + 4));
+                        load_cell8(V, batch, h, w, C, cb + lane * 8, x);
                     }
-                    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
                         if (x[e] > mv[e]) { mv[e] = x[e]; mi[e] = idx0 + e; }
@@ -333,7 +372,9 @@ using namespace mv3d;
 static int fill_views(const mv3d_roi_view* views, int n_views, bool fused, RoiViews* v) {
     for (int i = 0; i < n_views; ++i) {
         const int src = fused ? views[i].source : MV3D_ROI_GIVEN;
-        MV3D_REQUIRE(views[i].d_data && views[i].height > 0 && views[i].width > 0);
+        MV3D_REQUIRE((views[i].d_data || views[i].d_pad_hi) && views[i].height > 0 && views[i].width > 0);
+        MV3D_REQUIRE(!views[i].d_pad_hi || (views[i].d_pad_lo && views[i].pad_c % 8 == 0 &&
+                                             (views[i].pad_fmt == MV3D_FMT_BF16X2 || (views[i].pad_fmt == MV3D_FMT_F16E5 && views[i].pad_c % 64 == 0))));
         MV3D_REQUIRE(src >= MV3D_ROI_GIVEN && src <= MV3D_ROI_FV);
         MV3D_REQUIRE(src != MV3D_ROI_GIVEN || views[i].d_rois);
         MV3D_REQUIRE(views[i].d_top || views[i].d_top_hi);
@@ -344,6 +385,9 @@ static int fill_views(const mv3d_roi_view* views, int n_views, bool fused, RoiVi
         v->v[i].top_lo = static_cast<__nv_bfloat16*>(views[i].d_top_lo);
         v->v[i].source = src;
         v->v[i].rois_out = fused ? views[i].d_rois_out : nullptr;
+        v->v[i].pad_hi = static_cast<const unsigned short*>(views[i].d_pad_hi);
+        v->v[i].pad_lo = static_cast<const unsigned short*>(views[i].d_pad_lo);
+        v->v[i].pad_fmt = views[i].pad_fmt; v->v[i].pad_c = views[i].pad_c;
     }
     return MV3D_OK;
 }
@@ -388,6 +432,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_multiview(
     RoiViews v = {};
     const int rc = fill_views(views, n_views, false, &v);
     if (rc != MV3D_OK) return rc;
+    for (int i = 0; i < n_views; ++i) MV3D_REQUIRE(!v.v[i].pad_hi || channels % 8 == 0);   // PAD input: staged kernel only
     if (channels % 8 == 0) {   // staged kernel, given rectangles
         RoiProjDev proj = {};
         return launch_fused(v, n_views, proj, nullptr, num_rois, d_num_valid, channels, pooled_height, pooled_width,

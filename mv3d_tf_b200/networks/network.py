@@ -98,6 +98,7 @@ class Network(object):
         self._needed_now = set()
         self._anchor_pre = None
         self._aux_stream = None
+        self.roi_from_pad = os.environ.get('MV3D_ROI_FROM_PAD', '1') != '0'   # fused ROI pool reads conv5's PAD planes
         self.node_events = None         # list -> Network.run appends (name, kind, start event, end event) per node
         self.last_num_rois = None
         self.training = False           # True: roi_pool keeps argmax, dropout draws masks (set by the solver)
@@ -229,7 +230,8 @@ class Network(object):
                     return c.attrs.get('k') == (3, 3)
                 if c.kind == 'max_pool':
                     return all(accepts(cc) for cc in c.consumer_nodes if cc.kind in ('conv', 'max_pool'))
-                return True  # reads the dense rendering, not the PAD tensor
+                return True
+            # the ROI pool reads either rendering, so it does not vote: a map only it reads stays bf16 hi/lo (2^-17)
             readers = [c for c in node.consumer_nodes if c.kind in ('conv', 'max_pool')]
             fmt = K.FMT_F16E5 if readers and all(accepts(c) for c in readers) else K.FMT_BF16X2
             node.attrs['pad_out_fmt'] = fmt
@@ -247,9 +249,16 @@ class Network(object):
 
         def run(vals, node):
             v = vals[node.inputs[0]]
-            want_pad = any(c in ('conv', 'max_pool') for c in node.consumers) or self.training
-            want_dense = (not want_pad) or any(c not in ('conv', 'max_pool') for c in node.consumers) \
+            # the fused ROI pool reads the PAD operand planes directly (inference): no dense float32 copy of conv5_3
+            pad_readers = ('conv', 'max_pool') if (self.training or not self.roi_from_pad) else ('conv', 'max_pool', 'roi_pool')
+            want_pad = any(c in pad_readers for c in node.consumers) or self.training
+            want_dense = (not want_pad) or any(c not in pad_readers for c in node.consumers) \
                 or node.attrs.get('fetched', False)
+            unpad_for_fetch = False
+            if want_dense and 'roi_pool' in pad_readers and 'roi_pool' in node.consumers and (k_h, k_w) == (3, 3) \
+                    and all(c in pad_readers for c in node.consumers):
+                # fetched only: return the operand rendering the pool reads (unpad), not a second float32 epilogue output
+                want_dense, unpad_for_fetch = False, True
             if (k_h, k_w) == (3, 3) and c_i <= 4 and c_o % 8 == 0 and v.dense is not None and v.pad is None \
                     and not self.training and want_pad and not want_dense:
                 # tiny-channel first layer (RGB / front view, K = 27): one direct kernel straight into the consumer's
@@ -303,6 +312,8 @@ class Network(object):
                 return Val(pad=out, extra=dict(pooled=True))
             out, dense = K.conv(v.pad, pw, relu=relu, precise=self.precise,
                                 out_pad=want_pad, out_f32_dense=want_dense, out_fmt=self._pad_out_fmt(node))
+            if unpad_for_fetch:
+                dense = K.unpad_nhwc(out)
             return Val(pad=out, dense=dense)
         n = self._node(name, 'conv', [input], run, channels=c_o)
         n.attrs['k'] = (k_h, k_w)
@@ -451,19 +462,25 @@ class Network(object):
             results = []
             R = None
             for k, m in enumerate(group):
-                feat = vals[m.inputs[0]].dense
+                fv_ = vals[m.inputs[0]]
+                from_pad = (not self.training) and self.roi_from_pad and fv_.pad is not None and fv_.pad.lo is not None
+                feat = None if from_pad else fv_.dense
                 r = vals[m.inputs[1]].dense.contiguous()
                 R = r.shape[0]
                 ph, pw, sc = m.attrs['cfg']
-                Cc = feat.shape[-1]
-                hi = torch.empty((R, ph * pw * Cc), dtype=torch.bfloat16, device=feat.device)
+                Cc = fv_.pad.C if from_pad else feat.shape[-1]
+                fdev = fv_.pad.hi.device if from_pad else feat.device
+                fH, fW = (fv_.pad.H, fv_.pad.W) if from_pad else (feat.shape[1], feat.shape[2])
+                hi = torch.empty((R, ph * pw * Cc), dtype=torch.bfloat16, device=fdev)
                 lo = torch.empty_like(hi) if self.precise else None
                 top = None
                 if m.attrs.get('fetched', False):
-                    top = torch.empty((R, ph, pw, Cc), dtype=torch.float32, device=feat.device)
-                arg = torch.empty((R, ph, pw, Cc), dtype=torch.int32, device=feat.device) if self.training else None
+                    top = torch.empty((R, ph, pw, Cc), dtype=torch.float32, device=fdev)
+                arg = torch.empty((R, ph, pw, Cc), dtype=torch.int32, device=fdev) if self.training else None
                 v = views[k]
-                v.d_data, v.d_rois, v.height, v.width = ptr(feat), ptr(r), feat.shape[1], feat.shape[2]
+                v.d_data, v.d_rois, v.height, v.width = ptr(feat), ptr(r), fH, fW
+                if from_pad:
+                    v.d_pad_hi, v.d_pad_lo, v.pad_fmt, v.pad_c = ptr(fv_.pad.hi), ptr(fv_.pad.lo), fv_.pad.fmt, fv_.pad.c_pad
                 v.spatial_scale, v.d_top, v.d_argmax, v.d_top_hi, v.d_top_lo = sc, ptr(top), ptr(arg), ptr(hi), ptr(lo)
                 results.append(Val(dense=top, hi=hi, lo=lo, extra=dict(feat=feat, rois=r, argmax=arg, scale=sc)))
             ph, pw, _ = node.attrs['cfg']

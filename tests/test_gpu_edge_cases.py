@@ -194,3 +194,32 @@ def test_roi_pool_fused_projects_and_pools_three_views(oracle):
     v.d_top, v.source = ptr(top2), ROI_GIVEN
     _fused_pool(views2, torch.from_numpy(p).cuda(), proj, R, num, Cc)
     assert torch.equal(top2, tops[1])
+
+
+@pytest.mark.parametrize("fmt", [0, 1], ids=["bf16x2", "f16e5"])
+def test_roi_pool_reads_pad_operand_planes(oracle, fmt):
+    """The fused ROI pool fed from the PAD operand planes a conv writes (no dense float32 copy): values and arg-max equal
+    the oracle's RoiPool on the operand RENDERING of the map (what Network.run returns for that layer), bit for bit."""
+    from mv3d_tf_b200 import kernels as k
+    from mv3d_tf_b200._lib import ROI_GIVEN, RoiView, check, current_stream, lib, ptr
+
+    rng = np.random.default_rng(3 + fmt)
+    H, W, Cc, R = 46, 155, 128, 90
+    x = torch.from_numpy(rng.normal(size=(1, H, W, Cc)).astype(np.float32)).cuda()
+    pad = k.pad_nhwc(x, precise=True, fmt=fmt)
+    rendered = k.unpad_nhwc(pad).cpu().numpy()
+    x1, y1 = rng.integers(-60, W * 8, R), rng.integers(-60, H * 8, R)
+    rois = np.stack((np.zeros(R), x1, y1, x1 + rng.integers(0, 300, R), y1 + rng.integers(0, 200, R)), 1).astype(np.float32)
+    rois[0] = [0, 0, 0, W * 8, H * 8]          # whole map: direct reads
+    r_dev = torch.from_numpy(rois).cuda()
+    top = torch.empty((R, 7, 7, Cc), device="cuda")
+    arg = torch.empty((R, 7, 7, Cc), dtype=torch.int32, device="cuda")
+    views = (RoiView * 1)()
+    v = views[0]
+    v.d_data, v.d_rois, v.height, v.width, v.spatial_scale = None, ptr(r_dev), H, W, 0.125
+    v.d_top, v.d_argmax, v.source = ptr(top), ptr(arg), ROI_GIVEN
+    v.d_pad_hi, v.d_pad_lo, v.pad_fmt, v.pad_c = ptr(pad.hi), ptr(pad.lo), fmt, pad.c_pad
+    check(lib().mv3d_roi_pool_multiview(views, 1, R, None, Cc, 7, 7, current_stream()), "mv3d_roi_pool_multiview")
+    wt, wa = oracle.roi_pool_fwd(rendered, rois)
+    assert np.array_equal(top.cpu().numpy(), wt)
+    assert np.array_equal(arg.cpu().numpy(), wa)

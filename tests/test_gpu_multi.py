@@ -25,4 +25,4 @@ def test_two_rank_nccl_inference_bitwise_and_gradient_sum():
     print(out)
     assert out["inference_bitwise_equal"] and out["inference_rows"] > 0
     assert out["grad_rel_err"] <= 1e-6, out
-    assert out["grad_buckets"] >= 2
+    assert out["grad_buckets"] >= 2 and out["grad_covered"]
