@@ -57,6 +57,7 @@ struct GemmParams {
                       // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
     int softmax_cols;   // mv3d_gemm_desc::softmax_cols
     int pool, pool_Ho, pool_Wo, pool_nblk;   // fused 2x2 max-pool (pair kernel, POOL): pooled size, 128-column blocks per row
+    int e5_ksteps;      // f16e5 (PASSES = 2): 32-byte k-steps of the e5m2 row the MMA loop covers -- 4 = both correction terms, 2 = A_h W_l only
     long long* stamps;  // measurement only (mv3d_gemm_set_stamps): clock64 of pair 0's phases, see conv3x3_pair_kernel
 };
 
@@ -987,7 +988,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                     mma_f16_pair_lo(d_tmem, da + (Cfg::kAPlane >> 4), db, idesc, 1u);
                                     mma_f16_pair_lo(d_tmem, da, db + (Cfg::kWPlane >> 4), idesc, 1u);
                                 }
-                                if (PASSES == 2)
+                                if (PASSES == 2 && k < prm.e5_ksteps)
                                     mma_f8_pair_lo(d_tmem, da + (Cfg::kAPlane >> 4), db + (Cfg::kWPlane >> 4), idesc8, 1u);
                             }
                             if (!WRES) mma_commit_pair(&w_empty[ew], 3);
@@ -1221,6 +1222,12 @@ static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B com
     return g_pair_mode;
 }
 
+static int g_e5_ksteps = -1;
+static int e5_ksteps_mode() {   // MV3D_F16E5_TERMS=1: experiment -- drop the activation-residual term (A_l W_h) of the f16e5 product
+    if (g_e5_ksteps < 0) { const char* e = getenv("MV3D_F16E5_TERMS"); g_e5_ksteps = (e && atoi(e) == 1) ? 2 : 4; }
+    return g_e5_ksteps;
+}
+
 template <int BN, int PASSES, bool LEAN, bool WRES = false, bool POOL = false>
 static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     using Cfg = PairCfg<BN, PASSES, WRES, POOL>;
@@ -1253,8 +1260,8 @@ static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.out_fmt = d->out_fmt; p.acc_scale = (PASSES == 2) ? 1.f / kF16E5Scale : 1.f;
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = g_stamps;
+    p.e5_ksteps = e5_ksteps_mode();
     p.softmax_cols = d->softmax_cols;
-    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
     p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
