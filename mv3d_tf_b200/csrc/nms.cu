@@ -16,11 +16,18 @@
 //
 // IoU arithmetic is the reference's, float32 with IEEE roundings (file compiled with --fmad=false):
 //   area = (x2-x1+1)*(y2-y1+1); w = max(0, min(x2)-max(x1)+1); ovr = w*h / (area_i + area_j - w*h).
+#include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mv3d {
+
+using namespace ptx;
 
 constexpr int kNmsTile = 64;
 constexpr int kMaskThreads = 256;
@@ -180,6 +187,159 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask, int n_max, const 
     if (tid == 0) *num_out = count_s;
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// nms_lazy_kernel: greedy NMS that only ever tests a candidate against KEPT boxes (and its own block), for callers
+// that want at most max_keep <= 2048 survivors (the proposal layer: 300 at test time, 2000 in training).  The all-pairs
+// mask above costs n^2/2 tests (18 M at n = 6000) of which the keep chain reads the rows of the <= max_keep kept boxes
+// only, and it stops at max_keep -- here the work is (candidates scanned) x (kept so far).
+// One cluster of 8 CTAs x 512 threads walks the sorted candidates in blocks of 512:
+//   (a) every CTA tests the block's 512 candidates (one per thread) against its 1/8 slice of the kept list (boxes in
+//       shared memory, broadcast reads) and ORs the 512 suppression bits into ALL eight CTAs' shared memory (DSMEM atomics);
+//   (b) every CTA forms 1/8 of the block's own 512 x 512 upper-triangular mask (a warp per row, __ballot_sync words)
+//       and stores its rows into all eight CTAs' shared memory;
+//   one cluster barrier; then EVERY CTA resolves the block redundantly (same inputs, same result: no second exchange):
+//   if the block's own mask is empty, all un-suppressed candidates are kept at once (prefix popcount); otherwise warp 0
+//   walks the chain with one step per KEPT box (ffs -> one shared-memory word -> OR), the later words' suppression
+//   accumulating in lanes 0..7 off the critical path.  Exchange buffers are double-buffered by block parity, so one
+//   barrier per block suffices.  Same predicate, same order => the same survivor list as the mask + reduce path.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kLazyC = 8;            // CTAs per cluster
+constexpr int kLazyBS = 512;         // candidates per block
+constexpr int kLazyThreads = 512;
+constexpr int kLazyWords = kLazyBS / 64;
+constexpr int kLazyMaxKeep = 2048;
+
+struct LazySmem {
+    float4 kept_box[kLazyMaxKeep];
+    float4 cand_box[kLazyBS];
+    unsigned long long rowsT[2][kLazyWords][kLazyBS];   // [parity][word][row]: word-major, conflict-free for the chain
+    unsigned long long flags[2][kLazyWords + 1];        // suppressed-by-kept bits; [8] != 0: the block's own mask has a bit
+    float kept_area[kLazyMaxKeep];
+    float cand_area[kLazyBS];
+    int kept_blk[kLazyBS];
+    int m_s;
+};
+
+__global__ void __cluster_dims__(kLazyC, 1, 1) __launch_bounds__(kLazyThreads)
+nms_lazy_kernel(const float* __restrict__ boxes, int n_max, int stride, const int* __restrict__ d_n, double thresh,
+                int rule_ge, int max_keep, int* __restrict__ keep_out, int* __restrict__ num_out) {
+    extern __shared__ __align__(16) unsigned char lazy_smem_raw[];
+    LazySmem& S = *reinterpret_cast<LazySmem*>(lazy_smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n = n_max;
+    if (d_n) n = min(n, *d_n);
+    if (max_keep <= 0 || max_keep > n) max_keep = n;
+    const float thresh_gt = (float)thresh;
+    float thresh_ge = (float)thresh;
+    if ((double)thresh_ge < thresh) thresh_ge = nextafterf(thresh_ge, INFINITY);
+    const bool positive = thresh > 0.0;
+    if (tid < 2 * (kLazyWords + 1)) (&S.flags[0][0])[tid] = 0ull;
+    cluster.sync();                       // every CTA's exchange buffers exist and are clear before the first remote write
+    int cnt = 0;
+    for (int b = 0, base = 0; base < n && cnt < max_keep; ++b, base += kLazyBS) {
+        const int p = b & 1;
+        const int valid = min(kLazyBS, n - base);
+        const float4 box = tid < valid ? load_box(boxes, stride, base + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float area = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
+        S.cand_box[tid] = box;
+        S.cand_area[tid] = area;
+        // (a) against this CTA's slice of the kept list
+        bool sup = false;
+        if (tid < valid)
+            for (int i = rank; i < cnt; i += kLazyC)
+                if (suppresses(S.kept_box[i], S.kept_area[i], box, area, rule_ge, thresh_ge, thresh_gt, positive)) { sup = true; break; }
+        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0 && bal != 0u) {   // this warp's 32 candidates = one 32-bit half of a flags word
+            const uint32_t a = smem_u32(&S.flags[p][warp >> 1]) + 4u * (warp & 1);
+            for (int r = 0; r < kLazyC; ++r) red_or_cluster_u32(mapa_u32(a, r), bal);
+        }
+        __syncthreads();                  // cand_box / cand_area complete
+        // (b) rows rank, rank + 8, ... of the block's own mask
+        bool any = false;
+        for (int q = warp; q < kLazyBS / kLazyC; q += kLazyThreads / 32) {
+            const int r = rank + kLazyC * q;
+            unsigned long long mine = 0ull;
+            if (r < valid) {
+                const float4 a = S.cand_box[r];
+                const float a_area = S.cand_area[r];
+                for (int ch = r >> 5; ch < ((valid + 31) >> 5); ++ch) {
+                    const int col = ch * 32 + lane;
+                    const bool s = col > r && col < valid &&
+                                   suppresses(a, a_area, S.cand_box[col], S.cand_area[col], rule_ge, thresh_ge, thresh_gt, positive);
+                    const unsigned w32 = __ballot_sync(0xffffffffu, s);
+                    if (lane == (ch >> 1)) mine |= (unsigned long long)w32 << (32 * (ch & 1));
+                }
+            }
+            any |= mine != 0ull;
+            if (lane < kLazyWords) {
+                const uint32_t a = smem_u32(&S.rowsT[p][lane][r]);
+                for (int rr = 0; rr < kLazyC; ++rr) st_cluster_u64(mapa_u32(a, rr), mine);
+            }
+        }
+        if (__any_sync(0xffffffffu, any) && lane == 0)
+            for (int rr = 0; rr < kLazyC; ++rr) red_or_cluster_u32(mapa_u32(smem_u32(&S.flags[p][kLazyWords]), rr), 1u);
+        cluster.sync();                   // flags[p] and rowsT[p] of this block complete in every CTA
+        int m;
+        if (S.flags[p][kLazyWords] == 0ull) {
+            // nobody in the block suppresses anybody in it: every candidate the kept list left alone survives
+            int before = 0, total = 0;
+            bool mine_ok = false;
+#pragma unroll
+            for (int w = 0; w < kLazyWords; ++w) {
+                unsigned long long av = ~S.flags[p][w];
+                const int vb = valid - w * 64;
+                av = vb <= 0 ? 0ull : (vb < 64 ? av & ((1ull << vb) - 1ull) : av);
+                total += __popcll(av);
+                if (w < (tid >> 6)) before += __popcll(av);
+                if (w == (tid >> 6)) {
+                    before += __popcll(av & ((1ull << (tid & 63)) - 1ull));
+                    mine_ok = (av >> (tid & 63)) & 1ull;
+                }
+            }
+            m = min(total, max_keep - cnt);
+            if (mine_ok && before < m) S.kept_blk[before] = tid;
+        } else {
+            if (warp == 0) {
+                int c = cnt, mm = 0;
+                unsigned long long pend = 0ull;     // lane l < 8: suppression of word l by this block's kept boxes so far
+                const int nw = (valid + 63) >> 6;
+                for (int w = 0; w < nw && c < max_keep; ++w) {
+                    unsigned long long cur = S.flags[p][w] | __shfl_sync(0xffffffffu, pend, w);
+                    const int vb = valid - w * 64;
+                    if (vb < 64) cur |= ~0ull << vb;
+                    while (c < max_keep) {
+                        const unsigned long long avail = ~cur;
+                        if (avail == 0ull) break;
+                        const int bit = __ffsll((long long)avail) - 1;
+                        const int k = w * 64 + bit;
+                        if (lane == 0) S.kept_blk[mm] = k;
+                        pend |= S.rowsT[p][lane & (kLazyWords - 1)][k];
+                        cur |= S.rowsT[p][w][k] | (1ull << bit);
+                        ++c; ++mm;
+                    }
+                }
+                if (lane == 0) S.m_s = mm;
+            }
+            __syncthreads();
+            m = S.m_s;
+        }
+        __syncthreads();                  // kept_blk complete
+        for (int i = tid; i < m; i += kLazyThreads) {
+            const int k = S.kept_blk[i];
+            S.kept_box[cnt + i] = S.cand_box[k];
+            S.kept_area[cnt + i] = S.cand_area[k];
+            if (rank == 0) keep_out[cnt + i] = base + k;
+        }
+        if (tid <= kLazyWords) S.flags[p][tid] = 0ull;   // clear for block b + 2 (peers write it only after the next barrier)
+        cnt += m;
+        __syncthreads();                  // kept list extended; cand_box free for the next block
+    }
+    if (rank == 0 && tid == 0) *num_out = cnt;
+    cluster.sync();                       // no CTA leaves while a peer may still address its shared memory
+}
+
 static size_t nms_words(int n) { return (size_t)ceil_div(n > 0 ? n : 1, kNmsTile); }
 
 }  // namespace mv3d
@@ -203,6 +363,20 @@ extern "C" __attribute__((visibility("default"))) int mv3d_nms(const float* d_bo
         return MV3D_OK;
     }
     MV3D_REQUIRE(d_boxes != nullptr);
+    static int lazy = -1;   // MV3D_NMS_LAZY=0: always the all-pairs mask + reduce path (A/B comparisons)
+    if (lazy < 0) { const char* e = getenv("MV3D_NMS_LAZY"); lazy = e ? atoi(e) : 1; }
+    if (lazy && max_keep > 0 && max_keep <= kLazyMaxKeep) {
+        static bool lazy_attr = false;
+        if (!lazy_attr) {
+            cudaError_t e = cudaFuncSetAttribute(nms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LazySmem));
+            if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+            lazy_attr = true;
+        }
+        nms_lazy_kernel<<<kLazyC, kLazyThreads, sizeof(LazySmem), s>>>(d_boxes, n_boxes, box_stride, d_n_boxes, thresh, rule_ge,
+                                                                      max_keep, d_keep_out, d_num_out);
+        MV3D_CHECK_LAUNCH();
+        return MV3D_OK;
+    }
     const int nwords = (int)nms_words(n_boxes);
     MV3D_REQUIRE(nwords <= kMaxWords);
     if (!d_workspace || workspace_bytes < mv3d_nms_workspace_bytes(n_boxes)) return MV3D_ERR_WORKSPACE;

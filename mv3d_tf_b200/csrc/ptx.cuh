@@ -133,6 +133,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// plain data exchange through distributed shared memory (addresses from mapa_u32).  NOTE: the generic-address atomicOr on a
+// 64-bit word of a PEER's shared memory compiles to a non-atomic load/or/store (neither global nor shared::cta) -- use these.
+__device__ __forceinline__ void red_or_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t cluster_addr, uint64_t v) {
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

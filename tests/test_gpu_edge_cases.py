@@ -114,11 +114,47 @@ def test_nms_clustered_boxes(oracle, n, clusters, thresh):
     assert gpu_nms(d, thresh) == oracle.nms(d, thresh, "gt")
     order = np.argsort(d[:, 4], kind="stable")[::-1]
     boxes = torch.from_numpy(np.ascontiguousarray(d[order, :4])).cuda()
-    for cap in (1, 17, len(want)):
+    for cap in (1, 17, 300, 2000, len(want)):       # <= 2048: the lazy cluster kernel; above: mask + keep chain
         keep, num = nms_device(boxes, thresh, True, max_keep=cap)
         m = int(num.item())
         assert m == min(cap, len(want))
         assert list(order[keep[:m].cpu().numpy()]) == want[:m]
+    want_gt = oracle.nms(d, thresh, "gt")
+    keep, num = nms_device(boxes, thresh, False, max_keep=300)
+    m = int(num.item())
+    assert m == min(300, len(want_gt)) and list(order[keep[:m].cpu().numpy()]) == want_gt[:m]
+
+
+@pytest.mark.parametrize("n", [1, 2, 511, 512, 513, 1025, 6000, 12000])
+@pytest.mark.parametrize("spread", [560, 120])
+def test_nms_lazy_kernel_equals_full_chain(oracle, n, spread):
+    """mv3d_nms with 0 < max_keep <= 2048 (nms_lazy_kernel: candidates tested against kept boxes only, 8-CTA cluster)
+    returns the prefix of the full greedy chain, for sparse (nothing suppressed: the block fast path) and dense inputs,
+    block-boundary sizes, and a device-side box count."""
+    from mv3d_tf_b200._lib import check, current_stream, lib, ptr
+    from mv3d_tf_b200.nms.gpu_nms import nms_device
+
+    rng = np.random.default_rng(7 * n + spread)
+    x1, y1 = rng.integers(0, spread, n), rng.integers(0, spread, n)
+    b = np.stack((x1, y1, x1 + rng.integers(4, 70, n), y1 + rng.integers(4, 70, n)), 1).astype(np.float32)
+    sc = (np.arange(n)[::-1] / max(n, 1)).astype(np.float32)          # already sorted
+    full = oracle.nms(np.hstack((b, sc[:, None])), 0.7, "ge")
+    boxes = torch.from_numpy(b).cuda()
+    for cap in (1, 300, 2000, 2048):
+        keep, num = nms_device(boxes, 0.7, True, max_keep=cap)
+        m = int(num.item())
+        assert m == min(cap, len(full)) and keep[:m].cpu().tolist() == full[:m], (n, spread, cap)
+    # device-side count smaller than the capacity (the proposal layer's form)
+    n_dev = max(1, n - 37)
+    full_dev = oracle.nms(np.hstack((b[:n_dev], sc[:n_dev, None])), 0.7, "ge")
+    L = lib()
+    keep = torch.empty(n, dtype=torch.int32, device="cuda")
+    num = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_n = torch.tensor([n_dev], dtype=torch.int32, device="cuda")
+    ws = torch.empty(L.mv3d_nms_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    check(L.mv3d_nms(ptr(boxes), n, 4, ptr(d_n), 0.7, 1, 300, ptr(keep), ptr(num), ptr(ws), ws.numel(), current_stream()), "mv3d_nms")
+    m = int(num.item())
+    assert m == min(300, len(full_dev)) and keep[:m].cpu().tolist() == full_dev[:m]
 
 
 def _fused_pool(views, rois_3d, proj, R, num, Cc):
