@@ -1,5 +1,7 @@
 // Layout / elementwise kernels around the tcgen05 GEMM: weight packing, PAD-layout conversion,
 // 2x2 max-pool on the PAD layout, pair-softmax, split-K epilogue.  All HBM-bound, one pass each.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mv3d {
@@ -633,6 +635,10 @@ extern "C" __attribute__((visibility("default"))) int mv3d_bias_act(const float*
     return MV3D_OK;
 }
 
+namespace mv3d {
+int launch_small_cin_mma(const float* d_in, int B, int H, int W, int C, const float* d_w, const float* d_bias, int relu,
+                         void* d_out_hi, void* d_out_lo, int fmt, cudaStream_t st);   // first_layer_tcgen05.cu
+}
 /* Direct 3x3 SAME conv (+bias, +ReLU) of a dense float32 (B,H,W,C) input with C <= 4 into the PAD layout in `fmt`
  * (Network.conv on the RGB / front-view image, lib/networks/network.py:108-132 with MV3D_test.py:51): replaces
  * mv3d_im2col3x3_pad + the K = 32 GEMM in inference.  d_w: HWIO (3,3,C,Cout) float32; Cout % 8 == 0, c_pad >= Cout. */
@@ -642,11 +648,15 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv3x3_small_cin(
     MV3D_REQUIRE(d_in && d_w && d_out_hi && B > 0 && H > 0 && W > 0 && C > 0 && C <= 4 && Cout > 0 && Cout % 8 == 0);
     MV3D_REQUIRE(c_pad >= Cout && c_pad % 8 == 0);
     MV3D_REQUIRE(fmt == MV3D_FMT_BF16X2 || (fmt == MV3D_FMT_F16E5 && d_out_lo && c_pad % 64 == 0));
+    cudaStream_t st = (cudaStream_t)stream;
+    static int mma_mode = -1;   // MV3D_SMALL_CIN_MMA=0: always the direct fp32 kernel (A/B comparisons)
+    if (mma_mode < 0) { const char* e = getenv("MV3D_SMALL_CIN_MMA"); mma_mode = e ? atoi(e) : 1; }
+    if (mma_mode && C <= 3 && Cout == 64 && c_pad == 64)
+        return mv3d::launch_small_cin_mma(d_in, B, H, W, C, d_w, d_bias, relu, d_out_hi, d_out_lo, fmt, st);
     const size_t smem = sizeof(float) * ((size_t)9 * C * Cout + Cout);
     MV3D_REQUIRE(smem <= 48 * 1024);
     const long long total = (long long)B * (H + 1) * ((W + 1 + kSmallPx - 1) / kSmallPx) * (c_pad / 8);
     const int grid = grid_for(total, 256);
-    cudaStream_t st = (cudaStream_t)stream;
 #define MV3D_SMALL_CIN(FMT, CC) \
     conv3x3_small_cin_kernel<FMT, CC><<<grid, 256, smem, st>>>(d_in, B, H, W, d_w, d_bias, Cout, relu, d_out_hi, d_out_lo, c_pad)
     if (fmt == MV3D_FMT_F16E5) {

@@ -21,6 +21,9 @@ __device__ __forceinline__ float pair_val(__nv_bfloat16 h, __nv_bfloat16 l) {
 // The gradient goes to the FIRST maximum of each window in (dy,dx) order -- the same element the forward kernel
 // (maxpool2x2_pad_kernel, strict `>`) selected -- and only if that maximum is > 0 (ReLU').  Output: PAD H x W.
 // ------------------------------------------------------------------------------------------------
+// One thread per 2x2 WINDOW and 8 channels: the four inputs and the pooled gradient are read once (the per-output form
+// re-read every window four times through L2), the four outputs written as 16-byte stores.  Threads of the extra row /
+// column groups write the zeros of the halo (PAD column 0, row H) and of an odd trailing row / column.
 __global__ void maxpool2x2_bwd_pad_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                           const __nv_bfloat16* __restrict__ gh, const __nv_bfloat16* __restrict__ gl,
                                           int B, int H, int W, int c_pad, __nv_bfloat16* __restrict__ oh,
@@ -28,58 +31,68 @@ __global__ void maxpool2x2_bwd_pad_kernel(const __nv_bfloat16* __restrict__ xh, 
     const int Ho = H / 2, Wo = W / 2;
     const int Hp = H + 1, Wp = W + 1, Hop = Ho + 1, Wop = Wo + 1;
     const int cv = c_pad / 8;
-    const long long total = (long long)B * Hp * Wp * cv;
+    const int ncg = Wo + 1 + (W & 1);    // column groups: {0}, {1,2}, {3,4}, ..., and {W} when W is odd
+    const int nrg = Ho + 1;              // row groups: {0,1}, {2,3}, ..., and the tail rows 2*Ho .. H (one or two)
+    const long long total = (long long)B * nrg * ncg * cv;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % cv);
         long long r = i / cv;
-        const int wp = (int)(r % Wp);
-        r /= Wp;
-        const int hp = (int)(r % Hp);
-        const int b = (int)(r / Hp);
-        uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
-        const int h = hp, w = wp - 1;
-        if (wp > 0 && hp < H && (h >> 1) < Ho && (w >> 1) < Wo) {
-            const int ph = h >> 1, pw = w >> 1;
-            const int my = (h & 1) * 2 + (w & 1);  // position of this element in the window scan order
+        const int cg = (int)(r % ncg);
+        r /= ncg;
+        const int rg = (int)(r % nrg);
+        const int b = (int)(r / nrg);
+        const int row0 = 2 * rg, nrows = rg < Ho ? 2 : Hp - 2 * Ho;
+        const int col0 = cg == 0 ? 0 : 2 * cg - 1, ncols = (cg == 0 || cg > Wo) ? 1 : 2;
+        if (rg < Ho && cg >= 1 && cg <= Wo) {
             float v[4][8];
+            long long j[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const long long j = ((((long long)b * Hp + ph * 2 + (k >> 1)) * Wp + (pw * 2 + (k & 1) + 1)) * c_pad) + c8 * 8;
-                const uint4 vh = *reinterpret_cast<const uint4*>(xh + j);
-                const uint4 vl = xl ? *reinterpret_cast<const uint4*>(xl + j) : make_uint4(0, 0, 0, 0);
+                j[k] = ((((long long)b * Hp + row0 + (k >> 1)) * Wp + (col0 + (k & 1))) * c_pad) + c8 * 8;
+                const uint4 vh = *reinterpret_cast<const uint4*>(xh + j[k]);
+                const uint4 vl = xl ? *reinterpret_cast<const uint4*>(xl + j[k]) : zero;
                 const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(&vh);
                 const __nv_bfloat16* c = reinterpret_cast<const __nv_bfloat16*>(&vl);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[k][e] = pair_val(a[e], c[e]);
             }
-            const long long gj = ((((long long)b * Hop + ph) * Wop + (pw + 1)) * c_pad) + c8 * 8;
+            const long long gj = ((((long long)b * Hop + rg) * Wop + cg) * c_pad) + c8 * 8;
             const uint4 g4h = *reinterpret_cast<const uint4*>(gh + gj);
-            const uint4 g4l = gl ? *reinterpret_cast<const uint4*>(gl + gj) : make_uint4(0, 0, 0, 0);
-            const __nv_bfloat16* pgh = reinterpret_cast<const __nv_bfloat16*>(&g4h);
-            const __nv_bfloat16* pgl = reinterpret_cast<const __nv_bfloat16*>(&g4l);
-            __nv_bfloat16 outh[8], outl[8];
+            const uint4 g4l = gl ? *reinterpret_cast<const uint4*>(gl + gj) : zero;
+            const uint32_t* pgh = reinterpret_cast<const uint32_t*>(&g4h);
+            const uint32_t* pgl = reinterpret_cast<const uint32_t*>(&g4l);
+            uint32_t outh[4][4], outl[4][4];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float mine = 0.f;
-                bool win = true;
+                // the FIRST maximum in (dy,dx) scan order takes the gradient (forward: strict `>`), and only if it is > 0
+                int win = 0;
+                float best = v[0][e];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k == my) mine = v[k][e];
+                for (int k = 1; k < 4; ++k)
+                    if (v[k][e] > best) { best = v[k][e]; win = k; }
+                if (!(best > 0.f)) win = -1;
+                const uint32_t sel = (e & 1) ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (k < my && !(v[k][e] < mine)) win = false;
-                    if (k > my && !(v[k][e] <= mine)) win = false;
+                    if ((e & 1) == 0) { outh[k][e >> 1] = 0u; outl[k][e >> 1] = 0u; }
+                    if (k == win) { outh[k][e >> 1] |= pgh[e >> 1] & sel; outl[k][e >> 1] |= pgl[e >> 1] & sel; }
                 }
-                win = win && (mine > 0.f);
-                outh[e] = win ? pgh[e] : __float2bfloat16_rn(0.f);
-                outl[e] = win ? pgl[e] : __float2bfloat16_rn(0.f);
             }
-            rh = *reinterpret_cast<uint4*>(outh);
-            rl = *reinterpret_cast<uint4*>(outl);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                *reinterpret_cast<uint4*>(oh + j[k]) = make_uint4(outh[k][0], outh[k][1], outh[k][2], outh[k][3]);
+                if (ol) *reinterpret_cast<uint4*>(ol + j[k]) = make_uint4(outl[k][0], outl[k][1], outl[k][2], outl[k][3]);
+            }
+        } else {
+            for (int dy = 0; dy < nrows; ++dy)
+                for (int dx = 0; dx < ncols; ++dx) {
+                    const long long jz = ((((long long)b * Hp + row0 + dy) * Wp + (col0 + dx)) * c_pad) + c8 * 8;
+                    *reinterpret_cast<uint4*>(oh + jz) = zero;
+                    if (ol) *reinterpret_cast<uint4*>(ol + jz) = zero;
+                }
         }
-        *reinterpret_cast<uint4*>(oh + i * 8) = rh;
-        if (ol) *reinterpret_cast<uint4*>(ol + i * 8) = rl;
     }
 }
 
@@ -434,7 +447,7 @@ using namespace mv3d;
 MV3D_API int mv3d_maxpool2x2_bwd_pad(const void* d_x_hi, const void* d_x_lo, const void* d_g_hi, const void* d_g_lo,
                                      int B, int H, int W, int c_pad, void* d_out_hi, void* d_out_lo, void* stream) {
     MV3D_REQUIRE(d_x_hi && d_g_hi && d_out_hi && B > 0 && H > 1 && W > 1 && c_pad % 8 == 0);
-    const long long total = (long long)B * (H + 1) * (W + 1) * (c_pad / 8);
+    const long long total = (long long)B * (H / 2 + 1) * (W / 2 + 1 + (W & 1)) * (c_pad / 8);
     maxpool2x2_bwd_pad_kernel<<<grid_for_t(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)d_x_hi, (const __nv_bfloat16*)d_x_lo, (const __nv_bfloat16*)d_g_hi,
         (const __nv_bfloat16*)d_g_lo, B, H, W, c_pad, (__nv_bfloat16*)d_out_hi, (__nv_bfloat16*)d_out_lo);

@@ -125,10 +125,12 @@ def test_first_layer_im2col_conv(B, H, W, Cout, passes):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,fmt", [(1, 9, 11, 3, 64, 0), (2, 37, 50, 3, 64, 1), (1, 64, 96, 3, 64, 1),
-                                                 (1, 33, 40, 1, 64, 0), (1, 20, 31, 4, 128, 1)])
+                                                 (1, 33, 40, 1, 64, 0), (1, 20, 31, 4, 128, 1), (1, 17, 300, 2, 64, 1),
+                                                 (1, 375, 1242, 3, 64, 1), (1, 64, 512, 3, 128, 0)])
 def test_first_layer_direct_kernel(B, H, W, Cin, Cout, fmt):
-    """conv1_1 on an image-like input through the direct small-Cin kernel (fp32 FMA accumulation) vs torch in float64;
-    the PAD output carries the consumer's operand format (0 = bf16 hi/lo, 1 = f16e5) and zero halos."""
+    """conv1_1 on an image-like input vs torch in float64: Cout = 64 and Cin <= 3 go through the tcgen05 form (operand rows
+    built in shared memory by the CTA, bf16 hi/lo 3-pass MMAs, first_layer_tcgen05.cu), anything else through the direct
+    fp32 FMA kernel; the PAD output carries the consumer's operand format (0 = bf16 hi/lo, 1 = f16e5) and zero halos."""
     from mv3d_tf_b200 import kernels as k
 
     g = torch.Generator(device="cuda").manual_seed(H * W + Cin)
