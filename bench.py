@@ -541,8 +541,8 @@ def main():
             "steps": args.steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"precise": "bf16x3 (bf16 hi/lo split, 3 tcgen05 passes, fp32 accumulate)",
-                      "mixed": "f16+2xe5m2 in the 3x3 convs (fp16 pass + one e5m2 pass carrying both correction terms = 2 "
-                               "pass-equivalents, fp32 accumulate), bf16x3 in 1x1/fc layers",
+                      "mixed": "f16+2xe5m2 in the 3x3 convs and fc6 (fp16 pass + one e5m2 pass carrying both correction terms = 2 "
+                               "pass-equivalents, fp32 accumulate), bf16x3 in the first image layer, 1x1 convs and the other fc layers",
                       "fast": "bf16"}[args.mode],
             "data": "synthetic", "config": make_config(args.views),
             "impl_config": {"mode": args.mode, "frames_in_flight": depth,

@@ -161,6 +161,10 @@ typedef struct {
      * ((B, H+1, W+1, pad_c), pad_fmt = MV3D_FMT_*) instead of a dense float32 copy (d_data may then be NULL); the values
      * pooled are the operand renderings (what Network.run returns for that layer when fetched) */
     const void* d_pad_hi; const void* d_pad_lo; int pad_fmt, pad_c;
+    /* rendering of d_top_hi / d_top_lo: MV3D_FMT_BF16X2 (bf16 hi/lo, the default 0) or MV3D_FMT_F16E5 -- d_top_hi = fp16
+     * (R, PH*PW*C), d_top_lo = the byte plane of the same rows (K index = bin*C + c, 64-element chunks [e5m2(h) | e5m2
+     * residual]): fc6's operand for the 2-pass fc GEMM (mv3d_gemm_desc.passes = 2).  channels % 64 == 0. */
+    int top_fmt;
 } mv3d_roi_view;
 /* projection constants of the fused form: BEV grid (transform.py:3-20) + clip bounds (im_info), the float32 3x4 image
  * projection (P2.R0).Tr by value or as a device pointer (graph replay), the FV map geometry (radians) */

@@ -28,7 +28,8 @@ class RoiView(C.Structure):
     _fields_ = [("d_data", c_void_p), ("d_rois", c_void_p), ("height", c_int), ("width", c_int),
                 ("spatial_scale", c_float), ("d_top", c_void_p), ("d_argmax", c_void_p),
                 ("d_top_hi", c_void_p), ("d_top_lo", c_void_p), ("source", c_int), ("d_rois_out", c_void_p),
-                ("d_pad_hi", c_void_p), ("d_pad_lo", c_void_p), ("pad_fmt", c_int), ("pad_c", c_int)]
+                ("d_pad_hi", c_void_p), ("d_pad_lo", c_void_p), ("pad_fmt", c_int), ("pad_c", c_int),
+                ("top_fmt", c_int)]
 
 
 ROI_GIVEN, ROI_BEV, ROI_IMG, ROI_FV = 0, 1, 2, 3   # MV3D_ROI_* of include/mv3d_b200.h

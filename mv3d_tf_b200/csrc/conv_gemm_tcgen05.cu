@@ -1050,6 +1050,8 @@ struct FcSwapParams {
     int stages, stage_bytes;
     float* out;             // (R, ld) fp32, zeroed by the caller
     int ld;
+    int passes;             // 3: bf16 hi/lo operands; 2: f16e5 operands (fp16 plane + e5m2 byte plane, see common.cuh)
+    float out_scale;        // 2^-12 for f16e5 (the fp16 weight plane holds 4096 w), else 1
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -1119,7 +1121,8 @@ fc_swapped_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gri
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            const uint32_t idesc = make_idesc_bf16(2 * kBM, prm.C);
+            const uint32_t idesc = prm.passes == 2 ? make_idesc_f16(2 * kBM, prm.C) : make_idesc_bf16(2 * kBM, prm.C);
+            const uint32_t idesc8 = make_idesc_e5m2(2 * kBM, prm.C);
             int it = 0, tl = 0;
             for (int w = pair_id; w < prm.n_work; w += n_pairs, ++tl) {
                 const int sp = w % prm.n_split;
@@ -1146,8 +1149,12 @@ fc_swapped_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gri
                                 const uint64_t da = make_kmajor_desc(a_hi + h * a_chunk + k * 32, 128);
                                 const uint64_t dal = make_kmajor_desc(a_lo + h * a_chunk + k * 32, 128);
                                 mma_bf16_ss_pair(d_tmem, dw, da, idesc, (ks > k_begin || k > 0) ? 1u : 0u);
-                                mma_bf16_ss_pair(d_tmem, dwl, da, idesc, 1u);
-                                mma_bf16_ss_pair(d_tmem, dw, dal, idesc, 1u);
+                                if (prm.passes == 2) {   // [W_l8 | W_h8] . [A_h8 ; A_l8]: both correction terms, one e5m2 pass
+                                    mma_f8_ss_pair(d_tmem, dwl, dal, idesc8, 1u);
+                                } else {
+                                    mma_bf16_ss_pair(d_tmem, dwl, da, idesc, 1u);
+                                    mma_bf16_ss_pair(d_tmem, dw, dal, idesc, 1u);
+                                }
                             }
                         }
                         mma_commit_pair(&empty_bar[s], 3);
@@ -1181,7 +1188,7 @@ fc_swapped_pair_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gri
                     float* o = prm.out + (long long)(ci * 32) * prm.ld + f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (ci * 32 + j < prm.R) red_add_f32(o + (long long)j * prm.ld, __uint_as_float(v[j]));
+                        if (ci * 32 + j < prm.R) red_add_f32(o + (long long)j * prm.ld, __uint_as_float(v[j]) * prm.out_scale);
                 }
             }
         }
@@ -1339,7 +1346,7 @@ static int try_launch_pair(const mv3d_gemm_desc* d, cudaStream_t stream, bool* t
 
 // fc over <= 512 ROIs with a split-K fp32 accumulator: the swapped CTA-pair kernel (weights stream through once).
 static bool fc_swap_applicable(const mv3d_gemm_desc* d) {
-    return d->taps == 1 && d->Hp == 0 && d->passes == 3 && d->split_k > 1 && d->d_out_f32 && d->Cin % 64 == 0 &&
+    return d->taps == 1 && d->Hp == 0 && (d->passes == 3 || d->passes == 2) && d->split_k > 1 && d->d_out_f32 && d->Cin % 64 == 0 &&
            d->N % 256 == 0 && d->M >= 64 && d->M <= 512 && pair_mode() != 0;
 }
 
@@ -1361,6 +1368,7 @@ static int launch_fc_swapped(const mv3d_gemm_desc* d, cudaStream_t stream) {
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return MV3D_ERR_ARG;
     p.out = d->d_out_f32; p.ld = d->ld_f32;
+    p.passes = d->passes; p.out_scale = d->passes == 2 ? 1.f / kF16E5Scale : 1.f;
     CUtensorMap mw_hi, mw_lo, ma_hi, ma_lo;
     int rc;
     if ((rc = make_map_2d(&mw_hi, d->d_w_hi, d->N, d->Cin, kBM, 64)) != MV3D_OK) return rc;
@@ -1534,8 +1542,8 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_gemm(const mv3d_
     // f16e5 output: whole 64-channel chunks, both planes
     MV3D_REQUIRE(d->out_fmt != MV3D_FMT_F16E5 || !d->d_out_hi || (d->d_out_lo && d->N % 64 == 0 && d->ld_out % 64 == 0 && d->split_k <= 1 &&
                                                                    ((reinterpret_cast<uintptr_t>(d->d_out_hi) | reinterpret_cast<uintptr_t>(d->d_out_lo)) & 31) == 0));
-    // f16e5 operands: the tap-reuse 3x3 kernels only
-    MV3D_REQUIRE(d->passes != 2 || (d->taps == 9 && d->Cin % 64 == 0 && d->split_k <= 1));
+    // f16e5 operands: the tap-reuse 3x3 kernels, and the swapped split-K fc kernel
+    MV3D_REQUIRE(d->passes != 2 || (d->taps == 9 && d->Cin % 64 == 0 && d->split_k <= 1) || fc_swap_applicable(d));
     MV3D_REQUIRE(d->taps == 1 || (d->Hp > 1 && d->Wp > 1));
     MV3D_REQUIRE((d->Hp > 0) == (d->Wp > 0));
     MV3D_REQUIRE(d->Hp == 0 || d->M % (d->Hp * d->Wp) == 0);

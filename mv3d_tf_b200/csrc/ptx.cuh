@@ -192,6 +192,15 @@ __device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_des
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void mma_f8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Pair MMAs with the shared-memory descriptors passed as their LOW words (start address >> 4 | LBO field); the high
 // word of a SWIZZLE_128B K-major descriptor is a constant.  Advancing a descriptor along K or by whole rows is then one
 // 32-bit add in the issuing thread -- the issue loop is the bottleneck of the narrow (Cout <= 128) layers.

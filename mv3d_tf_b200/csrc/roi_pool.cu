@@ -41,6 +41,7 @@ struct RoiViewDev {
     const unsigned short* pad_hi;
     const unsigned short* pad_lo;
     int pad_fmt, pad_c;
+    int top_fmt;       // rendering of top_hi / top_lo: MV3D_FMT_BF16X2 or MV3D_FMT_F16E5 (fc6 operand, K = bin*C + c)
 };
 struct RoiProjDev {
     BevGrid bev;
@@ -338,7 +339,17 @@ roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__
                 *reinterpret_cast<int4*>(V.argmax + o) = make_int4(mi[0], mi[1], mi[2], mi[3]);
                 *reinterpret_cast<int4*>(V.argmax + o + 4) = make_int4(mi[4], mi[5], mi[6], mi[7]);
             }
-            if (V.top_hi) {
+            if (V.top_hi && V.top_fmt == MV3D_FMT_F16E5) {
+                uint32_t h2[4];
+                unsigned short h8[4], l8[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_f16e5_x2(mv[2 * e], mv[2 * e + 1], h2[e], h8[e], l8[e]);
+                *reinterpret_cast<uint4*>(V.top_hi + o) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+                const size_t k0 = (size_t)bin * C + cb + lane * 8;      // K index inside the ROI's row
+                uint8_t* row = reinterpret_cast<uint8_t*>(V.top_lo) + 2 * roi_base + ((k0 >> 6) << 7) + (k0 & 63);
+                *reinterpret_cast<uint2*>(row) = make_uint2(h8[0] | ((uint32_t)h8[1] << 16), h8[2] | ((uint32_t)h8[3] << 16));
+                *reinterpret_cast<uint2*>(row + 64) = make_uint2(l8[0] | ((uint32_t)l8[1] << 16), l8[2] | ((uint32_t)l8[3] << 16));
+            } else if (V.top_hi) {
                 __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) split_bf16(mv[e], hi[e], lo[e]);
@@ -388,6 +399,8 @@ static int fill_views(const mv3d_roi_view* views, int n_views, bool fused, RoiVi
         v->v[i].pad_hi = static_cast<const unsigned short*>(views[i].d_pad_hi);
         v->v[i].pad_lo = static_cast<const unsigned short*>(views[i].d_pad_lo);
         v->v[i].pad_fmt = views[i].pad_fmt; v->v[i].pad_c = views[i].pad_c;
+        MV3D_REQUIRE(views[i].top_fmt == MV3D_FMT_BF16X2 || (views[i].top_fmt == MV3D_FMT_F16E5 && views[i].d_top_hi && views[i].d_top_lo));
+        v->v[i].top_fmt = views[i].top_fmt;
     }
     return MV3D_OK;
 }
@@ -432,7 +445,10 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_multiview(
     RoiViews v = {};
     const int rc = fill_views(views, n_views, false, &v);
     if (rc != MV3D_OK) return rc;
-    for (int i = 0; i < n_views; ++i) MV3D_REQUIRE(!v.v[i].pad_hi || channels % 8 == 0);   // PAD input: staged kernel only
+    for (int i = 0; i < n_views; ++i) {
+        MV3D_REQUIRE(!v.v[i].pad_hi || channels % 8 == 0);                       // PAD input: staged kernel only
+        MV3D_REQUIRE(v.v[i].top_fmt != MV3D_FMT_F16E5 || channels % 64 == 0);    // f16e5 operand: whole 64-channel chunks
+    }
     if (channels % 8 == 0) {   // staged kernel, given rectangles
         RoiProjDev proj = {};
         return launch_fused(v, n_views, proj, nullptr, num_rois, d_num_valid, channels, pooled_height, pooled_width,
@@ -450,7 +466,10 @@ extern "C" __attribute__((visibility("default"))) int mv3d_roi_pool_fused(
     const int rc = fill_views(views, n_views, true, &v);
     if (rc != MV3D_OK) return rc;
     bool projected = false;
-    for (int i = 0; i < n_views; ++i) projected |= (v.v[i].source != MV3D_ROI_GIVEN);
+    for (int i = 0; i < n_views; ++i) {
+        projected |= (v.v[i].source != MV3D_ROI_GIVEN);
+        MV3D_REQUIRE(v.v[i].top_fmt != MV3D_FMT_F16E5 || channels % 64 == 0);
+    }
     MV3D_REQUIRE(!projected || (d_rois_3d && proj));
     RoiProjDev pd = {};
     if (proj) {

@@ -166,7 +166,7 @@ GEMM_EVENTS = None  # bench.py sets this to a list to time every GEMM launch wit
 def gemm_kernel_name(taps: int, k_per_tap: int, n: int, passes: int, split_k: int = 1, m: int = 0, hp: int = 0) -> str:
     """Which template instantiation mv3d_conv_gemm dispatches to (mirrors dispatch_bn / launch_gemm in
     csrc/conv_gemm_tcgen05.cu) -- used to attribute per-launch timings to kernels in bench.py."""
-    if (taps == 1 and hp == 0 and passes == 3 and split_k > 1 and k_per_tap % 64 == 0 and n % 256 == 0
+    if (taps == 1 and hp == 0 and passes in (2, 3) and split_k > 1 and k_per_tap % 64 == 0 and n % 256 == 0
             and 64 <= m <= 512 and PAIR_MODE):
         return "fc_swapped_pair_kernel"
     if passes == 2:
@@ -269,10 +269,15 @@ def linear(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], w: PackedWeight, re
     if out_bf16:
         hi = torch.zeros((M, n_pad), dtype=BF16, device=dev)
         lo = torch.zeros_like(hi) if precise else None
+    if w.fmt == FMT_F16E5:
+        # f16e5 rows (a_hi = fp16 plane, a_lo = byte plane, both in 16-bit containers) x f16e5 weights: the swapped
+        # split-K CTA-pair kernel only (a few hundred rows, wide output)
+        assert split_k > 1 and mask_hi is None and a_lo is not None and 64 <= M <= 512 and w.cout % 256 == 0 and K % 64 == 0 \
+            and PAIR_MODE, "f16e5 fc operands need the swapped split-K kernel"
     if split_k > 1 and mask_hi is None:
         acc = torch.zeros((M, w.cout), dtype=torch.float32, device=dev)
         _run_gemm(_flops=2.0 * M * w.cin * w.cout,
-                  M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=3 if precise else 1, d_a_hi=ptr(a_hi),
+                  M=M, N=w.cout, Cin=K, taps=1, Hp=0, Wp=0, passes=2 if w.fmt == FMT_F16E5 else (3 if precise else 1), d_a_hi=ptr(a_hi),
                   d_a_lo=ptr(a_lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo), d_bias=None, relu=0, d_out_hi=None,
                   d_out_lo=None, ld_out=0, d_out_f32=ptr(acc), ld_f32=w.cout, f32_dense=0, split_k=split_k)
         if out_f32:

@@ -99,6 +99,7 @@ class Network(object):
         self._anchor_pre = None
         self._aux_stream = None
         self.roi_from_pad = os.environ.get('MV3D_ROI_FROM_PAD', '1') != '0'   # fused ROI pool reads conv5's PAD planes
+        self.fc_f16e5 = os.environ.get('MV3D_FC_F16E5', '1') != '0'   # mixed mode: ROI pool -> fc6 in the 2-pass f16e5 format
         self.node_events = None         # list -> Network.run appends (name, kind, start event, end event) per node
         self.last_num_rois = None
         self.training = False           # True: roi_pool keeps argmax, dropout draws masks (set by the solver)
@@ -471,8 +472,14 @@ class Network(object):
                 Cc = fv_.pad.C if from_pad else feat.shape[-1]
                 fdev = fv_.pad.hi.device if from_pad else feat.device
                 fH, fW = (fv_.pad.H, fv_.pad.W) if from_pad else (feat.shape[1], feat.shape[2])
+                # mixed-mode inference: the pooled rows leave as f16e5 operands when every reader is a wide fc over <= 512
+                # ROIs (the swapped split-K fc kernel runs them in 2 pass-equivalents instead of 3); same 16-bit containers
+                top_fmt = K.FMT_F16E5 if (self.mixed and self.fc_f16e5 and not self.training and Cc % 64 == 0
+                                          and 64 <= R <= 512 and m.consumer_nodes
+                                          and all(c.kind == 'fc' and c.channels % 256 == 0 for c in m.consumer_nodes)) \
+                    else K.FMT_BF16X2
                 hi = torch.empty((R, ph * pw * Cc), dtype=torch.bfloat16, device=fdev)
-                lo = torch.empty_like(hi) if self.precise else None
+                lo = torch.empty_like(hi) if (self.precise or top_fmt == K.FMT_F16E5) else None
                 top = None
                 if m.attrs.get('fetched', False):
                     top = torch.empty((R, ph, pw, Cc), dtype=torch.float32, device=fdev)
@@ -482,7 +489,8 @@ class Network(object):
                 if from_pad:
                     v.d_pad_hi, v.d_pad_lo, v.pad_fmt, v.pad_c = ptr(fv_.pad.hi), ptr(fv_.pad.lo), fv_.pad.fmt, fv_.pad.c_pad
                 v.spatial_scale, v.d_top, v.d_argmax, v.d_top_hi, v.d_top_lo = sc, ptr(top), ptr(arg), ptr(hi), ptr(lo)
-                results.append(Val(dense=top, hi=hi, lo=lo, extra=dict(feat=feat, rois=r, argmax=arg, scale=sc)))
+                v.top_fmt = top_fmt
+                results.append(Val(dense=top, hi=hi, lo=lo, extra=dict(feat=feat, rois=r, argmax=arg, scale=sc, fmt=top_fmt)))
             ph, pw, _ = node.attrs['cfg']
             e = vals[node.inputs[1]].extra
             num = e['num'] if (isinstance(e, dict) and e.get('num') is not None and e['num'].numel() == 1) else None
@@ -580,8 +588,10 @@ class Network(object):
                     f.attrs['result'] = Val(dense=f32[:, off:off + f.channels])
                     off += f.channels
                 return Val(dense=f32[:, :num_out])
-            hi, lo, f32 = K.linear(v.hi, v.lo, self._weight(name, transform), relu=relu, precise=self.precise,
-                                   out_bf16=want_vec, out_f32=want_f32, split_k=split_for(M, num_out, dim))
+            a_fmt = v.extra.get('fmt', K.FMT_BF16X2) if isinstance(v.extra, dict) else K.FMT_BF16X2
+            hi, lo, f32 = K.linear(v.hi, v.lo, self._weight(name, transform, fmt=a_fmt), relu=relu, precise=self.precise,
+                                   out_bf16=want_vec, out_f32=want_f32, split_k=max(2, split_for(M, num_out, dim))
+                                   if a_fmt == K.FMT_F16E5 else split_for(M, num_out, dim))
             return Val(hi=hi, lo=lo, dense=f32)
         n = self._node(name, 'fc', [input], run, channels=num_out)
         n.attrs['relu'] = relu

@@ -259,3 +259,41 @@ def test_roi_pool_reads_pad_operand_planes(oracle, fmt):
     wt, wa = oracle.roi_pool_fwd(rendered, rois)
     assert np.array_equal(top.cpu().numpy(), wt)
     assert np.array_equal(arg.cpu().numpy(), wa)
+
+
+def test_roi_pool_emits_f16e5_fc_operand(oracle):
+    """mv3d_roi_view.top_fmt = MV3D_FMT_F16E5: the pooled rows leave as fc6's 2-pass operand -- fp16 plane = fp16(top) bit
+    for bit, byte plane = per 64-element chunk [e5m2(h) | e5m2((top - h) * 4096)] -- next to the exact float32 top."""
+    from mv3d_tf_b200._lib import ROI_GIVEN, RoiView, check, current_stream, lib, ptr
+
+    rng = np.random.default_rng(17)
+    H, W, Cc, R = 40, 60, 128, 70
+    x = torch.from_numpy(np.maximum(rng.normal(size=(1, H, W, Cc)), 0).astype(np.float32)).cuda()
+    x1, y1 = rng.integers(-40, W * 8, R), rng.integers(-40, H * 8, R)
+    rois = np.stack((np.zeros(R), x1, y1, x1 + rng.integers(0, 250, R), y1 + rng.integers(0, 200, R)), 1).astype(np.float32)
+    r_dev = torch.from_numpy(rois).cuda()
+    n_valid = torch.tensor([R - 5], dtype=torch.int32, device="cuda")     # rows past the count are zero-filled
+    top = torch.empty((R, 7, 7, Cc), device="cuda")
+    Kd = 49 * Cc
+    hi = torch.full((R, Kd), -1, dtype=torch.int16, device="cuda")
+    lo = torch.full((R, Kd), -1, dtype=torch.int16, device="cuda")
+    views = (RoiView * 1)()
+    v = views[0]
+    v.d_data, v.d_rois, v.height, v.width, v.spatial_scale = ptr(x), ptr(r_dev), H, W, 0.125
+    v.d_top, v.source, v.d_top_hi, v.d_top_lo, v.top_fmt = ptr(top), ROI_GIVEN, ptr(hi), ptr(lo), 1
+    check(lib().mv3d_roi_pool_multiview(views, 1, R, ptr(n_valid), Cc, 7, 7, current_stream()), "mv3d_roi_pool_multiview")
+    torch.cuda.synchronize()
+    wt, _ = oracle.roi_pool_fwd(x.cpu().numpy(), rois[: R - 5])
+    t = top.view(R, Kd)
+    assert np.array_equal(t[: R - 5].cpu().numpy(), wt.reshape(R - 5, Kd))
+    t = t.clone()
+    t[R - 5:] = 0
+    h = t.half()
+    assert torch.equal(hi.view(torch.float16), h)
+    planes = lo.view(torch.uint8).view(R, Kd // 64, 2, 64)
+    h8 = planes[:, :, 0].reshape(R, Kd).view(torch.float8_e5m2).float()
+    l8 = planes[:, :, 1].reshape(R, Kd).view(torch.float8_e5m2).float()
+    assert torch.equal(h8, h.float().to(torch.float8_e5m2).float())
+    resid = (t - h.float()) * 4096.0
+    assert torch.equal(l8, resid.to(torch.float8_e5m2).float())
+    assert float(((h.float() + l8 / 4096.0) - t).abs().max() / t.abs().max()) < 2.0 ** -13

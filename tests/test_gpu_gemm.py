@@ -48,6 +48,41 @@ def test_fc_gemm(M, N, K, passes, split_k):
     assert _relerr(got, ref) < (tol if lo is not None else 1e-2)
 
 
+def _f16e5_rows(x):
+    """(R, K) float32 -> the f16e5 operand rows (fp16 plane, byte plane) in 16-bit containers, built with torch: per
+    64-element chunk 64 x e5m2(h) then 64 x e5m2((x - h) * 4096) (csrc/common.cuh)."""
+    R, Kd = x.shape
+    h = x.half()
+    h8 = h.float().to(torch.float8_e5m2).view(torch.uint8)
+    l8 = ((x - h.float()) * 4096.0).to(torch.float8_e5m2).view(torch.uint8)
+    planes = torch.stack((h8.view(R, Kd // 64, 64), l8.view(R, Kd // 64, 64)), dim=2).reshape(R, 2 * Kd)
+    return h.view(torch.bfloat16).contiguous(), planes.contiguous().view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 2048, 25088), (64, 256, 128), (301, 512, 1024), (512, 256, 4096)])
+def test_fc_gemm_f16e5_operands(M, N, K):
+    """fc over a few hundred rows with f16e5 operands (mv3d_gemm_desc.passes = 2 on the swapped split-K kernel: one fp16
+    pass + one e5m2 pass carrying both first-order correction terms) vs torch float64; error ~2^-14.5 per product."""
+    from mv3d_tf_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.relu(torch.randn(M, K, device="cuda", generator=g))
+    w = torch.randn(K, N, device="cuda", generator=g) * 0.02
+    b = torch.randn(N, device="cuda", generator=g)
+    pw = k.pack_weights(w, b, cin_pad=K, fmt=k.FMT_F16E5)
+    a_hi, a_lo = _f16e5_rows(a)
+    assert k.gemm_kernel_name(1, K, N, 2, 3, M, 0) == "fc_swapped_pair_kernel"
+    hi, lo, f32 = k.linear(a_hi, a_lo, pw, relu=True, precise=True, out_bf16=True, out_f32=True, split_k=3)
+    torch.cuda.synchronize()
+    ref = torch.relu(a.double() @ w.double() + b.double())
+    assert _relerr(f32, ref) < 1e-4
+    assert _relerr(hi[:, :N].float() + lo[:, :N].float(), ref) < 1e-4
+    # and against the 3-pass result of the same layer
+    a_h3, a_l3 = _split(a)
+    _, _, f3 = k.linear(a_h3, a_l3, k.pack_weights(w, b, cin_pad=K), relu=True, precise=True, out_bf16=False, out_f32=True, split_k=3)
+    assert _relerr(f32, f3) < 1e-4
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [
     (1, 9, 11, 3, 64, 3), (2, 16, 20, 64, 64, 3), (1, 37, 41, 36, 64, 3), (1, 23, 50, 128, 256, 3),
     (1, 23, 50, 128, 256, 1), (1, 12, 13, 512, 512, 3), (1, 75, 75, 64, 128, 3), (1, 40, 33, 9, 64, 1),
