@@ -23,8 +23,8 @@ dram)  # DRAM bytes + duration of EVERY GEMM launch of one frame -> roofline.tra
         -k regex:"$GEMMS" -s $((N * 5)) -c $N --csv --log-file $OUT/${TAG}_gemm_dram_v$V.csv \
         $BENCH --views $V > $OUT/${TAG}_gemm_dram_v$V.log 2>&1
   done ;;
-hbm)   # the HBM-/latency-bound kernels: raster, first layer, ROI pool, NMS, proposal chain, remaining max-pools
-  ncu --set full --clock-control none --import-source on -k regex:'raster_|roi_pool|nms_mask|nms_reduce|maxpool|small_cin|proposal_' -s 68 -c 17 \
+hbm)   # the HBM-/latency-bound kernels: raster, first image layer, ROI pool, NMS, proposal chain, remaining max-pools
+  ncu --set full --clock-control none --import-source on -k regex:'raster_|roi_pool|nms_|maxpool|small_cin|proposal_' -s 60 -c 15 \
       -f -o $OUT/${TAG}_hbm_full $BENCH > $OUT/${TAG}_hbm_full.log 2>&1 ;;
 wgrad) # training: the backward-filter GEMM, full sections
   ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 70 -c 4 \

@@ -21,8 +21,15 @@ run() {  # tool, label, time limit, pytest args...
   grep -E "Invalid|Race reported|hazard" $log | sort | uniq -c | head -20 >> $OUT
   echo '```' >> $OUT
 }
+SET=${2:-all}   # all | new (only the kernels added late in round 2: cluster NMS, first-layer tcgen05, f16e5 ROI/fc operands)
+run memcheck edge 600 tests/test_gpu_edge_cases.py -k "nms or roi_pool"
+run racecheck edge 600 tests/test_gpu_edge_cases.py -k "nms_lazy or emits_f16e5 or pad_operand"
+run memcheck first_layer 300 tests/test_gpu_gemm.py -k "first_layer_direct or f16e5_operands"
+run racecheck first_layer 300 tests/test_gpu_gemm.py -k "first_layer_direct and not 1242"
+if [ "$SET" = all ]; then
 run memcheck kernels 600 tests/test_gpu_kernels.py
 run memcheck gemm 600 tests/test_gpu_gemm.py -k "not full and not big"
 run racecheck kernels 600 tests/test_gpu_kernels.py -k "nms or roi or raster"
 run racecheck gemm 420 tests/test_gpu_gemm.py -k "pair or f16e5"
+fi
 cat $OUT

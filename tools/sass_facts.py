@@ -8,14 +8,14 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PAT = ["UTCHMMA.2CTA", "UTCQMMA.2CTA", "UTCHMMA", "UTCQMMA", "UTMALDG.2D.2CTA", "UTMALDG.2D", "UTCBAR.2CTA.MULTICAST", "UTCBAR",
-       "UTCATOMSWS.2CTA", "UTCATOMSWS", "LDTM", "UCGABAR_ARV", "STG.E.ENL2.256", "SYNCS.PHASECHK", "HMMA", "REDG", "RED.E.ADD.F32", "VOTE", "REDUX", "SHFL", "STAS", "ATOMS", "LDS.128"]
+       "UTCATOMSWS.2CTA", "UTCATOMSWS", "LDTM", "UCGABAR_ARV", "STG.E.ENL2.256", "SYNCS.PHASECHK", "HMMA", "REDG", "RED.E.ADD.F32", "VOTE", "REDUX", "SHFL", "STAS", "ATOMS", "LDS.128", "MAPA", "ATOM.E.OR"]
 
 
 def main():
     print("# SASS mnemonics per kernel (cuobjdump -sass of mv3d_tf_b200/csrc/_obj/*.o, sm_100a)\n")
     print("UTCHMMA = tcgen05.mma kind::f16, UTCQMMA = tcgen05.mma kind::f8f6f4, `.2CTA` = cta_group::2, UTMALDG = "
           "cp.async.bulk.tensor (TMA), UTCBAR = tcgen05.commit, UTCATOMSWS = tcgen05.alloc, LDTM = tcgen05.ld, UCGABAR = "
-          "barrier.cluster, STG.256 = st.global.v8.b32, VOTE = __ballot_sync, REDUX = __reduce_or_sync, SHFL = warp shuffles, STAS = st.async (distributed shared memory + complete_tx).  Pair-kernel template arguments: <BN, PASSES, LEAN, WRES, POOL>.  No legacy HMMA (mma.sync) anywhere.\n")
+          "barrier.cluster, STG.256 = st.global.v8.b32, VOTE = __ballot_sync, REDUX = __reduce_or_sync, SHFL = warp shuffles, STAS = st.async (distributed shared memory + complete_tx), MAPA = mapa (peer shared-memory address), ATOM.E.OR on a mapa address = red.shared::cluster.or.  Pair-kernel template arguments: <BN, PASSES, LEAN, WRES, POOL>.  No legacy HMMA (mma.sync) anywhere.\n")
     print("| object | kernel | " + " | ".join(PAT) + " |")
     print("|---|---|" + "---|" * len(PAT))
     for obj in sorted(glob.glob(os.path.join(ROOT, "mv3d_tf_b200", "csrc", "_obj", "*.o"))):
