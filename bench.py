@@ -563,6 +563,13 @@ def main():
     leg.close()
     del net, runner
 
+    # configs[2] right after the headline leg (its memory released): the second number BASELINE's metric names, measured
+    # before the side legs below heat the board further
+    if not args.no_train:
+        try:
+            line["train_step"] = run_train_bench(args, rank, world, local_rank)
+        except Exception as e:  # the inference headline must survive a failure of the secondary leg
+            line["train_step"] = {"error": repr(e)[:300]}
     if not args.no_other_views:
         # the other view count through the same pipeline, beside the headline (north_star names three views; the
         # reference has two).  Same clocks caveat: shorter run.
@@ -591,11 +598,6 @@ def main():
             leg.close()
         except Exception as e:
             line["precise_mode"] = {"error": repr(e)[:300]}
-    if not args.no_train:
-        try:
-            line["train_step"] = run_train_bench(args, rank, world, local_rank)
-        except Exception as e:  # the inference headline must survive a failure of the secondary leg
-            line["train_step"] = {"error": repr(e)[:300]}
     if not args.no_extras:
         # configs[4] (raster sweep, every rank rasterises its own clouds: N GPUs = N x the frames) and configs[0]
         # (BEV-only 3D-RPN forward: the CPU port beside the device layer) in the driver-run line
