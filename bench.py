@@ -250,8 +250,10 @@ def run_train_bench(args, rank, world, local_rank):
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_host = time.perf_counter()
     for i in range(args.train_steps):
         loss = step(i)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.train_steps   # Python + host sampling + its two D2H syncs per step
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.train_steps
@@ -274,7 +276,8 @@ def run_train_bench(args, rank, world, local_rank):
     gemm_by_kernel = {k: {"launches": v[0], "ms": v[1], "tflops_1x": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
                       for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
     return {"ms": ms, "gemm_by_kernel": gemm_by_kernel, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
-            "n_gpus": world, "gpu_launches_per_step": launches, "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
+            "n_gpus": world, "gpu_launches_per_step": launches, "host_enqueue_ms_per_step": host_ms,
+            "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
             "loss": [float(x) for x in loss.tolist()], "optimizer": "Adam lr=1e-5 (TF-1.0 defaults), keep_prob 0.5",
             "grad_allreduce": "NCCL all-reduce of the flat fp32 gradient buffer (%.0f MB)" % (sw.grad.numel() * 4 / 1e6)
             if world > 1 else "off (single GPU)", "mode": "precise" if args.mode != "fast" else "fast",

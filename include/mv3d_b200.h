@@ -75,6 +75,9 @@ int mv3d_bev_raster_pad_fmt(const float* d_points, int n_points, int point_strid
  *         (gpu_nms.pyx:23-25 sorts on the host before calling _nms).  Stops after max_keep survivors
  *         (<=0: no limit), which equals the reference's `keep[:post_nms_topN]` (proposal_layer_tf.py:173).
  *         d_n_boxes (optional) overrides n_boxes with a count that lives on the device.
+ *         0 < max_keep <= 2048 (the proposal layer: 300 / 2000) runs as ONE 8-CTA cluster that tests candidates against
+ *         kept boxes only (nms_lazy_kernel: same predicate, same order, identical survivor list; the workspace is not
+ *         touched); otherwise the all-pairs mask + keep chain.  MV3D_NMS_LAZY=0 forces the latter.
  * ------------------------------------------------------------------------------------------- */
 void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
           float nms_overlap_thresh, int device_id);
