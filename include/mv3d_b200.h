@@ -239,6 +239,9 @@ typedef struct {
      * are then the POOLED PAD planes (B, H/2 + 1, W/2 + 1, ld_out), halos zeroed by the kernel; the un-pooled activation
      * is never written.  N = 64 or 128, Cin % 64 == 0, passes 2 or 3, no float32 / gate / addend output. */
     int pool;
+    /* > 0 with Cin == 64: only the first cin_valid input channels of the (zero-padded) 64-channel chunk are non-zero
+     * (the BEV map: 36), so the CTA-pair 3x3 kernel skips the 16-channel k-steps that would multiply zeros.  0 = all. */
+    int cin_valid;
 } mv3d_gemm_desc;
 int mv3d_conv_gemm(const mv3d_gemm_desc* desc, void* stream);
 /* A/B switch for the CTA-pair (tcgen05 cta_group::2, 256 x N tiles) form of the tap-reuse 3x3 conv kernel: on (default,

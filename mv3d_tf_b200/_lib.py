@@ -50,7 +50,8 @@ class GemmDesc(C.Structure):
                 ("d_out_hi", c_void_p), ("d_out_lo", c_void_p), ("ld_out", c_int),
                 ("d_out_f32", c_void_p), ("ld_f32", c_int), ("f32_dense", c_int), ("split_k", c_int),
                 ("d_mask_hi", c_void_p), ("ld_mask", c_int), ("mask_scale", c_float),
-                ("d_addend_f32", c_void_p), ("ld_addend", c_int), ("out_fmt", c_int), ("softmax_cols", c_int), ("pool", c_int)]
+                ("d_addend_f32", c_void_p), ("ld_addend", c_int), ("out_fmt", c_int), ("softmax_cols", c_int), ("pool", c_int),
+                ("cin_valid", c_int)]
 
 
 class WgradDesc(C.Structure):

@@ -197,6 +197,12 @@ def _run_gemm(_flops=0.0, **kw):
         GEMM_EVENTS.append((e0, e1, gemm_kernel_name(d.taps, d.Cin, d.N, d.passes, d.split_k, d.M, d.Hp), float(_flops)))
 
 
+def _cin_valid(a: PadAct, w: PackedWeight) -> int:
+    """mv3d_gemm_desc.cin_valid: a single zero-padded 64-channel chunk with fewer real channels (the 36-channel BEV map)."""
+    c = min(a.C, w.cin)
+    return c if (w.taps == 9 and a.c_pad == 64 and c < 64) else 0
+
+
 def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, out_pad: bool = True,
          out_f32_dense: bool = False, mask: Optional["PadAct"] = None, mask_scale: float = 1.0,
          addend: Optional[torch.Tensor] = None, use_bias: bool = True, out_fmt: int = FMT_BF16X2, softmax_cols: int = 0,
@@ -219,7 +225,7 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
                   M=a.rows, N=w.cout, Cin=a.c_pad, taps=w.taps, Hp=a.H + 1, Wp=a.W + 1, passes=passes, out_fmt=out_fmt,
                   d_a_hi=ptr(a.hi), d_a_lo=ptr(a.lo), d_w_hi=ptr(w.hi), d_w_lo=ptr(w.lo),
                   d_bias=ptr(w.bias) if use_bias else None, relu=int(relu), d_out_hi=ptr(hi), d_out_lo=ptr(lo), ld_out=n_pad,
-                  d_out_f32=None, ld_f32=0, f32_dense=0, split_k=1, pool=1)
+                  d_out_f32=None, ld_f32=0, f32_dense=0, split_k=1, pool=1, cin_valid=_cin_valid(a, w))
         return out, None
     if out_pad:
         assert out_fmt == FMT_BF16X2 or w.cout % 64 == 0
@@ -238,7 +244,8 @@ def conv(a: PadAct, w: PackedWeight, relu: bool = True, precise: bool = True, ou
               ld_out=n_pad, d_out_f32=ptr(dense), ld_f32=w.cout, f32_dense=1 if out_f32_dense else 0, split_k=1,
               d_mask_hi=ptr(mask.hi) if mask is not None else None, ld_mask=mask.c_pad if mask is not None else 0,
               mask_scale=float(mask_scale), d_addend_f32=ptr(addend),
-              ld_addend=addend.shape[-1] if addend is not None else 0, softmax_cols=int(softmax_cols))
+              ld_addend=addend.shape[-1] if addend is not None else 0, softmax_cols=int(softmax_cols),
+              cin_valid=_cin_valid(a, w))
     return out, dense
 
 

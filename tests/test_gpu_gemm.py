@@ -86,6 +86,7 @@ def test_fc_gemm_f16e5_operands(M, N, K):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,passes", [
     (1, 9, 11, 3, 64, 3), (2, 16, 20, 64, 64, 3), (1, 37, 41, 36, 64, 3), (1, 23, 50, 128, 256, 3),
     (1, 23, 50, 128, 256, 1), (1, 12, 13, 512, 512, 3), (1, 75, 75, 64, 128, 3), (1, 40, 33, 9, 64, 1),
+    (1, 21, 40, 20, 64, 3), (1, 21, 40, 33, 256, 3),
 ])
 def test_conv3x3(B, H, W, Cin, Cout, passes):
     from mv3d_tf_b200 import kernels as k
@@ -245,7 +246,7 @@ def _f16e5_conv_emulation(x, w, b):
 @pytest.mark.parametrize("pair", [True, False])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [
     (1, 12, 13, 64, 64), (1, 23, 50, 128, 256), (1, 30, 33, 256, 512), (2, 75, 75, 64, 128), (1, 87, 100, 512, 512),
-    (1, 37, 41, 36, 64),
+    (1, 37, 41, 36, 64), (1, 20, 60, 17, 64), (1, 20, 60, 48, 128),   # zero-padded 64-channel chunk: k-steps of zeros skipped
 ])
 def test_conv3x3_f16e5(B, H, W, Cin, Cout, pair):
     """passes=2: fp16 main pass + one e5m2 pass carrying both first-order correction terms.  Checked (a) against an fp64
