@@ -147,7 +147,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_bf16_mn(128, BNX);
-        constexpr uint32_t x_layout = BNX >= 64 ? 2u : 6u;                 // SWIZZLE_128B / SWIZZLE_32B
+        constexpr uint32_t x_layout = BNX >= 64 ? 2u : (BNX == 32 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B (= the TMA box width)
         constexpr uint32_t x_sbo = 8 * Cfg::kXRowBytes;                     // 8 pixel rows
         constexpr uint32_t x_k16 = 16 * Cfg::kXRowBytes;                    // 16 pixels (one MMA K step)
         int it = 0, tl = 0;
@@ -289,6 +289,7 @@ template <int PASSES>
 static int dispatch_wgrad(const mv3d_wgrad_desc* d, cudaStream_t s) {
     if (d->Cx % 128 == 0) return launch_wgrad<128, PASSES>(d, s);
     if (d->Cx % 64 == 0) return launch_wgrad<64, PASSES>(d, s);
+    if (d->Cx == 32) return launch_wgrad<32, PASSES>(d, s);   // the im2col'd first image layer: taps = 1, K = 27 of 32
     return launch_wgrad<16, PASSES>(d, s);
 }
 
@@ -303,7 +304,7 @@ extern "C" __attribute__((visibility("default"))) int mv3d_conv_wgrad(const mv3d
     MV3D_REQUIRE(d->d_x_hi && d->d_g_hi && d->d_dw);
     MV3D_REQUIRE(d->passes == 1 || (d->d_x_lo && d->d_g_lo));
     MV3D_REQUIRE(d->Cg % 64 == 0 && d->Cg >= d->cout);
-    MV3D_REQUIRE((d->Cx % 64 == 0 || d->Cx == 16) && d->Cx >= d->cin);
+    MV3D_REQUIRE((d->Cx % 64 == 0 || d->Cx == 16 || (d->Cx == 32 && d->taps == 1)) && d->Cx >= d->cin);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return d->passes == 3 ? dispatch_wgrad<3>(d, s) : dispatch_wgrad<1>(d, s);
 }

@@ -330,7 +330,13 @@ class SolverWrapper(object):
             gn = K.pad_nhwc_masked(d, vals[node].pad, precise=precise)   # only the ROI path feeds this layer
         src = node.inputs[0]
         x = vals[src].pad
-        K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
+        if x is None and isinstance(vals[src].extra, K.PadAct):
+            # first image layer: the forward kept the im2col rows of the input (Network.conv) -- one taps = 1 GEMM, K = 27
+            dw = g[node.name]['weights']
+            K.conv_wgrad(vals[src].extra, gn, dw.view(1, dw.shape[0] * dw.shape[1] * dw.shape[2], dw.shape[3]),
+                         precise=precise, accumulate=True, tap_window=False)
+        else:
+            K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
         K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
         if self.exchange is not None:   # this layer's slice (and everything above it in its region) is final
             off = self.slices[node.name][0]

@@ -268,6 +268,15 @@ class Network(object):
                 p = self.params[name]
                 return Val(pad=K.conv3x3_small_cin(v.dense, p['weights'].contiguous(), p['biases'], relu=relu,
                                                    precise=self.precise, out_fmt=self._pad_out_fmt(node)))
+            if (k_h, k_w) == (3, 3) and c_i <= 3 and c_o == 64 and v.dense is not None and v.pad is None \
+                    and self.training and not want_dense:
+                # training: the same tcgen05 first-layer kernel forward (bf16 hi/lo out); the backward-filter pass of this
+                # layer is ONE taps = 1 GEMM over the im2col rows kept here (K = 27 of 32) instead of nine N = 16 taps
+                p = self.params[name]
+                if not isinstance(v.extra, K.PadAct):
+                    v.extra = K.im2col3x3(v.dense, precise=self.precise)
+                return Val(pad=K.conv3x3_small_cin(v.dense, p['weights'].contiguous(), p['biases'], relu=relu,
+                                                   precise=self.precise, out_fmt=K.FMT_BF16X2))
             if (k_h, k_w) == (3, 3) and 9 * c_i <= 32 and v.dense is not None and v.pad is None and not self.training:
                 # same layer when its dense output is wanted too: im2col once, then ONE K=32 GEMM instead of nine taps
                 # of 13/16 zero padding

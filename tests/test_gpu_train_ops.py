@@ -47,6 +47,28 @@ def test_conv_wgrad(B, H, W, Cin, Cout, tap_window, passes):
     assert _relerr(dw, 2 * ref) < (5e-5 if precise else 1e-5)
 
 
+def test_first_layer_wgrad_through_im2col():
+    """Backward-filter of the first image layer as ONE taps = 1 GEMM over the im2col rows (K = 27 of 32, wgrad_kernel<32>)
+    == the nine-tap form over the 16-channel PAD image == torch."""
+    from mv3d_tf_b200 import kernels as k
+
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, Cout = 2, 37, 120, 64
+    x = torch.randn(B, H, W, 3, device="cuda", generator=gen) * 40
+    g = torch.randn(B, H, W, Cout, device="cuda", generator=gen)
+    ga = k.pad_nhwc(g, precise=True)
+    col = k.im2col3x3(x, precise=True)
+    assert col.c_pad == 32
+    dw = torch.zeros(3, 3, 3, Cout, device="cuda")
+    k.conv_wgrad(col, ga, dw.view(1, 27, Cout), precise=True, accumulate=True, tap_window=False)
+    dw9 = torch.zeros(3, 3, 3, Cout, device="cuda")
+    k.conv_wgrad(k.pad_nhwc(x, precise=True), ga, dw9, precise=True, accumulate=True)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (Cout, 3, 3, 3), g.double().permute(0, 3, 1, 2), padding=1)
+    ref = ref.permute(2, 3, 1, 0)
+    assert _relerr(dw, ref) < 5e-5 and _relerr(dw9, ref) < 5e-5
+
+
 @pytest.mark.parametrize("R,K,N,accumulate", [(100, 1024, 200, 1), (256, 3136, 2048, 0), (77, 128, 50, 1), (300, 4096, 50, 1)])
 def test_linear_wgrad(R, K, N, accumulate):
     from mv3d_tf_b200 import kernels as k
