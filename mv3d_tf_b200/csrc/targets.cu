@@ -38,23 +38,30 @@ __global__ void anchor_overlap_kernel(const int* __restrict__ anchors, int N, co
                                       float im_h, float im_w, double* __restrict__ max_ov, int* __restrict__ argmax,
                                       unsigned long long* __restrict__ gt_max_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int* a = anchors + (size_t)i * 4;
-    if (!anchor_inside(a, im_h, im_w)) {
-        max_ov[i] = -1.0;
-        argmax[i] = -1;
-        return;
-    }
+    const int* a = anchors + (size_t)(i < N ? i : 0) * 4;
+    const bool inside = i < N && anchor_inside(a, im_h, im_w);
     double best = -1.0;
-    int arg = 0;
+    int arg = inside ? 0 : -1;
     for (int g = 0; g < G; ++g) {
         const float* q = gt_bv + (size_t)g * 5;
-        const double ov = iou_f64(a[0], a[1], a[2], a[3], q[0], q[1], q[2], q[3]);
-        if (ov > best) { best = ov; arg = g; }
-        atomicMax(gt_max_bits + g, (unsigned long long)__double_as_longlong(ov));
+        unsigned long long bits = 0ull;   // non-negative doubles order like their bit patterns; 0 = no contribution
+        if (inside) {
+            const double ov = iou_f64(a[0], a[1], a[2], a[3], q[0], q[1], q[2], q[3]);
+            if (ov > best) { best = ov; arg = g; }
+            bits = (unsigned long long)__double_as_longlong(ov);
+        }
+        // one atomic per warp and GT box instead of one per anchor (34 800 x G updates of G addresses serialise in L2)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, d);
+            bits = o > bits ? o : bits;
+        }
+        if ((threadIdx.x & 31) == 0 && bits != 0ull) atomicMax(gt_max_bits + g, bits);
     }
-    max_ov[i] = best;
-    argmax[i] = arg;
+    if (i < N) {
+        max_ov[i] = best;
+        argmax[i] = arg;
+    }
 }
 
 // pass 2: labels before sub-sampling (anchor_target_layer_tf.py:104-143) and regression targets (:164-165).

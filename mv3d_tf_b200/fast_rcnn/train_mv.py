@@ -60,6 +60,7 @@ class SolverWrapper(object):
         self.loss = torch.zeros(4, dtype=torch.float32, device=net.device)  # rpn_cls, rpn_box, cls, box
         self.last_grad_events = None
         self._side = None
+        self._bias_streams = {}          # producing stream handle -> helper stream for that trunk's bias gradients
         if self.exchange is not None:
             self._set_exchange_regions()
 
@@ -304,6 +305,8 @@ class SolverWrapper(object):
                 self._backward_node(node, vals, grads, dense_in, g, precise)
         if side is not None:
             main.wait_stream(side)
+        for bs in self._bias_streams.values():   # every bias gradient landed before the exchange finishes / Adam reads
+            main.wait_stream(bs)
 
     def _region_of(self, off):
         for key, (lo, hi) in self.exchange._regions.items():
@@ -328,6 +331,23 @@ class SolverWrapper(object):
             if d is None:
                 return
             gn = K.pad_nhwc_masked(d, vals[node].pad, precise=precise)   # only the ROI path feeds this layer
+        # The bias gradient re-reads the whole gradient at the HBM rate while the filter-gradient GEMM of the same layer is
+        # tensor-bound and leaves most of every SM's shared memory / registers free: it goes to a helper stream and runs
+        # UNDER that GEMM instead of in front of it.
+        cur = torch.cuda.current_stream()
+        bs = self._bias_streams.get(cur.cuda_stream)
+        if bs is None:
+            bs = self._bias_streams[cur.cuda_stream] = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        bs.wait_event(ready)
+        with torch.cuda.stream(bs):
+            K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
+            bias_done = torch.cuda.Event()
+            bias_done.record(bs)
+        gn.hi.record_stream(bs)
+        if gn.lo is not None:
+            gn.lo.record_stream(bs)
         src = node.inputs[0]
         x = vals[src].pad
         if x is None and isinstance(vals[src].extra, K.PadAct):
@@ -337,8 +357,8 @@ class SolverWrapper(object):
                          precise=precise, accumulate=True, tap_window=False)
         else:
             K.conv_wgrad(x, gn, g[node.name]['weights'], precise=precise, accumulate=True)
-        K.bias_grad(gn.hi, gn.lo, node.channels, g[node.name]['biases'])
         if self.exchange is not None:   # this layer's slice (and everything above it in its region) is final
+            cur.wait_event(bias_done)
             off = self.slices[node.name][0]
             self.exchange.ready(self.grad, off, key=self._region_of(off))
         if src.kind == 'placeholder':
