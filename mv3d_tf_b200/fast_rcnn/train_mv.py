@@ -55,11 +55,12 @@ class SolverWrapper(object):
         if pretrained_model is not None:
             net.load(pretrained_model, None, None, True)
         self._flatten_parameters()
-        self._dpacked: Dict[str, K.PackedWeight] = {}
+        self._dpacked = K.PackCache()
         net._on_weights_changed.append(self._dpacked.clear)   # Network.load on a live solver (resume)
         self.loss = torch.zeros(4, dtype=torch.float32, device=net.device)  # rpn_cls, rpn_box, cls, box
         self.last_grad_events = None
         self._side = None
+        self._pack_stream = None
         self._bias_streams = {}          # producing stream handle -> helper stream for that trunk's bias gradients
         if self.exchange is not None:
             self._set_exchange_regions()
@@ -158,12 +159,10 @@ class SolverWrapper(object):
 
     def _dweight(self, key, names) -> K.PackedWeight:
         """Backward-data operand of one layer (or of sibling heads concatenated along the output axis)."""
-        pw = self._dpacked.get(key)
-        if pw is None:
+        def build():
             ws = [self.net.params[n]['weights'] for n in names]
-            w = ws[0] if len(ws) == 1 else torch.cat(ws, dim=-1).contiguous()
-            pw = self._dpacked[key] = K.pack_weights_dgrad(w)
-        return pw
+            return K.pack_weights_dgrad(ws[0] if len(ws) == 1 else torch.cat(ws, dim=-1).contiguous())
+        return self._dpacked.get(key, build)
 
     # ------------------------------------------------------------------ one training step
     def train_step(self, blobs, keep_prob=None, apply_update=True):
@@ -200,8 +199,19 @@ class SolverWrapper(object):
             check(lib().mv3d_adam(ptr(self.theta), ptr(self.grad), ptr(self.m), ptr(self.v), self.theta.numel(),
                                   self.lr, self.beta1, self.beta2, self.epsilon, self.step, grad_scale,
                                   current_stream()), 'mv3d_adam')
-            net._packed.clear()
-            self._dpacked.clear()
+            # every GEMM operand of the new weights is re-packed on a helper stream right away (under the next step's
+            # target layers / rasteriser / first convs) instead of lazily in front of its consumer
+            if os.environ.get('MV3D_ASYNC_REPACK', '1') == '0':     # A/B: lazy re-pack in front of each consumer
+                net._packed.clear()
+                self._dpacked.clear()
+                return self.loss
+            if self._pack_stream is None:
+                self._pack_stream = torch.cuda.Stream()
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            self._pack_stream.wait_event(done)
+            net._packed.rebuild_async(self._pack_stream)
+            self._dpacked.rebuild_async(self._pack_stream)
         return self.loss
 
     # ------------------------------------------------------------------ backward pass
