@@ -251,12 +251,21 @@ def run_train_bench(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t_host = time.perf_counter()
+    per_step = []
     for i in range(args.train_steps):
         loss = step(i)
+        if os.environ.get("MV3D_TRAIN_TRACE"):   # per-step device times (adds one event per step)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            per_step.append(ev)
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.train_steps   # Python + host sampling + its two D2H syncs per step
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.train_steps
+    if per_step:
+        ts = [e0.elapsed_time(ev) for ev in per_step]
+        d = [b - a for a, b in zip([0.0] + ts[:-1], ts)]
+        print("train per-step ms: median %.2f | %s" % (float(np.median(d)), " ".join("%.1f" % x for x in d)), file=sys.stderr)
     launches = _lib.launch_count() // args.train_steps
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:

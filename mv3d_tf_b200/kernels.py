@@ -149,55 +149,6 @@ def pack_weights(w_hwio: torch.Tensor, bias: Optional[torch.Tensor], cin_pad: Op
     return PackedWeight(hi, lo, b, taps, cin, cp, cout, fmt)
 
 
-class PackCache:
-    """Packed GEMM operands by key, rebuilt when the weights change.  `get(key, build)` builds lazily the first time and
-    remembers the recipe; a trainer calls `rebuild_async(stream)` after its optimizer step so that every operand used since
-    the last rebuild is re-packed on a helper stream (under the next step's first layers) instead of in front of its
-    consumer; `get` then makes the consuming stream wait for that operand's event only."""
-
-    def __init__(self):
-        self.store, self.recipes, self.events = {}, {}, {}
-        self.used, self.waited = set(), set()
-
-    def get(self, key, build):
-        pw = self.store.get(key)
-        self.used.add(key)
-        if pw is None:
-            pw = self.store[key] = build()
-            self.recipes[key] = build
-            return pw
-        ev = self.events.get(key)
-        if ev is not None:
-            cur = torch.cuda.current_stream()
-            tag = (key, cur.cuda_stream)
-            if tag not in self.waited:
-                cur.wait_event(ev)
-                self.waited.add(tag)
-        return pw
-
-    def clear(self):
-        self.store.clear()
-        self.events.clear()
-        self.waited.clear()
-
-    def __contains__(self, key):
-        return key in self.store
-
-    def __len__(self):
-        return len(self.store)
-
-    def rebuild_async(self, stream) -> None:
-        keys = [k for k in self.recipes if k in self.used]
-        self.clear()
-        self.used = set()
-        with torch.cuda.stream(stream):
-            for k in keys:
-                self.store[k] = self.recipes[k]()
-                ev = torch.cuda.Event()
-                ev.record(stream)
-                self.events[k] = ev
-
-
 PAIR_MODE = os.environ.get("MV3D_PAIR", "1") != "0"  # mirrors pair_mode() in csrc/conv_gemm_tcgen05.cu
 
 

@@ -88,7 +88,7 @@ class Network(object):
         self.device = torch.device(device)
         self.params: Dict[str, Dict[str, torch.Tensor]] = {}
         self.param_specs: Dict[str, dict] = {}
-        self._packed = K.PackCache()      # packed GEMM operands by key (see kernels.PackCache)
+        self._packed: Dict[str, K.PackedWeight] = {}
         self._on_weights_changed: List[Callable] = []   # e.g. the solver's backward-data operand cache
         self._program: List[Node] = []
         self._proposal_layers: Dict[tuple, ProposalLayer3D] = {}
@@ -210,14 +210,14 @@ class Network(object):
 
     def _weight(self, name, transform=None, fmt=K.FMT_BF16X2) -> K.PackedWeight:
         key = name if fmt == K.FMT_BF16X2 else name + '/f16e5'
-
-        def build():
+        pw = self._packed.get(key)
+        if pw is None:
             p = self.params[name]
             w = p['weights']
             if transform is not None and not self.native_fc_layout:
                 w = transform(w)
-            return K.pack_weights(w, p['biases'], fmt=fmt)
-        return self._packed.get(key, build)
+            pw = self._packed[key] = K.pack_weights(w, p['biases'], fmt=fmt)
+        return pw
 
     def _pad_out_fmt(self, node) -> int:
         """Operand format of a conv node's PAD output: FMT_F16E5 when every reader of that PAD tensor is a 3x3 conv
@@ -282,8 +282,11 @@ class Network(object):
                 # of 13/16 zero padding
                 col = v.extra if isinstance(v.extra, K.PadAct) else K.im2col3x3(v.dense, precise=self.precise)
                 v.extra = col
-                pw = self._packed.get(name + '/im2col', lambda: K.pack_weights(
-                    self.params[name]['weights'].reshape(1, 1, 9 * c_i, c_o), self.params[name]['biases'], cin_pad=32))
+                pw = self._packed.get(name + '/im2col')
+                if pw is None:
+                    p = self.params[name]
+                    pw = self._packed[name + '/im2col'] = K.pack_weights(p['weights'].reshape(1, 1, 9 * c_i, c_o),
+                                                                         p['biases'], cin_pad=32)
                 out, dense = K.conv(col, pw, relu=relu, precise=self.precise, out_pad=want_pad, out_f32_dense=want_dense,
                                     out_fmt=self._pad_out_fmt(node))
                 return Val(pad=out, dense=dense)
@@ -298,11 +301,11 @@ class Network(object):
                 # concatenated output channels; when the leader only feeds reshape -> softmax -> reshape (:76-81) the
                 # pair softmax runs in that GEMM's epilogue and the three glue nodes pass the result through
                 key = name + '+' + '+'.join(f.name for f in followers)
-                def build_heads():
+                pw = self._packed.get(key)
+                if pw is None:
                     ws = [self.params[name]] + [self.params[f.name] for f in followers]
-                    return K.pack_weights(torch.cat([q['weights'] for q in ws], dim=3).contiguous(),
-                                          torch.cat([q['biases'] for q in ws], dim=0).contiguous())
-                pw = self._packed.get(key, build_heads)
+                    pw = self._packed[key] = K.pack_weights(torch.cat([q['weights'] for q in ws], dim=3).contiguous(),
+                                                            torch.cat([q['biases'] for q in ws], dim=0).contiguous())
                 fold = self._softmax_chain(node) is not None
                 _, dense = K.conv(v.pad, pw, relu=False, precise=self.precise, out_pad=False, out_f32_dense=True,
                                   softmax_cols=c_o if fold else 0)
@@ -581,11 +584,12 @@ class Network(object):
             followers = node.attrs.get('fused_followers', [])
             if followers:  # sibling heads on the same input (cls_score + bbox_pred): ONE GEMM over concatenated weights
                 key = name + '+' + '+'.join(f.name for f in followers)
-                def build_fc_heads():
+                pw = self._packed.get(key)
+                if pw is None:
                     ws = [self.params[name]] + [self.params[f.name] for f in followers]
-                    return K.pack_weights(torch.cat([p['weights'] for p in ws], dim=1).contiguous(),
-                                          torch.cat([p['biases'] for p in ws], dim=0).contiguous())
-                pw = self._packed.get(key, build_fc_heads)
+                    wcat = torch.cat([p['weights'] for p in ws], dim=1).contiguous()
+                    bcat = torch.cat([p['biases'] for p in ws], dim=0).contiguous()
+                    pw = self._packed[key] = K.pack_weights(wcat, bcat)
                 _, _, f32 = K.linear(v.hi, v.lo, pw, relu=False, precise=self.precise, out_bf16=False, out_f32=True,
                                      split_k=split_for(M, pw.cout, dim))
                 off = num_out
