@@ -254,18 +254,17 @@ def run_train_bench(args, rank, world, local_rank):
     per_step = []
     for i in range(args.train_steps):
         loss = step(i)
-        if os.environ.get("MV3D_TRAIN_TRACE"):   # per-step device times (adds one event per step)
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-            per_step.append(ev)
+        ev = torch.cuda.Event(enable_timing=True)   # per-step device times (one event per step)
+        ev.record(stream)
+        per_step.append(ev)
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.train_steps   # Python + host sampling + its two D2H syncs per step
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.train_steps
-    if per_step:
-        ts = [e0.elapsed_time(ev) for ev in per_step]
-        d = [b - a for a, b in zip([0.0] + ts[:-1], ts)]
-        print("train per-step ms: median %.2f | %s" % (float(np.median(d)), " ".join("%.1f" % x for x in d)), file=sys.stderr)
+    ts = [e0.elapsed_time(ev) for ev in per_step]
+    step_ms = [b - a for a, b in zip([0.0] + ts[:-1], ts)]
+    if os.environ.get("MV3D_TRAIN_TRACE"):
+        print("train per-step ms: median %.2f | %s" % (float(np.median(step_ms)), " ".join("%.1f" % x for x in step_ms)), file=sys.stderr)
     launches = _lib.launch_count() // args.train_steps
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -284,7 +283,7 @@ def run_train_bench(args, rank, world, local_rank):
     kernels.GEMM_EVENTS = None
     gemm_by_kernel = {k: {"launches": v[0], "ms": v[1], "tflops_1x": v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0}
                       for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])}
-    return {"ms": ms, "gemm_by_kernel": gemm_by_kernel, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
+    return {"ms": ms, "ms_median_step": float(np.median(step_ms)), "gemm_by_kernel": gemm_by_kernel, "frames_per_step_per_gpu": B, "frames_per_s": world * B / (ms * 1e-3), "steps": args.train_steps,
             "n_gpus": world, "gpu_launches_per_step": launches, "host_enqueue_ms_per_step": host_ms,
             "gemm_ms": gemm_ms, "gemm_launches": n_gemm,
             "loss": [float(x) for x in loss.tolist()], "optimizer": "Adam lr=1e-5 (TF-1.0 defaults), keep_prob 0.5",
@@ -325,7 +324,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer: configs[1] frames/s (the headline); train: configs[2] train-step ms only")
-    ap.add_argument("--train-steps", type=int, default=5, help="timed train steps reported under train_step")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed train steps reported under train_step")
     ap.add_argument("--train-batch", type=int, default=2)
     ap.add_argument("--no-train", action="store_true", help="skip the train_step leg of the default run")
     ap.add_argument("--no-precise-leg", action="store_true",
