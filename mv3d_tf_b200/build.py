@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libmv3d_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("MV3D_NVCC_FLAGS", "").split()
 # --fmad=false: the integer-exact kernels restate numpy arithmetic (separate mul and add roundings);
 # the tensor-core GEMM does its math in tcgen05.mma and is unaffected.
 

@@ -877,8 +877,16 @@ struct PairCfg {
     static_assert(BN % 16 == 0 && BN <= 256, "M=256 MMA: N multiple of 16, at most 256");
 };
 
+// Register budget of the pair kernel.  Default: whatever the epilogue wants (168 x 320 threads = 82 % of the register file:
+// hardly anything of another stream can share the SM).  -DMV3D_PAIR_MAXNREG=128 caps it (a few spilled epilogue values)
+// so that small kernels of the other trunk / frame (<= 24 k registers, <= 27 KB shared memory) co-reside.
+#ifdef MV3D_PAIR_MAXNREG
+#define MV3D_PAIR_BOUNDS __maxnreg__(MV3D_PAIR_MAXNREG)
+#else
+#define MV3D_PAIR_BOUNDS __launch_bounds__(kGemmThreads, 1)
+#endif
 template <int BN, int PASSES, bool LEAN = false, bool WRES = false, bool POOL = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) MV3D_PAIR_BOUNDS
 conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                     const GemmParams prm) {
