@@ -57,6 +57,7 @@ struct GemmParams {
                       // drains the accumulator but skips its math and stores.  Together they isolate the MMA rate.
     int softmax_cols;   // mv3d_gemm_desc::softmax_cols
     int pool, pool_Ho, pool_Wo, pool_nblk;   // fused 2x2 max-pool (pair kernel, POOL): pooled size, 128-column blocks per row
+    int pdl;            // launched with programmaticStreamSerialization: griddepcontrol.wait before the first dependent read
     int k16_steps;      // 16-channel k-steps per 64-channel chunk that hold non-zero input channels (4 unless mv3d_gemm_desc::cin_valid)
     int e5_ksteps;      // f16e5 (PASSES = 2): 32-byte k-steps of the e5m2 row the MMA loop covers -- 4 = both correction terms, 2 = A_h W_l only
     long long* stamps;  // measurement only (mv3d_gemm_set_stamps): clock64 of pair 0's phases, see conv3x3_pair_kernel
@@ -912,6 +913,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     if (threadIdx.x == 0) stamp(prm, 0);   // kernel start
+    if (prm.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the NEXT kernel may be scheduled as SMs free up
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a_hi);
@@ -946,6 +948,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
     if (warp == 0) {
         if (lane == 0) {
+            // everything this kernel reads from global memory comes through this thread's TMA loads: the one place that has
+            // to wait for the stream predecessor (all other warps are ordered behind the loads through the mbarriers)
+            if (prm.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
             int ia = 0, iw = 0;
             for (int w = pair_id; w < n_work; w += n_pairs) {
                 const int n0 = (w % tiles_n) * BN + (int)rank * Cfg::kWRows;
@@ -1260,6 +1265,11 @@ static int pair_mode() {  // MV3D_PAIR=0 selects the single-CTA kernels (A/B com
     return g_pair_mode;
 }
 
+static int g_pdl = -1;
+static int pdl_mode() {   // MV3D_PDL=1: pair kernels are launched as programmatic dependents of their stream predecessor
+    if (g_pdl < 0) { const char* e = getenv("MV3D_PDL"); g_pdl = e ? atoi(e) : 0; }
+    return g_pdl;
+}
 static int g_e5_ksteps = -1;
 static int e5_ksteps_mode() {   // MV3D_F16E5_TERMS=1: experiment -- drop the activation-residual term (A_l W_h) of the f16e5 product
     if (g_e5_ksteps < 0) { const char* e = getenv("MV3D_F16E5_TERMS"); g_e5_ksteps = (e && atoi(e) == 1) ? 2 : 4; }
@@ -1301,7 +1311,7 @@ static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.e5_ksteps = e5_ksteps_mode();
     p.k16_steps = (d->cin_valid > 0 && d->Cin == 64) ? ceil_div(d->cin_valid < 64 ? d->cin_valid : 64, 16) : 4;
     p.softmax_cols = d->softmax_cols;
-    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0; p.pdl = 0;
     p.tiles_n = d->N / BN;
     p.tiles_m = ceil_div(d->M, 2 * kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1327,6 +1337,25 @@ static int launch_pair_impl(const mv3d_gemm_desc* d, cudaStream_t stream) {
         max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
     }
     const int pairs = p.n_work < max_pairs ? p.n_work : max_pairs;
+    if (pdl_mode()) {
+        // programmatic dependent launch: this kernel's CTAs may be scheduled while the previous kernel of the stream drains
+        // (each SM as soon as its CTA of that kernel has exited); the producer warp's griddepcontrol.wait holds every
+        // read of the previous kernel's output until that kernel has completed
+        p.pdl = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs, 1, 1);
+        cfg.blockDim = dim3(kGemmThreads, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mw_hi, mw_lo, p);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return MV3D_ERR_LAUNCH; }
+        return MV3D_OK;
+    }
     kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     MV3D_CHECK_LAUNCH();
     return MV3D_OK;
@@ -1453,7 +1482,7 @@ static int launch_reuse(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
     p.softmax_cols = d->softmax_cols;
-    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0; p.pdl = 0;
     p.tiles_n = ceil_div(d->N, BN);
     p.tiles_m = ceil_div(d->M, kBM);
     p.n_work = p.tiles_n * p.tiles_m;
@@ -1507,7 +1536,7 @@ static int launch_gemm(const mv3d_gemm_desc* d, cudaStream_t stream) {
     p.dbg_flags = gemm_dbg_flags();
     p.stamps = nullptr;
     p.softmax_cols = d->softmax_cols;
-    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0;
+    p.pool = 0; p.pool_Ho = p.pool_Wo = p.pool_nblk = 0; p.pdl = 0;
 
     auto kern = conv_gemm_kernel<BN, KC, PASSES>;
     static bool attr_set = false;  // per instantiation
