@@ -275,11 +275,18 @@ __device__ __forceinline__ void resolve_points(const float* __restrict__ pts, in
             if (__ldcg(bits + cell + sl) != key) continue;           // another point wrote this (cell, slice) later
             // highest occupied slice of the cell?  Slots above hold 0 (empty), a key, or a height > 0 -- never 0 once
             // occupied (slice sl' >= 1 starts at h0 + sl' * zres), whichever of its two states a slot is in right now.
-            bool top_slice = true;
-            for (int up = sl + 1; up < g.nslices; ++up)
-                if (__ldcg(bits + cell + up) != 0u) { top_slice = false; break; }
+            // All slots above are loaded first and OR-ed (independent loads, one memory latency): a loop with an early
+            // exit made up to nslices - 1 dependent round trips for the ground-level points that are most of a cloud.
+            unsigned int above = 0u;
+            int up = sl + 1;
+            for (; up < g.nslices && ((cell + up) & 3) != 0; ++up) above |= __ldcg(bits + cell + up);
+            for (; up + 4 <= g.nslices; up += 4) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(bits + cell + up));
+                above |= v.x | v.y | v.z | v.w;
+            }
+            for (; up < g.nslices; ++up) above |= __ldcg(bits + cell + up);
             top[cell + sl] = __fsub_rn(q.z, g.h0);                    // read_lidar.py:106,110
-            if (top_slice) top[cell + g.C - 1] = q.w;                 // :113: last writer of the highest occupied slice
+            if (above == 0u) top[cell + g.C - 1] = q.w;               // :113: last writer of the highest occupied slice
         }
     }
 }
