@@ -249,6 +249,9 @@ def run_train_bench(args, rank, world, local_rank):
     torch.cuda.synchronize()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()     # a generation-2 collection inside the 10 timed steps shows up as one 30+ ms step (Python, not the GPU)
     e0.record(stream)
     t_host = time.perf_counter()
     per_step = []
@@ -260,6 +263,7 @@ def run_train_bench(args, rank, world, local_rank):
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.train_steps   # Python + host sampling + its two D2H syncs per step
     e1.record(stream)
     torch.cuda.synchronize()
+    gc.enable()
     ms = e0.elapsed_time(e1) / args.train_steps
     ts = [e0.elapsed_time(ev) for ev in per_step]
     step_ms = [b - a for a, b in zip([0.0] + ts[:-1], ts)]
