@@ -199,7 +199,10 @@ __device__ __forceinline__ void load_cell8(const RoiViewDev& V, int batch, int h
 // One CTA = one roi x one view x one 64-channel slice: the window's cells of that slice are staged in shared memory
 // in ONE round of independent 128-bit loads (narrower channel sub-slices when the window has more than 108 cells,
 // direct reads beyond 864), then 8-channel lanes render the 49 bins from shared memory.
-__global__ void __launch_bounds__(kFusedThreads)
+#ifndef MV3D_ROI_MINBLOCKS
+#define MV3D_ROI_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kFusedThreads, MV3D_ROI_MINBLOCKS)
 roi_pool_fused_kernel(RoiViews views, RoiProjDev proj, const float* __restrict__ rois_3d, int R,
                       const int* __restrict__ d_num_valid, int C, int PH, int PW) {
     extern __shared__ float4 stage[];
