@@ -330,3 +330,4 @@ def test_conv3x3_fused_maxpool(B, H, W, Cin, Cout, fmt):
     assert int(hi[:, :, 0, :].abs().max()) == 0 and int(hi[:, H // 2, :, :].abs().max()) == 0
     lo = fused.lo.view(torch.int16)
     assert int(lo[:, :, 0, :].abs().max()) == 0 and int(lo[:, H // 2, :, :].abs().max()) == 0
+
