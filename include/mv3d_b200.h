@@ -299,9 +299,11 @@ int mv3d_pad_nhwc(const float* d_in, int B, int H, int W, int C, int c_pad, void
  * (B,H+1,W+1,k_pad) with K index tap*C + c (tap = kh*3+kw, SAME zero padding; k >= 9*C and halo rows zero), so that
  * Network.conv(3,3,...) on the input image (network.py:108-132) is ONE taps=1 GEMM with K = k_pad = 32. */
 int mv3d_im2col3x3_pad(const float* d_in, int B, int H, int W, int C, int k_pad, void* d_hi, void* d_lo, void* stream);
-/* The same first layer as ONE direct kernel (inference): 3x3 SAME conv + bias + ReLU of a dense float32 (B,H,W,C<=4)
- * input (Network.conv on the image placeholder, network.py:108-132 / MV3D_test.py:51-52), fp32 FMA accumulation,
- * output rendered in `fmt` into the PAD layout (B,H+1,W+1,c_pad), halos zero.  d_w: HWIO (3,3,C,Cout), Cout % 8 == 0. */
+/* The same first layer as ONE kernel: 3x3 SAME conv + bias + ReLU of a dense float32 (B,H,W,C<=4) input (Network.conv
+ * on the image placeholder, network.py:108-132 / MV3D_test.py:51-52), output rendered in `fmt` into the PAD layout
+ * (B,H+1,W+1,c_pad), halos zero.  d_w: HWIO (3,3,C,Cout), Cout % 8 == 0.  C <= 3 with Cout == c_pad == 64 runs on the
+ * tensor cores (operand rows built in shared memory by the CTA, bf16 hi/lo 3-pass tcgen05 MMAs, TMA tensor stores:
+ * error ~2^-17 per product); other shapes use a direct fp32 FMA kernel.  MV3D_SMALL_CIN_MMA=0 forces the latter. */
 int mv3d_conv3x3_small_cin(const float* d_in, int B, int H, int W, int C, const float* d_w, const float* d_bias,
                            int Cout, int relu, void* d_out_hi, void* d_out_lo, int c_pad, int fmt, void* stream);
 /* PAD -> dense float32 (B,H,W,C) (hi+lo). */
